@@ -1,0 +1,25 @@
+/* gsi_flatten.h -- host tree -> device slab image (layout in gsi_layout.h). */
+#ifndef GSI_FLATTEN_H
+#define GSI_FLATTEN_H
+
+#include <string>
+#include <vector>
+
+#include "gsi_builder.h"
+#include "gsi_layout.h"
+
+struct gsi_flatten_params
+{
+  double cells_per_leaf = 4.0;  /* grid resolution: G*G ~ cells_per_leaf * n_leaves */
+  uint32_t grid_g = 0;          /* explicit G (0 = derive from cells_per_leaf) */
+  double delta = 3.725290298461914e-09; /* 2^-28: absolute edge margin, standardised units */
+  double tau_floor = 9.094947017729282e-13; /* 2^-40 */
+};
+
+/* za: n_fields x n_points, field-major (may be NULL: values left zero).
+ * The seeds section is left zero; it is filled on the device. */
+int gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const double *za,
+                size_t n_fields, const gsi_flatten_params &prm, std::vector<char> *image,
+                std::string *err);
+
+#endif

@@ -1,0 +1,62 @@
+/* gsi_kernels.h -- host-callable launchers of the sm_100a kernels (gsi_kernels.cu). */
+#ifndef GSI_KERNELS_H
+#define GSI_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "gsi_layout.h"
+
+#define GSI_LOCATE_THREADS 256
+
+/* device counters (unsigned[16]) */
+#define GSI_CNT_DEFERRED 0       /* u32: length of the deferred list of the current launch */
+#define GSI_CNT_OUTSIDE 1        /* u32: queries outside the cage since the last reset */
+#define GSI_CNT_DEFERRED_TOTAL 2 /* u64: deferred queries since the last reset */
+#define GSI_CNT_STEPS 4          /* u64: walk steps of accepted queries (stats launches only) */
+#define GSI_CNT_WORDS 16
+
+#define GSI_MODE_FAST 0  /* grid-seeded walk + exact replay of the deferred queries */
+#define GSI_MODE_EXACT 1 /* exact DAG replay on every query */
+
+struct gsi_launch_cfg
+{
+  int mode = GSI_MODE_FAST;
+  int stats = 0;
+  int max_steps = 256;
+  int sm_count = 148;
+  int locate_ctas_per_sm = 8;
+  unsigned *list = nullptr;     /* deferred list, list_capacity entries */
+  size_t list_capacity = 0;     /* max queries per launch in fast mode */
+  unsigned *counters = nullptr; /* GSI_CNT_WORDS words */
+};
+
+/* locate + blend nq queries given as device arrays; val is field-major with leading
+ * dimension ld (val[f*ld + q]); val and leaf_out may each be NULL */
+cudaError_t gsi_launch_eval_arrays(const gsi_view &V, const double *xq, const double *yq,
+                                   size_t nq, double *val, int *leaf_out, size_t ld,
+                                   const gsi_launch_cfg &cfg, cudaStream_t st);
+
+/* same for pixels [q_first, q_first+nq) of an nx x ny raster (x-major, pixel = i*ny + j);
+ * val / leaf_out point at pixel q_first */
+cudaError_t gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, double y0, double dy,
+                                   unsigned long long ny, size_t q_first, size_t nq, double *val,
+                                   int *leaf_out, size_t ld, const gsi_launch_cfg &cfg,
+                                   cudaStream_t st);
+
+cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, unsigned *counters,
+                                  int sm_count, cudaStream_t st);
+
+cudaError_t gsi_launch_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo,
+                                   double xhi, double ylo, double yhi, double *xq, double *yq,
+                                   int sm_count, cudaStream_t st);
+
+cudaError_t gsi_launch_checksum(const int *leaf, const double *val, size_t n,
+                                unsigned long long *out2, int sm_count, cudaStream_t st);
+
+cudaError_t gsi_launch_compare(const int *leaf_a, const int *leaf_b, const double *val_a,
+                               const double *val_b, size_t n, size_t n_val,
+                               unsigned long long *out2, int sm_count, cudaStream_t st);
+
+#endif

@@ -1,0 +1,207 @@
+/* gsl_scattered_cuda.h -- C ABI of libgsl_scattered_cuda (B200 / sm_100a).
+ *
+ * Batched scattered-data interpolation on the GPU: locate each 2-D query point in the
+ * Delaunay triangulation and blend the containing triangle's vertex values with
+ * barycentric weights.  It is a drop-in for the evaluation loop of the GSL
+ * scattered-interpolation branch,
+ *
+ *     leaf = find_leaf(tree, data, point, accel);                       (linear_simplex.c:331-350)
+ *     val  = interp_point(tree, leaf, data, response, point, accel);    (linear_simplex.c:678-711)
+ *
+ * as driven by /root/reference/interpolation/scattered_interp_example.c:158-160,171-173,
+ * 184-199, and returns exactly what that loop returns: the containing leaf as the reference's
+ * simplex_index (node id in the history DAG, linear_simplex.h:6) bit-exact -- including the
+ * reference's edge/vertex tie-breaks and its cage leaves for points outside the data hull --
+ * and the interpolated values bit-identical in binary64.
+ *
+ * Conventions follow gsl_interp2d / gsl_spline2d (interpolation/gsl_interp2d.h:37-80,
+ * interpolation/spline2d.c:30-110): opaque workspace, alloc returns NULL on failure, init
+ * returns a status, eval returns the value and eval_e a status with out-parameters, free(NULL)
+ * is a no-op.  Status codes are GSL's numeric values (err/gsl_errno.h:38-108).  The header is
+ * plain C89, has no GSL or CUDA types in any signature and can be bound over FFI (see
+ * INTEGRATION.md for the reference-side stub).
+ */
+#ifndef GSL_SCATTERED_CUDA_H
+#define GSL_SCATTERED_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes, numerically identical to err/gsl_errno.h:38-75 */
+#define GSL_SCATTERED_SUCCESS 0
+#define GSL_SCATTERED_EDOM 1     /* at least one query lies outside the cage (find_leaf would assert) */
+#define GSL_SCATTERED_EINVAL 4   /* invalid argument */
+#define GSL_SCATTERED_EFAILED 5  /* CUDA failure / inconsistent tree */
+#define GSL_SCATTERED_ENOMEM 8   /* host or device allocation failed */
+#define GSL_SCATTERED_EBADLEN 19 /* array lengths do not conform */
+
+/* init_flags, identical to SIMPLEX_TREE_* (interpolation/linear_simplex.h:109-112) */
+#define GSL_SCATTERED_DEFAULT 0
+#define GSL_SCATTERED_NOSTANDARDIZE (1 << 0)
+#define GSL_SCATTERED_ISOSCALE (1 << 1)
+
+typedef struct gsl_scattered_cuda gsl_scattered_cuda;
+
+/* Error hook with the signature of gsl_error_handler_t (err/gsl_errno.h:110-123).  Every
+ * failing call reports through it before returning its status; pass gsl_error itself to get
+ * GSL's policy (print + abort unless gsl_set_error_handler_off).  Default: none (status only).
+ * Returns the previous handler. */
+typedef void gsl_scattered_cuda_error_handler_t(const char *reason, const char *file, int line,
+                                                int gsl_errno);
+gsl_scattered_cuda_error_handler_t *
+gsl_scattered_cuda_set_error_handler(gsl_scattered_cuda_error_handler_t *handler);
+
+/* Number of usable CUDA devices (0 if none / no driver). */
+int gsl_scattered_cuda_device_count(void);
+
+/* ---- workspace --------------------------------------------------------------------------
+ * replaces simplex_tree_alloc + simplex_tree_accel_alloc (linear_simplex.c:53-106,298-307)
+ * and simplex_tree_free (linear_simplex.c:108-132). */
+gsl_scattered_cuda *gsl_scattered_cuda_alloc(size_t n_nodes, size_t n_fields);
+void gsl_scattered_cuda_free(gsl_scattered_cuda *w);
+
+/* Select the GPUs of this process that hold a replica of the triangulation (default:
+ * device 0 only).  Call before init/upload.  eval_e / eval_raster_e split their queries
+ * into one contiguous slice per device; no collective is involved. */
+int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_t ndev);
+
+/* Tuning knobs (before init/upload).  Known names: "cells_per_leaf" (grid resolution,
+ * default 4), "grid_g" (explicit grid size), "max_steps" (walk cap, default 256),
+ * "delta" (edge safety margin in standardised units, default 2^-28), "mode" (0 = fast
+ * path + exact replay of deferred queries, 1 = exact replay of every query),
+ * "stats" (1 = count walk steps), "chunk" (queries per launch), "ctas_per_sm". */
+int gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double value);
+
+/* order[] for init: what gsl_ran_shuffle(rng, shuffle, n, sizeof(size_t)) leaves in
+ * tree->shuffle for rng = gsl_rng_mt19937 seeded with `seed` (linear_simplex.c:280-281,
+ * randist/shuffle.c:69-79, rng/mt.c).  seed 0 = gsl_rng_default's default. */
+int gsl_scattered_cuda_shuffle_mt19937(unsigned long seed, size_t n, size_t order[]);
+
+/* ---- init -------------------------------------------------------------------------------
+ * replaces simplex_tree_init (linear_simplex.c:134-296) with min = max = NULL.
+ * xa, ya: node coordinates; za: n_fields x n_nodes values, field-major (field f of node i at
+ * za[f*n_nodes + i]); order: insertion order (NULL = data order, i.e. rng == NULL).  The
+ * triangulation is built on the host by the library's own restatement of the reference's
+ * incremental builder (same DAG, node for node), flattened and uploaded to every selected
+ * GPU.  Inputs are copied; nothing is borrowed after return.
+ *
+ * init == build (host only, timed separately) followed by upload (needs a GPU). */
+int gsl_scattered_cuda_init(gsl_scattered_cuda *w, const double xa[], const double ya[],
+                            const double za[], size_t n_nodes, int init_flags,
+                            const size_t order[]);
+int gsl_scattered_cuda_build(gsl_scattered_cuda *w, const double xa[], const double ya[],
+                             size_t n_nodes, int init_flags, const size_t order[]);
+int gsl_scattered_cuda_upload(gsl_scattered_cuda *w, const double za[], size_t n_fields);
+
+/* True drop-in: adopt a tree built by the reference's own simplex_tree_init.  The arrays are
+ * the flattened simplex_tree pools (linear_simplex.h:31-59): for node k, pts3[3k+i] =
+ * POINT(k,i), lnk3[3k+i] = LINK(k,i), type[k] = SIMP(k)->type; shuffle = tree->shuffle->data;
+ * shift/scale = tree->shift/scale; seed_points = tree->seed_points (3x2 row-major);
+ * data = the n_nodes x 2 gsl_matrix the tree was built on (row stride data_tda).
+ * INTEGRATION.md shows the 20-line stub that fills these from a simplex_tree*. */
+int gsl_scattered_cuda_init_from_tree(gsl_scattered_cuda *w, size_t n_simplexes,
+                                      const int pts3[], const int lnk3[], const int type[],
+                                      const size_t shuffle[], const double shift[2],
+                                      const double scale[2], const double seed_points[6],
+                                      const double data[], size_t data_tda, size_t n_nodes,
+                                      const double za[], size_t n_fields);
+
+/* ---- eval -------------------------------------------------------------------------------
+ * replaces the loop  find_leaf + n_fields x interp_point  over nq points.
+ * xq, yq: HOST arrays of nq query coordinates.  zq: n_fields x nq values, field-major, may
+ * be NULL.  leaf: nq reference simplex_index values, may be NULL.  A query outside the cage
+ * (the reference asserts there, linear_simplex.c:343-347) gets leaf -1 and NaN values and
+ * makes the call return GSL_SCATTERED_EDOM after all other queries have been evaluated. */
+int gsl_scattered_cuda_eval_e(const gsl_scattered_cuda *w, const double xq[], const double yq[],
+                              size_t nq, double zq[], int leaf[]);
+
+/* one point, field 0 (NaN outside the cage) */
+double gsl_scattered_cuda_eval(const gsl_scattered_cuda *w, double x, double y);
+
+/* The reference's raster driver (scattered_interp_example.c:176-199): pixel (i,j) is the
+ * point (x0 + dx*i, y0 + dy*j) -- two roundings each, as the reference computes them --
+ * results x-major: zq[f*nx*ny + i*ny + j], leaf[i*ny + j].  HOST outputs. */
+int gsl_scattered_cuda_eval_raster_e(const gsl_scattered_cuda *w, double x0, double dx, size_t nx,
+                                     double y0, double dy, size_t ny, double zq[], int leaf[]);
+
+/* Same two entry points on DEVICE pointers of device `dev` (must be one of the selected
+ * devices), asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the library's
+ * own stream followed by a synchronize).  ld = leading dimension of d_zq (>= nq). */
+int gsl_scattered_cuda_eval_device_e(const gsl_scattered_cuda *w, int dev, const double *d_xq,
+                                     const double *d_yq, size_t nq, double *d_zq, size_t ld,
+                                     int *d_leaf, void *stream);
+int gsl_scattered_cuda_eval_raster_device_e(const gsl_scattered_cuda *w, int dev, double x0,
+                                            double dx, size_t nx, double y0, double dy, size_t ny,
+                                            double *d_zq, int *d_leaf, void *stream);
+
+/* ---- introspection / replication / measurement helpers ------------------------------------- */
+typedef struct
+{
+  size_t n_nodes;          /* data points */
+  size_t n_fields;
+  size_t n_simplexes;      /* history-DAG nodes (tree->n_simplexes) */
+  size_t n_leaves;
+  size_t grid_g;           /* acceleration grid is grid_g x grid_g */
+  size_t slab_bytes;       /* device bytes per replica */
+  size_t n_devices;
+  double build_seconds;    /* host Delaunay build */
+  double flatten_seconds;  /* host flatten */
+  double upload_seconds;   /* H2D + device seeding + peer replication */
+  unsigned long long n_deferred; /* queries resolved by the exact replay since reset */
+  unsigned long long n_outside;  /* queries outside the cage since reset */
+  unsigned long long n_steps;    /* walk steps (only with param "stats") */
+} gsl_scattered_cuda_info;
+int gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info *info);
+int gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w);
+
+/* Copy out the host tree in the format of init_from_tree (for parity checks against the
+ * reference builder).  Any pointer may be NULL. */
+int gsl_scattered_cuda_get_tree(const gsl_scattered_cuda *w, int pts3[], int lnk3[], int type[],
+                                size_t shuffle[], double shift[2], double scale[2],
+                                double seed_points[6]);
+
+/* The device layout is one position-independent slab: replicate it to another process /
+ * GPU by copying the bytes (NCCL broadcast, peer copy) and adopting them there. */
+size_t gsl_scattered_cuda_slab_bytes(const gsl_scattered_cuda *w);
+int gsl_scattered_cuda_slab_export_device(const gsl_scattered_cuda *w, int dev, void *d_dst,
+                                          void *stream);
+int gsl_scattered_cuda_init_from_slab_device(gsl_scattered_cuda *w, const void *d_src,
+                                             size_t bytes);
+
+/* Pinned host memory for zero-staging eval_e calls. */
+void *gsl_scattered_cuda_host_alloc(size_t bytes);
+void gsl_scattered_cuda_host_free(void *p);
+
+/* Deterministic synthetic queries, generated on the device:
+ * query k of the stream `seed` is (xlo + (xhi-xlo)*u(seed,2k), ylo + (yhi-ylo)*u(seed,2k+1))
+ * with u = splitmix64-based uniform; fills k in [first, first+nq). */
+int gsl_scattered_cuda_generate_uniform_device(const gsl_scattered_cuda *w, int dev,
+                                               unsigned long long seed, unsigned long long first,
+                                               size_t nq, double xlo, double xhi, double ylo,
+                                               double yhi, double *d_xq, double *d_yq,
+                                               void *stream);
+/* same generator on the host (bit-identical) */
+void gsl_scattered_cuda_generate_uniform_host(unsigned long long seed, unsigned long long first,
+                                              size_t nq, double xlo, double xhi, double ylo,
+                                              double yhi, double xq[], double yq[]);
+
+/* out[0] = wrapping sum of leaf ids, out[1] = wrapping sum of the value bit patterns */
+int gsl_scattered_cuda_checksum_device(const gsl_scattered_cuda *w, int dev, const int *d_leaf,
+                                       const double *d_val, size_t n, unsigned long long out[2],
+                                       void *stream);
+/* out[0] = number of differing leaf ids, out[1] = number of differing value bit patterns */
+int gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, const int *d_leaf_a,
+                                      const int *d_leaf_b, const double *d_val_a,
+                                      const double *d_val_b, size_t n, size_t n_val,
+                                      unsigned long long out[2], void *stream);
+
+const char *gsl_scattered_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GSL_SCATTERED_CUDA_H */
