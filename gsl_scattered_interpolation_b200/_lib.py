@@ -23,7 +23,8 @@ class Info(ctypes.Structure):
         ("n_leaves", c_size_t), ("grid_g", c_size_t), ("slab_bytes", c_size_t),
         ("n_devices", c_size_t), ("build_seconds", c_double), ("flatten_seconds", c_double),
         ("upload_seconds", c_double), ("n_deferred", c_ulonglong), ("n_outside", c_ulonglong),
-        ("n_steps", c_ulonglong),
+        ("n_steps", c_ulonglong), ("n_kernel_launches", c_ulonglong),
+        ("locate_seconds", c_double), ("exact_seconds", c_double),
     ]
 
 

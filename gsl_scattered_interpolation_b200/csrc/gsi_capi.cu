@@ -89,6 +89,10 @@ struct replica
   unsigned long long *scratch2 = nullptr; /* 2 x u64 for checksum / compare */
   stage_buf st[2];
   size_t st_cap = 0, st_fields = 0;
+  /* profiling (param "profile"): timed event pairs around every kernel launch */
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_locate, prof_exact;
+  double locate_seconds = 0, exact_seconds = 0;
+  unsigned long long n_launches = 0;
   std::mutex mu;
 };
 
@@ -102,8 +106,9 @@ struct gsl_scattered_cuda
   std::vector<double> xa, ya;
   bool built = false, uploaded = false;
   gsi_flatten_params fprm;
-  int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8;
-  size_t chunk = (size_t) 1 << 26;
+  int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
+  size_t chunk = (size_t) 0xfffffff0u;
+  double list_fraction = 1.0 / 16;
   size_t host_chunk = (size_t) 1 << 22;
   std::vector<int> devs;
   std::vector<replica *> reps;
@@ -119,6 +124,8 @@ free_replica(replica *r)
 {
   if (!r) return;
   cudaSetDevice(r->dev);
+  for (auto &p : r->prof_locate) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto &p : r->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   if (r->slab && r->owns_slab) cudaFree(r->slab);
   if (r->list) cudaFree(r->list);
   if (r->counters) cudaFree(r->counters);
@@ -226,14 +233,35 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
   const size_t chunk = std::max<size_t>(1, std::min(w->chunk, (size_t) 0xfffffff0u));
   if (w->mode == GSI_MODE_FAST)
     {
-      const int s = ensure_list(r, std::min(chunk, nq));
+      /* deferred list: a fraction of the launch size (overflow is resolved in place) */
+      const size_t per_launch = std::min(chunk, nq);
+      const size_t want = std::max<size_t>(std::min<size_t>(per_launch, 65536),
+                                           (size_t) (w->list_fraction * (double) per_launch));
+      const int s = ensure_list(r, want);
       if (s) return s;
     }
-  const gsi_launch_cfg cfg = cfg_of(w, r);
+  gsi_launch_cfg cfg = cfg_of(w, r);
   for (size_t off = 0; off < nq; off += chunk)
     {
       const size_t n = std::min(chunk, nq - off);
       cudaError_t e;
+      if (w->profile)
+        {
+          cudaEvent_t ev[4];
+          for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ev[i]));
+          if (w->mode == GSI_MODE_FAST)
+            {
+              cfg.ev_locate0 = ev[0]; cfg.ev_locate1 = ev[1];
+              r->prof_locate.emplace_back(ev[0], ev[1]);
+            }
+          else
+            {
+              cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+            }
+          cfg.ev_exact0 = ev[2]; cfg.ev_exact1 = ev[3];
+          r->prof_exact.emplace_back(ev[2], ev[3]);
+        }
+      r->n_launches += (w->mode == GSI_MODE_FAST) ? 3 : 1;
       if (ras)
         e = gsi_launch_eval_raster(r->view, ras->x0, ras->dx, ras->y0, ras->dy, ras->ny,
                                    ras->first + off, n, d_z ? d_z + off : nullptr,
@@ -404,8 +432,8 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
   replica *r0 = w->reps[0];
   CU(cudaSetDevice(r0->dev));
   CU(cudaMemcpyAsync(r0->slab, image.data(), image.size(), cudaMemcpyHostToDevice, r0->s_k));
-  CU(gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->counters,
-                           r0->sm_count, r0->s_k));
+  CU(gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->sm_count,
+                           r0->s_k));
   CU(cudaStreamSynchronize(r0->s_k));
   for (size_t i = 1; i < w->reps.size(); i++)
     {
@@ -497,6 +525,8 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "chunk" && value >= 1) w->chunk = (size_t) value;
   else if (k == "host_chunk" && value >= 1) w->host_chunk = (size_t) value;
   else if (k == "ctas_per_sm" && value >= 1) w->ctas_per_sm = (int) value;
+  else if (k == "profile") w->profile = value != 0;
+  else if (k == "list_fraction" && value > 0 && value <= 1) w->list_fraction = value;
   else GSI_ERROR("unknown parameter or value out of range", GSL_SCATTERED_EINVAL);
   return GSL_SCATTERED_SUCCESS;
 }
@@ -729,6 +759,25 @@ gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info
       std::memcpy(&u, c + GSI_CNT_STEPS, 8);
       info->n_steps += u;
       info->n_outside += c[GSI_CNT_OUTSIDE];
+      /* fold finished profiling events into the running totals */
+      for (auto &p : r->prof_locate)
+        {
+          float ms = 0;
+          if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) r->locate_seconds += 1e-3 * ms;
+          cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+        }
+      for (auto &p : r->prof_exact)
+        {
+          float ms = 0;
+          if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) r->exact_seconds += 1e-3 * ms;
+          cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+        }
+      r->prof_locate.clear();
+      r->prof_exact.clear();
+      cudaGetLastError();
+      info->locate_seconds += r->locate_seconds;
+      info->exact_seconds += r->exact_seconds;
+      info->n_kernel_launches += r->n_launches;
     }
   return GSL_SCATTERED_SUCCESS;
 }
@@ -743,6 +792,12 @@ gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w)
       CU(cudaSetDevice(r->dev));
       CU(cudaMemsetAsync(r->counters, 0, GSI_CNT_WORDS * sizeof(unsigned), r->s_k));
       CU(cudaStreamSynchronize(r->s_k));
+      for (auto &p : r->prof_locate) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+      for (auto &p : r->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+      r->prof_locate.clear();
+      r->prof_exact.clear();
+      r->locate_seconds = r->exact_seconds = 0;
+      r->n_launches = 0;
     }
   return GSL_SCATTERED_SUCCESS;
 }

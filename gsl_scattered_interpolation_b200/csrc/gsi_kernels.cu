@@ -17,29 +17,12 @@
 #include <stdint.h>
 
 #include "gsi_core.h"
+#include "gsi_eval_core.h"
 #include "gsi_kernels.h"
 #include "gsi_layout.h"
 
 namespace
 {
-
-__device__ __forceinline__ void
-fetch_rec(gsi_rec &r, const gsi_rec *base, int idx)
-{
-  const double2 *p = reinterpret_cast<const double2 *>(base + idx);
-  const double2 a = __ldg(p);
-  const double2 b = __ldg(p + 1);
-  const double2 c = __ldg(p + 2);
-  const int4 d = __ldg(reinterpret_cast<const int4 *>(p + 3));
-  r.x0x = a.x; r.x0y = a.y;
-  r.u00 = b.x; r.u01 = b.y;
-  r.u11 = c.x; r.l10 = c.y;
-  r.lnk[0] = d.x; r.lnk[1] = d.y; r.lnk[2] = d.z;
-  r.meta = (uint32_t) d.w;
-}
-
-#define GSI_FETCH_DEV(dst, idx) fetch_rec((dst), dag, (idx))
-GSI_DEFINE_DESCEND(descend_dev, __device__ __forceinline__, const gsi_rec *, GSI_FETCH_DEV)
 
 /* ---- query sources -------------------------------------------------------------------- */
 struct src_arrays
@@ -66,100 +49,6 @@ struct src_raster
   }
 };
 
-struct src_cells /* grid-cell centres, for seeding */
-{
-  gsi_view V;
-  __device__ __forceinline__ void get(size_t q, double &qx, double &qy) const
-  {
-    const unsigned g = (unsigned) V.grid_g;
-    const unsigned iy = (unsigned) (q / g), ix = (unsigned) (q - (size_t) iy * g);
-    const double u = V.u0 + ((double) ix + 0.5) / V.inv_du;
-    const double v = V.v0 + ((double) iy + 0.5) / V.inv_dv;
-    qx = V.xf.cx + u / V.xf.sx;
-    qy = V.xf.cy + v / V.xf.sy;
-  }
-};
-
-/* ---- blend + store (interp_point, linear_simplex.c:689-710), F fields, field-major out --- */
-__device__ __forceinline__ void
-blend_store(const gsi_view &V, const int4 ax, double c0, double c1, double *val, size_t ld,
-            size_t q)
-{
-  const int F = V.n_fields;
-  const int ha = ax.x >= 0, hb = ax.y >= 0, hx = ax.z >= 0;
-  const double *za = V.z + (size_t) (ha ? ax.x : 0) * F;
-  const double *zb = V.z + (size_t) (hb ? ax.y : 0) * F;
-  const double *zx = V.z + (size_t) (hx ? ax.z : 0) * F;
-  if (F == 1)
-    {
-      const double a = ha ? __ldg(za) : 0.0, b = hb ? __ldg(zb) : 0.0, x = hx ? __ldg(zx) : 0.0;
-      __stcs(val + q, gsi_blend(c0, c1, ha, a, hb, b, hx, x));
-      return;
-    }
-  if ((F & 1) == 0)
-    {
-      const double2 *pa = reinterpret_cast<const double2 *>(za);
-      const double2 *pb = reinterpret_cast<const double2 *>(zb);
-      const double2 *px = reinterpret_cast<const double2 *>(zx);
-#pragma unroll 4
-      for (int f = 0; f < F; f += 2)
-        {
-          double2 a = make_double2(0, 0), b = a, x = a;
-          if (ha) a = __ldg(pa + (f >> 1));
-          if (hb) b = __ldg(pb + (f >> 1));
-          if (hx) x = __ldg(px + (f >> 1));
-          __stcs(val + (size_t) f * ld + q, gsi_blend(c0, c1, ha, a.x, hb, b.x, hx, x.x));
-          __stcs(val + (size_t) (f + 1) * ld + q, gsi_blend(c0, c1, ha, a.y, hb, b.y, hx, x.y));
-        }
-      return;
-    }
-  for (int f = 0; f < F; f++)
-    {
-      const double a = ha ? __ldg(za + f) : 0.0, b = hb ? __ldg(zb + f) : 0.0,
-                   x = hx ? __ldg(zx + f) : 0.0;
-      __stcs(val + (size_t) f * ld + q, gsi_blend(c0, c1, ha, a, hb, b, hx, x));
-    }
-}
-
-__device__ __forceinline__ void
-store_nan(const gsi_view &V, double *val, size_t ld, size_t q)
-{
-  for (int f = 0; f < V.n_fields; f++) val[(size_t) f * ld + q] = CUDART_NAN;
-}
-
-/* ---- exact replay of one query ----------------------------------------------------------- */
-template <bool WANT_SLOT>
-__device__ __forceinline__ int
-exact_one(const gsi_view &V, double qx, double qy, double *val, int *leaf_out, size_t ld,
-          size_t q, unsigned *counters)
-{
-  double c0 = 0, c1 = 0;
-  int last = -1;
-  gsi_rec lr;
-  const int node = descend_dev(V.dag, &V.xf, qx, qy, &c0, &c1, &last, &lr);
-  if (node < 0)
-    {
-      if (WANT_SLOT) return 0;
-      if (leaf_out) leaf_out[q] = -1;
-      if (val) store_nan(V, val, ld, q);
-      atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
-      return -1;
-    }
-  const int slot = lr.lnk[0];
-  if (WANT_SLOT) return slot;
-  /* interp_point recomputes the leaf's coordinates unless the leaf is singular, in which
-     case accel->coords keeps whatever the descent left there (linear_simplex.c:641-642,687) */
-  if (!(lr.meta & GSI_META_SINGULAR) && last != node)
-    gsi_solve(&V.xf, &lr, (int) (lr.meta & GSI_META_SWAP), qx, qy, &c0, &c1);
-  if (leaf_out) leaf_out[q] = node;
-  if (val)
-    {
-      const int4 ax = __ldg(reinterpret_cast<const int4 *>(V.aux) + slot);
-      blend_store(V, ax, c0, c1, val, ld, q);
-    }
-  return slot;
-}
-
 /* exact replay on every query of a source */
 template <class SRC>
 __global__ void __launch_bounds__(128)
@@ -171,39 +60,42 @@ k_exact_all(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_o
     {
       double qx, qy;
       src.get(q, qx, qy);
-      exact_one<false>(V, qx, qy, val, leaf_out, ld, q, counters);
+      if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
+        atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
     }
 }
 
 /* exact replay on the deferred list written by k_locate */
 template <class SRC>
 __global__ void __launch_bounds__(128)
-k_exact_list(const gsi_view V, const SRC src, const unsigned *list, double *val, int *leaf_out,
-             size_t ld, unsigned *counters)
+k_exact_list(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, double *val,
+             int *leaf_out, size_t ld, unsigned *counters)
 {
-  const unsigned count = counters[GSI_CNT_DEFERRED];
+  const unsigned count = min(counters[GSI_CNT_DEFERRED], list_cap);
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride)
     {
       const size_t q = list[t];
       double qx, qy;
       src.get(q, qx, qy);
-      exact_one<false>(V, qx, qy, val, leaf_out, ld, q, counters);
+      if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
+        atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
     }
 }
 
-/* seeds[cell] = leaf slot containing the cell centre */
+/* seeds[cell] = leaf slot containing the cell centre (exact replay of the centre) */
 __global__ void __launch_bounds__(128)
-k_seed_cells(const gsi_view V, int32_t *seeds, unsigned *counters)
+k_seed_cells(const gsi_view V, int32_t *seeds)
 {
-  const src_cells src{V};
-  const size_t ncell = (size_t) V.grid_g * V.grid_g;
+  const unsigned g = (unsigned) V.grid_g;
+  const size_t ncell = (size_t) g * g;
   const size_t stride = (size_t) gridDim.x * blockDim.x;
   for (size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += stride)
     {
       double qx, qy;
-      src.get(q, qx, qy);
-      seeds[q] = exact_one<true>(V, qx, qy, nullptr, nullptr, 0, q, counters);
+      gsi_cell_centre(&V, q, &qx, &qy);
+      const int slot = gsi_exact_one(&V, qx, qy, nullptr, nullptr, 0, q);
+      seeds[q] = slot < 0 ? 0 : slot;
     }
 }
 
@@ -211,7 +103,7 @@ k_seed_cells(const gsi_view V, int32_t *seeds, unsigned *counters)
 template <class SRC, bool STATS>
 __global__ void __launch_bounds__(GSI_LOCATE_THREADS)
 k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out, size_t ld,
-         unsigned *list, unsigned *counters, int max_steps)
+         unsigned *list, unsigned list_cap, unsigned *counters, int max_steps)
 {
   const size_t stride = (size_t) gridDim.x * blockDim.x;
   const unsigned lane = threadIdx.x & 31u;
@@ -220,63 +112,40 @@ k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out,
        base += stride)
     {
       const size_t q = base + lane;
-      const bool live = q < nq;
       bool defer = false;
-      if (live)
+      if (q < nq)
         {
           double qx, qy;
+          int steps;
           src.get(q, qx, qy);
-          /* grid cell in standardised coordinates (a hint only: no exactness needed) */
-          const double u = (qx - V.xf.cx) * V.xf.sx, v = (qy - V.xf.cy) * V.xf.sy;
-          const double gmax = (double) (V.grid_g - 1);
-          const double fx = fmin(fmax((u - V.u0) * V.inv_du, 0.0), gmax);
-          const double fy = fmin(fmax((v - V.v0) * V.inv_dv, 0.0), gmax);
-          /* fmin/fmax drop NaN, so non-finite queries get cell 0 and are deferred below */
-          int slot = __ldg(V.seeds + (size_t) __double2int_rd(fy) * V.grid_g + __double2int_rd(fx));
-          defer = true;
-          if (isfinite(qx) && isfinite(qy))
-            {
-              for (int step = 0; step < max_steps; step++)
-                {
-                  gsi_rec r;
-                  fetch_rec(r, V.leaf, slot);
-                  const double tau = (double) __uint_as_float(r.meta & 0x7fffffffu);
-                  double c0, c1;
-                  gsi_solve(&V.xf, &r, (int) (r.meta >> 31), qx, qy, &c0, &c1);
-                  const double c2 = __dsub_rn(1.0, __dadd_rn(__dadd_rn(0.0, c0), c1));
-                  if ((c0 >= tau) && (c1 >= tau) && (c2 >= tau))
-                    {
-                      /* strictly inside, `delta` away from every edge: the reference
-                         descent ends in this leaf */
-                      const int4 ax = __ldg(reinterpret_cast<const int4 *>(V.aux) + slot);
-                      if (leaf_out) __stcs(leaf_out + q, ax.w);
-                      if (val) blend_store(V, ax, c0, c1, val, ld, q);
-                      defer = false;
-                      if (STATS)
-                        atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS),
-                                  (unsigned long long) step + 1ull);
-                      break;
-                    }
-                  int e = 0;
-                  double m = c0;
-                  if (c1 < m) { m = c1; e = 1; }
-                  if (c2 < m) { m = c2; e = 2; }
-                  if (!(m <= -tau)) break; /* within the margin of an edge (or NaN): defer */
-                  const int nb = GSI_LNK(r, e);
-                  if (nb < 0) break;       /* beyond the cage hull: exact path decides */
-                  slot = nb;
-                }
-            }
+          defer = !gsi_locate_one(&V, qx, qy, max_steps, val, leaf_out, ld, q, &steps);
+          if (STATS && !defer)
+            atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS),
+                      (unsigned long long) steps);
         }
       /* warp-aggregated append to the deferred list */
       const unsigned mask = __ballot_sync(0xffffffffu, defer);
       if (mask)
         {
+          const int leader = __ffs(mask) - 1;
           unsigned pos = 0;
-          if (lane == (unsigned) (__ffs(mask) - 1))
+          if (lane == (unsigned) leader)
             pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(mask));
-          pos = __shfl_sync(0xffffffffu, pos, __ffs(mask) - 1);
-          if (defer) list[pos + __popc(mask & ((1u << lane) - 1u))] = (unsigned) q;
+          pos = __shfl_sync(0xffffffffu, pos, leader);
+          if (defer)
+            {
+              const unsigned slot = pos + __popc(mask & ((1u << lane) - 1u));
+              if (slot < list_cap)
+                list[slot] = (unsigned) q;
+              else
+                {
+                  /* list full (far more deferred queries than budgeted): resolve in place */
+                  double qx, qy;
+                  src.get(q, qx, qy);
+                  if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
+                    atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+                }
+            }
         }
     }
 }
@@ -363,26 +232,34 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
             const gsi_launch_cfg &cfg, cudaStream_t st)
 {
   if (nq == 0) return cudaSuccess;
-  if (nq > cfg.list_capacity && cfg.mode != GSI_MODE_EXACT) return cudaErrorInvalidValue;
+  if (nq > 0xfffffff0ull) return cudaErrorInvalidValue; /* list entries are 32-bit */
+  const unsigned list_cap = (unsigned) (cfg.list_capacity < 0xfffffff0ull ? cfg.list_capacity : 0xfffffff0ull);
   if (cfg.mode == GSI_MODE_EXACT)
     {
+      if (cfg.ev_exact0) cudaEventRecord(cfg.ev_exact0, st);
       k_exact_all<SRC><<<grid_for(nq, 128, cfg.sm_count, 16), 128, 0, st>>>(
           V, src, nq, val, leaf_out, ld, cfg.counters);
+      if (cfg.ev_exact1) cudaEventRecord(cfg.ev_exact1, st);
       return cudaGetLastError();
     }
   cudaError_t e = cudaMemsetAsync(cfg.counters + GSI_CNT_DEFERRED, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   const int g1 = grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm);
+  if (cfg.ev_locate0) cudaEventRecord(cfg.ev_locate0, st);
   if (cfg.stats)
     k_locate<SRC, true><<<g1, GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list,
-                                                          cfg.counters, cfg.max_steps);
+                                                          list_cap, cfg.counters, cfg.max_steps);
   else
     k_locate<SRC, false><<<g1, GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld,
-                                                           cfg.list, cfg.counters, cfg.max_steps);
+                                                           cfg.list, list_cap, cfg.counters,
+                                                           cfg.max_steps);
+  if (cfg.ev_locate1) cudaEventRecord(cfg.ev_locate1, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, cfg.list, val, leaf_out, ld,
+  if (cfg.ev_exact0) cudaEventRecord(cfg.ev_exact0, st);
+  k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld,
                                                       cfg.counters);
+  if (cfg.ev_exact1) cudaEventRecord(cfg.ev_exact1, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   k_accumulate_deferred<<<1, 1, 0, st>>>(cfg.counters);
@@ -409,11 +286,10 @@ gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, double y0, doubl
 }
 
 cudaError_t
-gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, unsigned *counters, int sm_count,
-                      cudaStream_t st)
+gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count, cudaStream_t st)
 {
   const size_t ncell = (size_t) V.grid_g * V.grid_g;
-  k_seed_cells<<<grid_for(ncell, 128, sm_count, 16), 128, 0, st>>>(V, seeds, counters);
+  k_seed_cells<<<grid_for(ncell, 128, sm_count, 16), 128, 0, st>>>(V, seeds);
   return cudaGetLastError();
 }
 

@@ -28,8 +28,10 @@ struct gsi_launch_cfg
   int sm_count = 148;
   int locate_ctas_per_sm = 8;
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
-  size_t list_capacity = 0;     /* max queries per launch in fast mode */
+  size_t list_capacity = 0;     /* deferred-list entries; overflow is resolved in place */
   unsigned *counters = nullptr; /* GSI_CNT_WORDS words */
+  /* optional profiling events recorded around the two kernels of a launch */
+  cudaEvent_t ev_locate0 = nullptr, ev_locate1 = nullptr, ev_exact0 = nullptr, ev_exact1 = nullptr;
 };
 
 /* locate + blend nq queries given as device arrays; val is field-major with leading
@@ -45,8 +47,8 @@ cudaError_t gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, doub
                                    int *leaf_out, size_t ld, const gsi_launch_cfg &cfg,
                                    cudaStream_t st);
 
-cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, unsigned *counters,
-                                  int sm_count, cudaStream_t st);
+cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count,
+                                  cudaStream_t st);
 
 cudaError_t gsi_launch_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo,
                                    double xhi, double ylo, double yhi, double *xq, double *yq,

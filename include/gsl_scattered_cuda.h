@@ -72,7 +72,9 @@ int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_
  * default 4), "grid_g" (explicit grid size), "max_steps" (walk cap, default 256),
  * "delta" (edge safety margin in standardised units, default 2^-28), "mode" (0 = fast
  * path + exact replay of deferred queries, 1 = exact replay of every query),
- * "stats" (1 = count walk steps), "chunk" (queries per launch), "ctas_per_sm". */
+ * "stats" (1 = count walk steps), "profile" (1 = time every kernel launch with CUDA events on
+ * its own stream), "chunk" (queries per launch), "host_chunk" (queries per pipeline stage
+ * of eval_e), "list_fraction" (deferred-list size / launch size), "ctas_per_sm". */
 int gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double value);
 
 /* order[] for init: what gsl_ran_shuffle(rng, shuffle, n, sizeof(size_t)) leaves in
@@ -153,6 +155,9 @@ typedef struct
   unsigned long long n_deferred; /* queries resolved by the exact replay since reset */
   unsigned long long n_outside;  /* queries outside the cage since reset */
   unsigned long long n_steps;    /* walk steps (only with param "stats") */
+  unsigned long long n_kernel_launches; /* eval kernels launched since reset */
+  double locate_seconds;   /* device time in the fast-path kernel (only with param "profile") */
+  double exact_seconds;    /* device time in the exact-replay kernel (only with param "profile") */
 } gsl_scattered_cuda_info;
 int gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info *info);
 int gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w);

@@ -1,0 +1,111 @@
+/* tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Runs the per-query logic of the CUDA kernels (csrc/gsi_eval_core.h, the same header the
+ * kernels are compiled from) on the host, over a slab image produced by the library's own
+ * builder + flatten code.  It exists so that the CPU test-suite (-m "not gpu") can check
+ * the kernel LOGIC (exact DAG replay, walk, safety-margin acceptance, deferred list,
+ * seeding) against the reference before a GPU is available.  It is not linked into
+ * libgsl_scattered_cuda.so and is not an evaluation fallback.
+ */
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gsi_builder.h"
+#include "gsi_eval_core.h"
+#include "gsi_flatten.h"
+
+struct hostsim
+{
+  std::vector<char> image;
+  gsi_slab_header hdr;
+  gsi_view view;
+};
+
+extern "C" {
+
+hostsim *
+hostsim_create(const double *xa, const double *ya, const double *za, size_t n, size_t n_fields,
+               int flags, const size_t *order, double cells_per_leaf, double delta)
+{
+  hostsim *h = new hostsim();
+  gsi_host_tree tree;
+  std::string err;
+  std::vector<int64_t> ord;
+  if (order)
+    {
+      ord.resize(n);
+      for (size_t i = 0; i < n; i++) ord[i] = (int64_t) order[i];
+    }
+  if (gsi_build_tree(xa, ya, n, flags, order ? ord.data() : nullptr, &tree, &err))
+    {
+      delete h;
+      return nullptr;
+    }
+  gsi_flatten_params prm;
+  if (cells_per_leaf > 0) prm.cells_per_leaf = cells_per_leaf;
+  if (delta > 0) prm.delta = delta;
+  if (gsi_flatten(tree, xa, ya, za, n_fields, prm, &h->image, &err))
+    {
+      delete h;
+      return nullptr;
+    }
+  std::memcpy(&h->hdr, h->image.data(), sizeof h->hdr);
+  h->view = gsi_view_of(h->image.data(), &h->hdr);
+  /* what k_seed_cells does on the device */
+  int32_t *seeds = (int32_t *) (h->image.data() + h->hdr.off_seeds);
+  const size_t ncell = (size_t) h->hdr.grid_g * h->hdr.grid_g;
+  for (size_t c = 0; c < ncell; c++)
+    {
+      double qx, qy;
+      gsi_cell_centre(&h->view, c, &qx, &qy);
+      const int slot = gsi_exact_one(&h->view, qx, qy, nullptr, nullptr, 0, c);
+      seeds[c] = slot < 0 ? 0 : slot;
+    }
+  return h;
+}
+
+void
+hostsim_free(hostsim *h)
+{
+  delete h;
+}
+
+size_t hostsim_n_leaves(const hostsim *h) { return (size_t) h->hdr.n_leaves; }
+size_t hostsim_grid_g(const hostsim *h) { return (size_t) h->hdr.grid_g; }
+
+/* leaf vertex rows (original data row ids, -1 = cage) for test-input generation */
+void
+hostsim_leaf_aux(const hostsim *h, int32_t *aux4)
+{
+  std::memcpy(aux4, h->view.aux, (size_t) h->hdr.n_leaves * 4 * sizeof(int32_t));
+}
+
+/* mode 0: k_locate + k_exact_list protocol; mode 1: k_exact_all.
+ * stats[0] = deferred, stats[1] = walk steps of accepted queries, stats[2] = outside cage */
+int
+hostsim_eval(const hostsim *h, const double *xq, const double *yq, size_t nq, double *zq, int *leaf,
+             int mode, int max_steps, long long stats[3])
+{
+  stats[0] = stats[1] = stats[2] = 0;
+  std::vector<size_t> deferred;
+  for (size_t q = 0; q < nq; q++)
+    {
+      if (mode == 1)
+        {
+          if (gsi_exact_one(&h->view, xq[q], yq[q], zq, leaf, nq, q) < 0) stats[2]++;
+          continue;
+        }
+      int steps = 0;
+      if (gsi_locate_one(&h->view, xq[q], yq[q], max_steps, zq, leaf, nq, q, &steps))
+        stats[1] += steps;
+      else
+        deferred.push_back(q);
+    }
+  for (size_t q : deferred)
+    if (gsi_exact_one(&h->view, xq[q], yq[q], zq, leaf, nq, q) < 0) stats[2]++;
+  stats[0] = (long long) deferred.size();
+  return 0;
+}
+}

@@ -1,0 +1,60 @@
+"""ctypes wrapper of tests/hostsim/libhostsim.so (kernel-logic simulator, tests only)."""
+import ctypes
+import os
+from ctypes import c_double, c_int, c_size_t, c_void_p
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_H = None
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def lib():
+    global _H
+    if _H is None:
+        H = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
+        H.hostsim_create.restype = c_void_p
+        H.hostsim_create.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_void_p,
+                                     c_double, c_double]
+        H.hostsim_free.argtypes = [c_void_p]
+        H.hostsim_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int,
+                                   c_int, c_void_p]
+        H.hostsim_n_leaves.restype = c_size_t
+        H.hostsim_n_leaves.argtypes = [c_void_p]
+        H.hostsim_grid_g.restype = c_size_t
+        H.hostsim_grid_g.argtypes = [c_void_p]
+        _H = H
+    return _H
+
+
+class HostSim:
+    def __init__(self, xa, ya, za, flags=0, order=None, cells_per_leaf=0.0, delta=0.0):
+        self.H = lib()
+        xa = np.ascontiguousarray(xa, dtype=np.float64)
+        ya = np.ascontiguousarray(ya, dtype=np.float64)
+        za = np.ascontiguousarray(np.atleast_2d(za), dtype=np.float64)
+        self.F = za.shape[0]
+        order = None if order is None else np.ascontiguousarray(order, dtype=np.uint64)
+        self.h = self.H.hostsim_create(_p(xa), _p(ya), _p(za), xa.size, self.F, flags, _p(order),
+                                       cells_per_leaf, delta)
+        if not self.h:
+            raise RuntimeError("hostsim_create failed")
+
+    def close(self):
+        if self.h:
+            self.H.hostsim_free(self.h)
+            self.h = None
+
+    def eval(self, xq, yq, mode=0, max_steps=256):
+        xq = np.ascontiguousarray(xq, dtype=np.float64)
+        yq = np.ascontiguousarray(yq, dtype=np.float64)
+        nq = xq.size
+        zq = np.zeros((self.F, nq))
+        leaf = np.zeros(nq, dtype=np.int32)
+        st = (ctypes.c_longlong * 3)()
+        self.H.hostsim_eval(self.h, _p(xq), _p(yq), nq, _p(zq), _p(leaf), mode, max_steps, st)
+        return leaf, zq, dict(deferred=st[0], steps=st[1], outside=st[2])

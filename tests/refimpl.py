@@ -131,3 +131,70 @@ class RefTree:
 
     def check(self):
         return self.L.ref_check(self.h)
+
+
+# ---- the plain-C restatement (oracle/simplex_oracle.c) -------------------------------------
+_PORT = None
+
+
+def port_lib():
+    global _PORT
+    if _PORT is None:
+        L = ctypes.CDLL(PORT_SO)
+        L.so_tree_create.restype = c_void_p
+        L.so_tree_create.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, ctypes.c_size_t, c_int]
+        L.so_tree_free.argtypes = [c_void_p]
+        L.so_eval.restype = c_long
+        L.so_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]
+        L.so_eval_stats.restype = c_long
+        L.so_eval_stats.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p]
+        _PORT = L
+    return _PORT
+
+
+class PortTree:
+    """The oracle port evaluated on flattened tree arrays (dict as returned by
+    RefTree.export() / ScatteredCuda.get_tree())."""
+
+    def __init__(self, tree, xa, ya):
+        self.L = port_lib()
+        xa = np.ascontiguousarray(xa, dtype=np.float64)
+        ya = np.ascontiguousarray(ya, dtype=np.float64)
+        self.n = xa.size
+        data = np.ascontiguousarray(np.stack([xa, ya], axis=1)) if self.n else np.zeros((1, 2))
+        a = {k: np.ascontiguousarray(v) for k, v in tree.items()}
+        self.h = self.L.so_tree_create(a["type"].size, _p(a["pts3"].astype(np.int32)),
+                                       _p(a["lnk3"].astype(np.int32)), _p(a["type"].astype(np.int32)),
+                                       _p(a["shuffle"].astype(np.uint64)), _p(a["shift"]), _p(a["scale"]),
+                                       _p(a["seed_points"]), _p(data), 2, self.n)
+
+    def close(self):
+        if self.h:
+            self.L.so_tree_free(self.h)
+            self.h = None
+
+    def eval(self, xq, yq, za):
+        xq = np.ascontiguousarray(xq, dtype=np.float64)
+        yq = np.ascontiguousarray(yq, dtype=np.float64)
+        za = np.ascontiguousarray(np.atleast_2d(za), dtype=np.float64)
+        F, nq = za.shape[0], xq.size
+        leaf = np.empty(nq, dtype=np.int32)
+        val = np.empty((F, nq), dtype=np.float64)
+        out = self.L.so_eval(self.h, _p(xq), _p(yq), nq, _p(za), F, _p(leaf), _p(val))
+        return leaf, val, int(out)
+
+    def stats(self, xq, yq):
+        xq = np.ascontiguousarray(xq, dtype=np.float64)
+        yq = np.ascontiguousarray(yq, dtype=np.float64)
+        depth = np.empty(xq.size, dtype=np.int32)
+        tests = np.empty(xq.size, dtype=np.int32)
+        self.L.so_eval_stats(self.h, _p(xq), _p(yq), xq.size, _p(depth), _p(tests))
+        return depth, tests
+
+
+def same_bits(a, b):
+    """bit-identical float arrays (NaN == NaN)"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    return a.shape == b.shape and bool(((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))).all())

@@ -1,0 +1,343 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the golden vectors
+frozen from the reference, against the oracle (port and, where present, the real reference
+in oracle/_ref), and -- at full size -- through size-independent properties (fast path ==
+exact DAG replay on 100 % of the queries, linear precision, host API == device API).
+Bar: leaf ids bit-exact, values bit-identical (stricter than the 1e-12 relative of
+BASELINE.json's north_star)."""
+import numpy as np
+import pytest
+
+import gsl_scattered_interpolation_b200 as g
+import refimpl
+from gsl_scattered_interpolation_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12   # north_star tolerance; the assertions below demand bit-identity instead
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def make(xa, ya, za, flags=g.DEFAULT, order=None, **params):
+    za = np.atleast_2d(za)
+    w = g.ScatteredCuda(len(xa), za.shape[0])
+    for k, v in params.items():
+        w.set_param(k, v)
+    w.init(xa, ya, za, flags, order)
+    return w
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_weather_golden(golden, mode):
+    wd = golden["weather"]
+    w = make(wd[:, 0], wd[:, 1], wd[:, 2], g.DEFAULT, g.shuffle_mt19937(0, 50), mode=mode)
+    q = golden["weatherB_q"]
+    st, zq, leaf = w.eval_e(q[:, 0], q[:, 1])
+    assert st == g.EDOM                                   # (1e6, 0) is outside the cage
+    assert np.array_equal(leaf, golden["weatherB_leaf"])
+    assert refimpl.same_bits(zq, golden["weatherB_val"])
+    assert w.eval(-88.0, 41.0) == 274.08608080148747
+    assert np.isnan(w.eval(1e6, 0.0))
+    x0, dx, nx, y0, dy, ny = golden["weatherB_raster_spec"]
+    st, rz, rl = w.eval_raster_e(x0, dx, int(nx), y0, dy, int(ny))
+    assert st == g.SUCCESS
+    assert np.array_equal(rl, golden["weatherB_raster_leaf"])
+    assert refimpl.same_bits(rz, golden["weatherB_raster_val"])
+    w.free()
+
+
+def test_weather_tree_a_nostandardize(golden):
+    wd = golden["weather"]
+    w = make(wd[:, 0], wd[:, 1], wd[:, 2], g.NOSTANDARDIZE, None)
+    q = golden["weatherB_q"][:8]
+    st, zq, leaf = w.eval_e(q[:, 0], q[:, 1])
+    assert np.array_equal(leaf, golden["weatherA_leaf"]) and refimpl.same_bits(zq, golden["weatherA_val"])
+    w.free()
+
+
+def test_trivial_empty_and_single_node(golden):
+    """scattered_interp_example.c:44-77: empty cage interpolates to 0; one node, then locate"""
+    w = make(np.zeros(0), np.zeros(0), np.zeros((1, 0)), g.NOSTANDARDIZE, None)
+    st, zq, leaf = w.eval_e(np.array([-88.0]), np.array([41.0]))
+    assert st == g.SUCCESS and leaf[0] == 0 and zq[0, 0] == 0.0
+    w.free()
+    w = make(np.array([-88.0]), np.array([41.0]), np.array([[5.0]]), g.NOSTANDARDIZE, None)
+    st, zq, leaf = w.eval_e(np.array([-89.0]), np.array([41.0]))
+    assert leaf[0] == golden["trivial_second_leaf"][0]
+    assert refimpl.same_bits(zq, golden["trivial_second_val"])
+    st, zq, leaf = w.eval_e(np.zeros(0), np.zeros(0))      # empty batch
+    assert st == g.SUCCESS and leaf.size == 0
+    w.free()
+
+
+@pytest.mark.parametrize("mode,cpl", [(0, 4.0), (0, 0.25), (0, 32.0), (1, 4.0)])
+def test_config1_golden(golden, mode, cpl):
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
+             mode=mode, cells_per_leaf=cpl)
+    xq, yq = synth.uniform_queries(10000)
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert st == g.SUCCESS
+    assert np.array_equal(leaf, golden["cfg1_leaf"])
+    assert refimpl.same_bits(zq, golden["cfg1_val"])
+    x0, dx, nx, y0, dy, ny = golden["cfg1_raster_spec"]
+    st, rz, rl = w.eval_raster_e(x0, dx, int(nx), y0, dy, int(ny))
+    assert np.array_equal(rl, golden["cfg1_raster_leaf"]) and refimpl.same_bits(rz, golden["cfg1_raster_val"])
+    info = w.info()
+    if mode == 0:
+        assert info["n_deferred"] < 0.02 * 20000           # the fast path is the common path
+    w.free()
+
+
+def test_config1_isoscale_golden(golden):
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa * 3.0, ya, synth.values(1000, 1), g.ISOSCALE, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000))
+    xq, yq = synth.uniform_queries(10000)
+    st, zq, leaf = w.eval_e(xq * 3.0, yq)
+    assert np.array_equal(leaf, golden["cfg1_iso_leaf"]) and refimpl.same_bits(zq, golden["cfg1_iso_val"])
+    w.free()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_config3_mixed_golden(golden, mode):
+    n = 3000
+    xa, ya = synth.clustered_nodes(n)
+    w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), mode=mode)
+    xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert st == g.SUCCESS
+    assert np.array_equal(leaf, golden["cfg3_leaf"])
+    assert refimpl.same_bits(zq, golden["cfg3_val"])
+    w.free()
+
+
+def test_tiny_deferred_list_overflow_and_walk_cap(golden):
+    """a 1-step walk cap defers most queries; a tiny list forces the in-place resolution"""
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
+             cells_per_leaf=0.05, max_steps=1, list_fraction=1e-4)
+    xq, yq = synth.uniform_queries(10000)
+    xq, yq = np.tile(xq, 20), np.tile(yq, 20)              # 2e5 queries, list capacity 65536
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert np.array_equal(leaf, np.tile(golden["cfg1_leaf"], 20))
+    assert refimpl.same_bits(zq, np.tile(golden["cfg1_val"], (1, 20)))
+    assert w.info()["n_deferred"] > 65536
+    w.free()
+
+
+def test_nonfinite_queries_follow_the_reference(golden):
+    xa, ya = synth.uniform_nodes(1000)
+    za = synth.values(1000, 1)
+    w = make(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000))
+    port = refimpl.PortTree({k: golden["cfg1_" + k] for k in
+                             ("pts3", "lnk3", "type", "shuffle", "shift", "scale", "seed_points")}, xa, ya)
+    bx = np.array([np.nan, np.inf, -np.inf, 0.5, 1e300])
+    by = np.array([0.5, 0.5, 0.5, np.nan, 0.5])
+    st, zq, leaf = w.eval_e(bx, by)
+    pl, pv, _ = port.eval(bx, by, za)
+    assert np.array_equal(leaf, pl) and refimpl.same_bits(zq, pv)
+    w.free()
+
+
+def test_degenerate_grid_nodes_vs_port():
+    """gridded_test(2,2)-style cocircular nodes, queries exactly on vertices / edges / centres"""
+    xa, ya = (np.arange(100) % 10).astype(float), (np.arange(100) // 10).astype(float)
+    za = synth.values(100, 2)
+    w = make(xa, ya, za, g.NOSTANDARDIZE, None)
+    tree = w.get_tree(w.n_simplexes(), 100)
+    rng = np.random.default_rng(3)
+    xq = np.concatenate([xa, xa + 0.5, rng.uniform(-2, 11, 3000), xa, xa + 0.5])
+    yq = np.concatenate([ya, ya, rng.uniform(-2, 11, 3000), ya + 0.5, ya + 0.5])
+    st, zq, leaf = w.eval_e(xq, yq)
+    port = refimpl.PortTree(tree, xa, ya)
+    pl, pv, _ = port.eval(xq, yq, za)
+    assert np.array_equal(leaf, pl) and refimpl.same_bits(zq, pv)
+    w.free()
+
+
+def test_config2_scale_vs_oracle():
+    """10^5 uniform nodes, 10^6 queries against the oracle (real reference on all cores when
+    oracle/_ref is present, else the port), then 10^7 device-generated queries: fast path vs
+    exact replay on 100 % of them."""
+    torch = _torch()
+    n = 100000
+    xa, ya = synth.uniform_nodes(n)
+    za = synth.values(n, 1)
+    order = g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
+    w = make(xa, ya, za, g.DEFAULT, order, stats=1)
+    nq = 1000000
+    xq, yq = synth.uniform_queries(nq)
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert st == g.SUCCESS
+    leaf_host_api = leaf.copy()
+    tree = w.get_tree(w.n_simplexes(), n)
+    if refimpl.have_ref():
+        rt = refimpl.RefTree(xa, ya, g.DEFAULT, synth.SEED_SHUFFLE)
+        assert rt.n_simplexes == tree["type"].size
+        import os
+        rl, rv, _ = rt.eval(xq, yq, za, nproc=max(1, min(32, os.cpu_count() or 1)))
+        rt.close()
+    else:
+        sub = slice(0, 200000)
+        port = refimpl.PortTree(tree, xa, ya)
+        rl, rv, _ = port.eval(xq[sub], yq[sub], za)
+        leaf, zq = leaf[sub], zq[:, sub]
+    assert np.array_equal(leaf, rl)
+    assert refimpl.same_bits(zq, rv)
+    info = w.info()
+    assert info["n_deferred"] < 1e-3 * nq
+    # device API, 10^7 queries generated on the device
+    nq = 10_000_000
+    dev = torch.device("cuda:0")
+    dx = torch.empty(nq, dtype=torch.float64, device=dev)
+    dy = torch.empty(nq, dtype=torch.float64, device=dev)
+    w.generate_uniform_device(0, synth.SEED_QUERIES, 0, nq, 0.0, 1.0, 0.0, 1.0, dx.data_ptr(), dy.data_ptr())
+    hx, hy = synth.uniform_queries(4096)
+    assert np.array_equal(dx[:4096].cpu().numpy(), hx) and np.array_equal(dy[:4096].cpu().numpy(), hy)
+    za_d = torch.empty(nq, dtype=torch.float64, device=dev)
+    la_d = torch.empty(nq, dtype=torch.int32, device=dev)
+    zb_d = torch.empty(nq, dtype=torch.float64, device=dev)
+    lb_d = torch.empty(nq, dtype=torch.int32, device=dev)
+    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, za_d.data_ptr(), nq, la_d.data_ptr()) == 0
+    w.set_param("mode", 1)
+    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, zb_d.data_ptr(), nq, lb_d.data_ptr()) == 0
+    w.set_param("mode", 0)
+    bad_leaf, bad_val = w.compare_device(0, la_d.data_ptr(), lb_d.data_ptr(), za_d.data_ptr(),
+                                         zb_d.data_ptr(), nq, nq)
+    assert bad_leaf == 0 and bad_val == 0
+    # host API (eval_e) and device API agree on the shared prefix of the query stream
+    assert np.array_equal(la_d[:1000000].cpu().numpy(), leaf_host_api)
+    w.free()
+
+
+def test_sixteen_fields_raster_vs_port():
+    """config 4 shape at test size: 2*10^4 nodes, 16 fields, 384 x 256 raster"""
+    n, F = 20000, 16
+    xa, ya = synth.uniform_nodes(n)
+    za = synth.values(n, F)
+    order = g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
+    w = make(xa, ya, za, g.DEFAULT, order)
+    nx, ny = 384, 256
+    x0, y0 = xa.min(), ya.min()
+    dx, dy = (xa.max() - x0) / nx, (ya.max() - y0) / ny
+    st, rz, rl = w.eval_raster_e(x0, dx, nx, y0, dy, ny)
+    assert st == g.SUCCESS and rz.shape == (F, nx, ny)
+    port = refimpl.PortTree(w.get_tree(w.n_simplexes(), n), xa, ya)
+    gx, gy = x0 + dx * np.arange(nx), y0 + dy * np.arange(ny)
+    pl, pv, _ = port.eval(np.repeat(gx, ny), np.tile(gy, nx), za)
+    assert np.array_equal(rl.ravel(), pl)
+    assert refimpl.same_bits(rz.reshape(F, -1), pv)
+    # odd field count exercises the scalar gather path
+    w3 = make(xa, ya, za[:3], g.DEFAULT, order)
+    st, z3, l3 = w3.eval_e(np.repeat(gx, ny)[:5000], np.tile(gy, nx)[:5000])
+    assert np.array_equal(l3, pl[:5000]) and refimpl.same_bits(z3, pv[:3, :5000])
+    w3.free()
+    w.free()
+
+
+def test_init_from_reference_tree_and_slab_replication(golden):
+    """true drop-in: adopt the arrays of a tree built by the reference's simplex_tree_init;
+    then replicate the device slab into a second workspace"""
+    torch = _torch()
+    xa, ya = synth.uniform_nodes(1000)
+    za = synth.values(1000, 1)
+    w = g.ScatteredCuda(1000, 1)
+    w.init_from_tree(golden["cfg1_pts3"], golden["cfg1_lnk3"], golden["cfg1_type"], golden["cfg1_shuffle"],
+                     golden["cfg1_shift"], golden["cfg1_scale"], golden["cfg1_seed_points"],
+                     np.stack([xa, ya], axis=1), za)
+    xq, yq = synth.uniform_queries(10000)
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq, golden["cfg1_val"])
+    nbytes = w.slab_bytes()
+    buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+    w.slab_export_device(0, buf.data_ptr())
+    w2 = g.ScatteredCuda(1000, 1)
+    w2.init_from_slab_device(buf.data_ptr(), nbytes)
+    st, zq2, leaf2 = w2.eval_e(xq, yq)
+    assert np.array_equal(leaf2, leaf) and refimpl.same_bits(zq2, zq)
+    w2.free()
+    w.free()
+
+
+def test_pinned_host_buffers_and_small_pipeline_chunks(golden):
+    """eval_e with pinned buffers and a pipeline chunk much smaller than the batch"""
+    import ctypes
+    from gsl_scattered_interpolation_b200 import _lib
+    L = _lib.load()
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
+             host_chunk=777)
+    nq = 10000
+    px = L.gsl_scattered_cuda_host_alloc(nq * 8); py = L.gsl_scattered_cuda_host_alloc(nq * 8)
+    pz = L.gsl_scattered_cuda_host_alloc(nq * 8); pl = L.gsl_scattered_cuda_host_alloc(nq * 4)
+    assert px and py and pz and pl
+    xq, yq = synth.uniform_queries(nq)
+    ctypes.memmove(px, xq.ctypes.data, nq * 8); ctypes.memmove(py, yq.ctypes.data, nq * 8)
+    assert w.eval_ptr_e(px, py, nq, pz, pl) == g.SUCCESS
+    zq = np.ctypeslib.as_array(ctypes.cast(pz, ctypes.POINTER(ctypes.c_double)), (nq,)).copy()
+    leaf = np.ctypeslib.as_array(ctypes.cast(pl, ctypes.POINTER(ctypes.c_int)), (nq,)).copy()
+    assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq[None, :], golden["cfg1_val"])
+    for p in (px, py, pz, pl):
+        L.gsl_scattered_cuda_host_free(p)
+    w.free()
+
+
+def test_two_devices_if_present(golden):
+    if g.device_count() < 2:
+        pytest.skip("single GPU box")
+    xa, ya = synth.uniform_nodes(1000)
+    w = g.ScatteredCuda(1000, 1)
+    w.set_devices([0, 1])
+    w.init(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000))
+    xq, yq = synth.uniform_queries(10000)
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert w.info()["n_devices"] == 2
+    assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq, golden["cfg1_val"])
+    w.free()
+
+
+def test_million_nodes_properties():
+    """BASELINE.json target size: 10^6 nodes.  CPU oracle on a strided subsample, fast path
+    vs exact replay on 100 % of 5*10^7 device-generated queries, linear precision."""
+    torch = _torch()
+    n = 1_000_000
+    xa, ya = synth.uniform_nodes(n)
+    za = np.stack([synth.values(n, 1)[0], xa + 1000.0 * ya])
+    order = g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
+    w = make(xa, ya, za, g.DEFAULT, order)
+    info = w.info()
+    assert info["n_leaves"] == 2 * n + 1                    # T = 2n + 1
+    nq = 50_000_000
+    dev = torch.device("cuda:0")
+    dx = torch.empty(nq, dtype=torch.float64, device=dev)
+    dy = torch.empty(nq, dtype=torch.float64, device=dev)
+    w.generate_uniform_device(0, synth.SEED_QUERIES, 0, nq, 0.0, 1.0, 0.0, 1.0, dx.data_ptr(), dy.data_ptr())
+    za_d = torch.empty((2, nq), dtype=torch.float64, device=dev)
+    la_d = torch.empty(nq, dtype=torch.int32, device=dev)
+    zb_d = torch.empty((2, nq), dtype=torch.float64, device=dev)
+    lb_d = torch.empty(nq, dtype=torch.int32, device=dev)
+    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, za_d.data_ptr(), nq, la_d.data_ptr()) == 0
+    w.set_param("mode", 1)
+    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, zb_d.data_ptr(), nq, lb_d.data_ptr()) == 0
+    w.set_param("mode", 0)
+    bad_leaf, bad_val = w.compare_device(0, la_d.data_ptr(), lb_d.data_ptr(), za_d.data_ptr(),
+                                         zb_d.data_ptr(), nq, 2 * nq)
+    assert bad_leaf == 0 and bad_val == 0
+    assert w.info()["n_deferred"] < 1e-3 * nq
+    # linear precision in non-cage leaves (field 1 = x + 1000 y)
+    want = dx + 1000.0 * dy
+    rel = ((za_d[1] - want).abs() / want.abs())
+    cage_free = rel < 1e-9                                   # cage leaves return partial sums
+    assert cage_free.float().mean().item() > 0.999
+    assert rel[cage_free].max().item() < REL_TOL
+    # CPU oracle (port) on the strided subsample k = 0 (mod 256)
+    sub = torch.arange(0, nq, 256, device=dev)
+    xs, ys = dx[sub].cpu().numpy(), dy[sub].cpu().numpy()
+    port = refimpl.PortTree(w.get_tree(w.n_simplexes(), n), xa, ya)
+    pl, pv, _ = port.eval(xs, ys, za)
+    assert np.array_equal(la_d[sub].cpu().numpy(), pl)
+    assert refimpl.same_bits(za_d[:, sub].cpu().numpy(), pv)
+    w.free()
