@@ -191,7 +191,7 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
     import gsl_scattered_interpolation_b200 as g
-    from gsl_scattered_interpolation_b200 import synth
+    from gsl_scattered_interpolation_b200 import dist_util, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -224,14 +224,12 @@ def main_ours(args):
                       "n_simplexes": inf["n_simplexes"], "n_leaves": inf["n_leaves"],
                       "grid": inf["grid_g"], "slab_bytes": inf["slab_bytes"]}
     if world > 1:
-        nb = torch.tensor([w.slab_bytes() if rank == 0 else 0], dtype=torch.int64, device=dev)
-        dist.broadcast(nb, 0)
-        slab = torch.empty(int(nb.item()), dtype=torch.uint8, device=dev)
+        slab = torch.empty(w.slab_bytes() if rank == 0 else 0, dtype=torch.uint8, device=dev)
         if rank == 0:
             w.slab_export_device(local, slab.data_ptr())
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        dist.broadcast(slab, 0)
+        slab = dist_util.broadcast_blob(slab, 0)
         torch.cuda.synchronize()
         build_info["slab_broadcast_seconds"] = time.perf_counter() - t0
         if rank != 0:
@@ -247,7 +245,8 @@ def main_ours(args):
     dy = torch.empty(Q, dtype=torch.float64, device=dev)
     dz = torch.empty((F, Q), dtype=torch.float64, device=dev)
     dl = torch.empty(Q, dtype=torch.int32, device=dev)
-    w.generate_uniform_device(local, synth.SEED_QUERIES, rank * Q, Q, 0.0, 1.0, 0.0, 1.0,
+    k0, k1 = dist_util.shard_range(rank, world, Q)
+    w.generate_uniform_device(local, synth.SEED_QUERIES, k0, k1 - k0, 0.0, 1.0, 0.0, 1.0,
                               dx.data_ptr(), dy.data_ptr(), sp)
     stream.synchronize()
 
@@ -273,11 +272,8 @@ def main_ours(args):
         step()
     e1.record(stream)
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = dist_util.max_over_ranks(e0.elapsed_time(e1), dev)
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = float(ms.item())
     inf = w.info()
     value = world * Q * args.steps / (ms_total * 1e-3)
     locate_s = inf["locate_seconds"] / max(1, args.steps)          # dominant kernel, per launch
@@ -324,10 +320,8 @@ def main_ours(args):
         for _ in range(e2e_steps):
             w.eval_ptr_e(hx, hy, Qe, hz, hl)
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * Qe * e2e_steps / float(dt.item()), "unit": "queries/s",
+        dt = dist_util.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e = {"value": world * Qe * e2e_steps / dt, "unit": "queries/s",
                "h2d_bytes_per_step": Qe * 16, "d2h_bytes_per_step": Qe * (4 + 8 * F),
                "queries_per_gpu_per_step": Qe, "host_memory": "pinned (gsl_scattered_cuda_host_alloc)"}
     for p in (hx, hy, hz, hl):
