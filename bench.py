@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--stats", action="store_true", help="extra untimed pass counting walk steps")
+    ap.add_argument("--param", action="append", default=[], help="library knob name=value (repeatable)")
     return ap.parse_args()
 
 
@@ -209,6 +210,9 @@ def main_ours(args):
     if args.cells_per_leaf:
         w.set_param("cells_per_leaf", args.cells_per_leaf)
     w.set_param("profile", 1)
+    for kv in args.param:
+        k, v = kv.split("=")
+        w.set_param(k, float(v))
     build_info = {}
     # --- triangulation: built once on the host by rank 0 (timed separately), uploaded, and
     #     replicated to the other GPUs as one slab over NCCL/NVLink
@@ -351,7 +355,7 @@ def main_ours(args):
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_locate", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_walk", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel_ms_per_launch": 1e3 * locate_s, "exact_replay_ms_per_step": 1e3 * exact_s},

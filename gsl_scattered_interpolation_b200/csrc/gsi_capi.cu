@@ -107,6 +107,8 @@ struct gsl_scattered_cuda
   bool built = false, uploaded = false;
   gsi_flatten_params fprm;
   int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
+  int kernel = GSI_KERNEL_WALK, walk_ctas_per_sm = 5;
+  size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
   double list_fraction = 1.0 / 16;
   size_t host_chunk = (size_t) 1 << 22;
@@ -210,6 +212,9 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r)
   c.max_steps = w->max_steps;
   c.sm_count = r->sm_count;
   c.locate_ctas_per_sm = w->ctas_per_sm;
+  c.kernel = w->kernel;
+  c.walk_ctas_per_sm = w->walk_ctas_per_sm;
+  c.walk_chunk = w->walk_chunk;
   c.list = r->list;
   c.list_capacity = r->list_cap;
   c.counters = r->counters;
@@ -526,6 +531,9 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "host_chunk" && value >= 1) w->host_chunk = (size_t) value;
   else if (k == "ctas_per_sm" && value >= 1) w->ctas_per_sm = (int) value;
   else if (k == "profile") w->profile = value != 0;
+  else if (k == "kernel" && (value == 0 || value == 1)) w->kernel = (int) value;
+  else if (k == "walk_ctas_per_sm" && value >= 1) w->walk_ctas_per_sm = (int) value;
+  else if (k == "walk_chunk" && value >= 0) w->walk_chunk = ((size_t) value + 31) & ~(size_t) 31;
   else if (k == "list_fraction" && value > 0 && value <= 1) w->list_fraction = value;
   else GSI_ERROR("unknown parameter or value out of range", GSL_SCATTERED_EINVAL);
   return GSL_SCATTERED_SUCCESS;

@@ -16,7 +16,7 @@
 
 #if defined(__CUDA_ARCH__)
 #define GSI_LDG(p) __ldg(p)
-#define GSI_STREAM_STORE(p, v) __stcs((p), (v))
+#define GSI_STREAM_STORE(p, v) (*(p) = (v))
 #define GSI_NAN __longlong_as_double(0x7ff8000000000000LL)
 #define GSI_FLOOR_INT(x) __double2int_rd(x)
 #define GSI_BITS_TO_FLOAT(u) __uint_as_float(u)
@@ -35,82 +35,102 @@ gsi_bits_to_float_host(uint32_t u)
 #define GSI_BITS_TO_FLOAT(u) gsi_bits_to_float_host(u)
 #endif
 
-typedef struct
-#if defined(__CUDACC__)
-    __align__(16)
-#endif
-    gsi_int4
+#if defined(__CUDA_ARCH__)
+/* one 32-byte sector with a single 256-bit load (LDG.E.256, sm_100+); read-only path */
+__device__ __forceinline__ void
+gsi_ld256(const void *p, unsigned long long &a, unsigned long long &b, unsigned long long &c,
+          unsigned long long &d)
 {
-  int32_t x, y, z, w;
-} gsi_int4;
-
-typedef struct
-#if defined(__CUDACC__)
-    __align__(16)
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+               : "l"(p));
+}
 #endif
-    gsi_double2
-{
-  double x, y;
-} gsi_double2;
 
+/* the 64-byte LU/link part of a record (DAG node or leaf): two sectors */
 GSI_HD void
-gsi_fetch_rec(gsi_rec *r, const gsi_rec *base, int idx)
+gsi_fetch_rec(gsi_rec *r, const void *rec)
 {
 #if defined(__CUDA_ARCH__)
-  const double2 *p = reinterpret_cast<const double2 *>(base + idx);
-  const double2 a = __ldg(p);
-  const double2 b = __ldg(p + 1);
-  const double2 c = __ldg(p + 2);
-  const int4 d = __ldg(reinterpret_cast<const int4 *>(p + 3));
-  r->x0x = a.x; r->x0y = a.y;
-  r->u00 = b.x; r->u01 = b.y;
-  r->u11 = c.x; r->l10 = c.y;
-  r->lnk[0] = d.x; r->lnk[1] = d.y; r->lnk[2] = d.z;
-  r->meta = (uint32_t) d.w;
+  unsigned long long a, b, c, d, e, f, g, h;
+  gsi_ld256(rec, a, b, c, d);
+  gsi_ld256(reinterpret_cast<const char *>(rec) + 32, e, f, g, h);
+  r->x0x = __longlong_as_double((long long) a);
+  r->x0y = __longlong_as_double((long long) b);
+  r->u00 = __longlong_as_double((long long) c);
+  r->u01 = __longlong_as_double((long long) d);
+  r->u11 = __longlong_as_double((long long) e);
+  r->l10 = __longlong_as_double((long long) f);
+  r->lnk[0] = (int32_t) (unsigned) g;
+  r->lnk[1] = (int32_t) (unsigned) (g >> 32);
+  r->lnk[2] = (int32_t) (unsigned) h;
+  r->meta = (uint32_t) (h >> 32);
 #else
-  *r = base[idx];
+  *r = *(const gsi_rec *) rec;
 #endif
 }
 
-GSI_HD gsi_int4
-gsi_fetch_aux(const int32_t *aux, int slot)
+/* the 32-byte tail of a leaf: one sector */
+GSI_HD void
+gsi_fetch_tail(gsi_leaf_tail *t, const gsi_leaf *leaf)
 {
 #if defined(__CUDA_ARCH__)
-  const int4 v = __ldg(reinterpret_cast<const int4 *>(aux) + slot);
-  gsi_int4 o;
-  o.x = v.x; o.y = v.y; o.z = v.z; o.w = v.w;
-  return o;
+  unsigned long long a, b, c, d;
+  gsi_ld256(&leaf->t, a, b, c, d);
+  t->s.node = (int32_t) (unsigned) a;
+  t->s.vflags = (uint32_t) (a >> 32);
+  t->s.z[0] = __longlong_as_double((long long) b);
+  t->s.z[1] = __longlong_as_double((long long) c);
+  t->s.z[2] = __longlong_as_double((long long) d);
 #else
-  gsi_int4 o;
-  o.x = aux[4 * slot]; o.y = aux[4 * slot + 1]; o.z = aux[4 * slot + 2]; o.w = aux[4 * slot + 3];
-  return o;
+  *t = leaf->t;
 #endif
 }
 
-#define GSI_FETCH_DAG(dst, idx) gsi_fetch_rec(&(dst), dag, (idx))
+#define GSI_FETCH_DAG(dst, idx) gsi_fetch_rec(&(dst), dag + (idx))
 GSI_DEFINE_DESCEND(gsi_descend, GSI_HD, const gsi_rec *, GSI_FETCH_DAG)
 
-/* interp_point for the F fields of one query, field-major output val[f*ld + q] */
+/* interp_point for the F fields of one query, field-major output val[f*ld + q].
+ * `t` is the accepted leaf's tail: with one field it carries the three vertex values, else the
+ * vertex slots of the vertex-major value table (gathered with 256-/128-bit loads). */
 GSI_HD void
-gsi_blend_store(const gsi_view *V, const gsi_int4 ax, double c0, double c1, double *val, size_t ld,
-                size_t q)
+gsi_blend_store(const gsi_view *V, const gsi_leaf_tail *t, double c0, double c1, double *val,
+                size_t ld, size_t q)
 {
   const int F = V->n_fields;
-  const int ha = ax.x >= 0, hb = ax.y >= 0, hx = ax.z >= 0;
-  const double *za = V->z + (size_t) (ha ? ax.x : 0) * F;
-  const double *zb = V->z + (size_t) (hb ? ax.y : 0) * F;
-  const double *zx = V->z + (size_t) (hx ? ax.z : 0) * F;
   if (F == 1)
     {
-      const double a = ha ? GSI_LDG(za) : 0.0, b = hb ? GSI_LDG(zb) : 0.0,
-                   x = hx ? GSI_LDG(zx) : 0.0;
-      GSI_STREAM_STORE(val + q, gsi_blend(c0, c1, ha, a, hb, b, hx, x));
+      const uint32_t vf = t->s.vflags;
+      GSI_STREAM_STORE(val + q, gsi_blend(c0, c1, (int) (vf & 1u), t->s.z[0], (int) (vf & 2u),
+                                          t->s.z[1], (int) (vf & 4u), t->s.z[2]));
       return;
     }
+  const int ha = t->g.v[0] >= 0, hb = t->g.v[1] >= 0, hx = t->g.v[2] >= 0;
+  const double *za = V->z + (size_t) (ha ? t->g.v[0] : 0) * F;
+  const double *zb = V->z + (size_t) (hb ? t->g.v[1] : 0) * F;
+  const double *zx = V->z + (size_t) (hx ? t->g.v[2] : 0) * F;
 #if defined(__CUDA_ARCH__)
+  if ((F & 3) == 0)
+    {
+      /* the F values of a vertex are contiguous and 32-byte aligned: 256-bit gathers */
+#pragma unroll 2
+      for (int f = 0; f < F; f += 4)
+        {
+          unsigned long long a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, x[4] = {0, 0, 0, 0};
+          if (ha) gsi_ld256(za + f, a[0], a[1], a[2], a[3]);
+          if (hb) gsi_ld256(zb + f, b[0], b[1], b[2], b[3]);
+          if (hx) gsi_ld256(zx + f, x[0], x[1], x[2], x[3]);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            val[(size_t) (f + k) * ld + q] =
+                gsi_blend(c0, c1, ha, __longlong_as_double((long long) a[k]), hb,
+                          __longlong_as_double((long long) b[k]), hx,
+                          __longlong_as_double((long long) x[k]));
+        }
+      return;
+    }
   if ((F & 1) == 0)
     {
-      /* 128-bit gathers: the F values of a vertex are contiguous and 16-byte aligned */
       const double2 *pa = reinterpret_cast<const double2 *>(za);
       const double2 *pb = reinterpret_cast<const double2 *>(zb);
       const double2 *px = reinterpret_cast<const double2 *>(zx);
@@ -121,8 +141,8 @@ gsi_blend_store(const gsi_view *V, const gsi_int4 ax, double c0, double c1, doub
           if (ha) a = __ldg(pa + (f >> 1));
           if (hb) b = __ldg(pb + (f >> 1));
           if (hx) x = __ldg(px + (f >> 1));
-          __stcs(val + (size_t) f * ld + q, gsi_blend(c0, c1, ha, a.x, hb, b.x, hx, x.x));
-          __stcs(val + (size_t) (f + 1) * ld + q, gsi_blend(c0, c1, ha, a.y, hb, b.y, hx, x.y));
+          val[(size_t) f * ld + q] = gsi_blend(c0, c1, ha, a.x, hb, b.x, hx, x.x);
+          val[(size_t) (f + 1) * ld + q] = gsi_blend(c0, c1, ha, a.y, hb, b.y, hx, x.y);
         }
       return;
     }
@@ -160,7 +180,12 @@ gsi_exact_one(const gsi_view *V, double qx, double qy, double *val, int *leaf_ou
   if (!(lr.meta & GSI_META_SINGULAR) && last != node)
     gsi_solve(&V->xf, &lr, (int) (lr.meta & GSI_META_SWAP), qx, qy, &c0, &c1);
   if (leaf_out) leaf_out[q] = node;
-  if (val) gsi_blend_store(V, gsi_fetch_aux(V->aux, slot), c0, c1, val, ld, q);
+  if (val)
+    {
+      gsi_leaf_tail t;
+      gsi_fetch_tail(&t, V->leaf + slot);
+      gsi_blend_store(V, &t, c0, c1, val, ld, q);
+    }
   return slot;
 }
 
@@ -188,14 +213,39 @@ gsi_cell_centre(const gsi_view *V, size_t cell, double *qx, double *qy)
   *qy = V->xf.cy + v / V->xf.sy;
 }
 
-/* Fast path for one query.  Returns 1 when the query was resolved (outputs written),
- * 0 when it must be deferred to the exact replay.  *steps = leaves visited.
+#define GSI_STEP_ACCEPT 0 /* strictly inside with margin: the leaf is the answer */
+#define GSI_STEP_MOVE 1   /* clearly outside across one edge: *slot = neighbour */
+#define GSI_STEP_DEFER 2  /* cannot be proven here: exact replay decides */
+
+/* One step of the fast path on the leaf record `r` of `*slot`.
  *
  * Acceptance: all three reference weights c0, c1, 1-(c0+c1) of the visited leaf are >= the
  * leaf's margin tau, i.e. the query is at least `delta` (standardised units) inside every
- * edge; then the reference's DAG descent provably ends in this leaf and the
- * weights are by construction the ones interp_point uses.  Otherwise cross the edge of the
+ * edge; then the reference's DAG descent provably ends in this leaf and
+ * the weights are by construction the ones interp_point uses.  Otherwise cross the edge of the
  * most negative weight if it is clearly negative (<= -tau), else defer. */
+GSI_HD int
+gsi_walk_step(const gsi_xform *xf, const gsi_rec *r, double qx, double qy, int *slot, double *c0,
+              double *c1)
+{
+  const double tau = (double) GSI_BITS_TO_FLOAT(r->meta & 0x7fffffffu);
+  gsi_solve(xf, r, (int) (r->meta >> 31), qx, qy, c0, c1);
+  const double c2 = GSI_SUB(1.0, GSI_ADD(GSI_ADD(0.0, *c0), *c1));
+  if ((*c0 >= tau) && (*c1 >= tau) && (c2 >= tau)) return GSI_STEP_ACCEPT;
+  int e = 0;
+  double m = *c0;
+  if (*c1 < m) { m = *c1; e = 1; }
+  if (c2 < m) { m = c2; e = 2; }
+  if (!(m <= -tau)) return GSI_STEP_DEFER; /* within the margin of an edge (or NaN) */
+  const int nb = GSI_LNK(*r, e);
+  if (nb < 0) return GSI_STEP_DEFER;       /* beyond the cage hull */
+  *slot = nb;
+  return GSI_STEP_MOVE;
+}
+
+/* Fast path for one query, start to finish (host logic simulator; the device kernel runs
+ * the same gsi_walk_step with lanes decoupled from queries).  Returns 1 when the query was
+ * resolved (outputs written), 0 when it must be deferred.  *steps = leaves visited. */
 GSI_HD int
 gsi_locate_one(const gsi_view *V, double qx, double qy, int max_steps, double *val, int *leaf_out,
                size_t ld, size_t q, int *steps)
@@ -206,27 +256,20 @@ gsi_locate_one(const gsi_view *V, double qx, double qy, int max_steps, double *v
   for (int step = 0; step < max_steps; step++)
     {
       gsi_rec r;
-      gsi_fetch_rec(&r, V->leaf, slot);
-      const double tau = (double) GSI_BITS_TO_FLOAT(r.meta & 0x7fffffffu);
       double c0, c1;
-      gsi_solve(&V->xf, &r, (int) (r.meta >> 31), qx, qy, &c0, &c1);
-      const double c2 = GSI_SUB(1.0, GSI_ADD(GSI_ADD(0.0, c0), c1));
+      const gsi_leaf *lf = V->leaf + slot;
+      gsi_fetch_rec(&r, lf);
       *steps = step + 1;
-      if ((c0 >= tau) && (c1 >= tau) && (c2 >= tau))
+      const int st = gsi_walk_step(&V->xf, &r, qx, qy, &slot, &c0, &c1);
+      if (st == GSI_STEP_ACCEPT)
         {
-          const gsi_int4 ax = gsi_fetch_aux(V->aux, slot);
-          if (leaf_out) GSI_STREAM_STORE(leaf_out + q, ax.w);
-          if (val) gsi_blend_store(V, ax, c0, c1, val, ld, q);
+          gsi_leaf_tail t;
+          gsi_fetch_tail(&t, lf);
+          if (leaf_out) GSI_STREAM_STORE(leaf_out + q, t.g.node);
+          if (val) gsi_blend_store(V, &t, c0, c1, val, ld, q);
           return 1;
         }
-      int e = 0;
-      double m = c0;
-      if (c1 < m) { m = c1; e = 1; }
-      if (c2 < m) { m = c2; e = 2; }
-      if (!(m <= -tau)) return 0; /* within the margin of an edge (or NaN): defer */
-      const int nb = GSI_LNK(r, e);
-      if (nb < 0) return 0; /* beyond the cage hull: the exact path decides */
-      slot = nb;
+      if (st == GSI_STEP_DEFER) return 0;
     }
   return 0;
 }

@@ -154,8 +154,7 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   h.delta = prm.delta;
   uint64_t off = align256(sizeof h);
   h.off_dag = off;   off = align256(off + N * sizeof(gsi_rec));
-  h.off_leaf = off;  off = align256(off + L * sizeof(gsi_rec));
-  h.off_aux = off;   off = align256(off + L * 4 * sizeof(int32_t));
+  h.off_leaf = off;  off = align256(off + L * sizeof(gsi_leaf));
   h.off_z = off;     off = align256(off + std::max<size_t>(1, n) * n_fields * sizeof(double));
   h.off_seeds = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
   h.total_bytes = off;
@@ -164,8 +163,7 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   char *base = image->data();
   std::memcpy(base, &h, sizeof h);
   gsi_rec *dag = (gsi_rec *) (base + h.off_dag);
-  gsi_rec *leaf = (gsi_rec *) (base + h.off_leaf);
-  int32_t *aux = (int32_t *) (base + h.off_aux);
+  gsi_leaf *leaf = (gsi_leaf *) (base + h.off_leaf);
   double *z = (double *) (base + h.off_z);
 
   /* --- DAG records --------------------------------------------------------------------- */
@@ -191,7 +189,7 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
         }
     }
 
-  /* --- leaf records + aux -------------------------------------------------------------- */
+  /* --- leaf records -------------------------------------------------------------------- */
   for (size_t k = 0; k < L; k++)
     {
       const size_t node = (size_t) keyed[k].second;
@@ -223,15 +221,27 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
       std::memcpy(&bits, &tf, 4);
       if (m & GSI_META_SWAP) bits |= 0x80000000u;
       r.meta = bits;
+      gsi_leaf_tail tail;
+      std::memset(&tail, 0, sizeof tail);
       for (int i = 0; i < 3; i++)
         {
           const int32_t nb = t.lnk[3 * node + i];
           r.lnk[i] = nb ? slot_of_node[(size_t) nb] : -1;
           const int32_t p = t.pts[3 * node + i];
-          aux[4 * k + i] = p < 0 ? -1 : vslot_of_row[(size_t) t.shuffle[(size_t) p]];
+          if (n_fields == 1)
+            {
+              if (p >= 0)
+                {
+                  tail.s.vflags |= 1u << i;
+                  tail.s.z[i] = za ? za[(size_t) t.shuffle[(size_t) p]] : 0.0;
+                }
+            }
+          else
+            tail.g.v[i] = p < 0 ? -1 : vslot_of_row[(size_t) t.shuffle[(size_t) p]];
         }
-      aux[4 * k + 3] = (int32_t) node;
-      leaf[k] = r;
+      tail.g.node = (int32_t) node; /* same offset in both views */
+      leaf[k].r = r;
+      leaf[k].t = tail;
     }
 
   /* --- values -------------------------------------------------------------------------- */

@@ -30,8 +30,8 @@ struct src_arrays
   const double *x, *y;
   __device__ __forceinline__ void get(size_t q, double &qx, double &qy) const
   {
-    qx = __ldcs(x + q); /* streamed once: do not let it evict the triangulation */
-    qy = __ldcs(y + q);
+    qx = __ldg(x + q);
+    qy = __ldg(y + q);
   }
 };
 
@@ -150,6 +150,130 @@ k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out,
     }
 }
 
+/* rare: the deferred list is full; kept out of line so it does not inflate the hot loop */
+__device__ __noinline__ void
+exact_in_place(const gsi_view &V, double qx, double qy, double *val, int *leaf_out, size_t ld,
+               size_t q, unsigned *counters)
+{
+  if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0) atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+}
+
+/* ---- fast path, lanes decoupled from queries -------------------------------------------------
+ * One warp owns a contiguous chunk of queries and consumes it through a warp-wide work queue:
+ * every loop iteration is ONE walk step (one 96-byte leaf fetch = three 256-bit loads) for
+ * whatever query each lane currently holds; a lane that accepted or deferred its query takes the
+ * next one from the queue at once instead of idling until the slowest lane of the warp finished
+ * its walk.  Each lane keeps two queries in flight behind the current one -- `nn` (coordinates
+ * being loaded) and `nxt` (seed cell being loaded) -- so the only exposed latency per iteration
+ * is the leaf fetch itself. */
+template <class SRC, bool STATS, bool ONE_FIELD>
+__global__ void __launch_bounds__(GSI_WALK_THREADS)
+k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
+       size_t ld, unsigned *list, unsigned list_cap, unsigned *counters, int max_steps)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const size_t warp_id = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t) gridDim.x * blockDim.x) >> 5;
+  const size_t n_chunks = (nq + chunk - 1) / chunk;
+  unsigned long long steps_acc = 0;
+  for (size_t ch = warp_id; ch < n_chunks; ch += n_warps)
+    {
+      const size_t q0 = ch * (size_t) chunk;
+      const unsigned total = (unsigned) (nq - q0 < (size_t) chunk ? nq - q0 : (size_t) chunk);
+      unsigned next = 0; /* warp-uniform: queries of this chunk handed out so far */
+      bool cur_v = false, nxt_v = false, nn_v = false;
+      unsigned cur_q = 0, nxt_q = 0, nn_q = 0;
+      double cur_x = 0, cur_y = 0, nxt_x = 0, nxt_y = 0, nn_x = 0, nn_y = 0;
+      int cur_slot = 0, nxt_seed = 0, cur_steps = 0;
+      for (;;)
+        {
+          /* refill: promote nxt -> cur, nn -> nxt (issue its seed load), take a new nn */
+          const bool need = !cur_v;
+          if (need)
+            {
+              cur_v = nxt_v; cur_q = nxt_q; cur_x = nxt_x; cur_y = nxt_y;
+              cur_slot = nxt_seed; cur_steps = 0;
+              nxt_v = nn_v; nxt_q = nn_q; nxt_x = nn_x; nxt_y = nn_y;
+              if (nxt_v) nxt_seed = __ldg(V.seeds + gsi_cell_of(&V, nxt_x, nxt_y));
+            }
+          const unsigned take = __ballot_sync(FULL, need);
+          if (need)
+            {
+              const unsigned off = next + __popc(take & lt_mask);
+              nn_v = off < total;
+              if (nn_v)
+                {
+                  nn_q = off;
+                  src.get(q0 + off, nn_x, nn_y);
+                }
+            }
+          next += __popc(take);
+          if (next > total) next = total;
+          if (!__any_sync(FULL, cur_v || nxt_v || nn_v)) break;
+
+          bool defer = false;
+          if (cur_v)
+            {
+              if (!(isfinite(cur_x) && isfinite(cur_y)))
+                defer = true;
+              else
+                {
+                  const gsi_leaf *lf = V.leaf + cur_slot;
+                  gsi_rec r;
+                  gsi_leaf_tail t;
+                  gsi_fetch_rec(&r, lf);
+                  gsi_fetch_tail(&t, lf); /* speculative: only used when this leaf is accepted */
+                  double c0, c1;
+                  const int st = gsi_walk_step(&V.xf, &r, cur_x, cur_y, &cur_slot, &c0, &c1);
+                  ++cur_steps;
+                  if (st == GSI_STEP_ACCEPT)
+                    {
+                      const size_t q = q0 + cur_q;
+                      if (leaf_out) leaf_out[q] = t.g.node;
+                      if (val)
+                        {
+                          if (ONE_FIELD)
+                            val[q] = gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0],
+                                               (int) (t.s.vflags & 2u), t.s.z[1],
+                                               (int) (t.s.vflags & 4u), t.s.z[2]);
+                          else
+                            gsi_blend_store(&V, &t, c0, c1, val, ld, q);
+                        }
+                      if (STATS) steps_acc += (unsigned) cur_steps;
+                      cur_v = false;
+                    }
+                  else if (st == GSI_STEP_DEFER || cur_steps >= max_steps)
+                    defer = true;
+                }
+              if (defer) cur_v = false;
+            }
+          /* warp-aggregated append to the deferred list */
+          const unsigned dm = __ballot_sync(FULL, defer);
+          if (dm)
+            {
+              const int leader = __ffs(dm) - 1;
+              unsigned pos = 0;
+              if (lane == (unsigned) leader)
+                pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+              pos = __shfl_sync(FULL, pos, leader);
+              if (defer)
+                {
+                  const size_t q = q0 + cur_q;
+                  const unsigned at = pos + __popc(dm & lt_mask);
+                  if (at < list_cap)
+                    list[at] = (unsigned) q;
+                  else
+                    exact_in_place(V, cur_x, cur_y, val, leaf_out, ld, q, counters);
+                }
+            }
+        }
+    }
+  if (STATS && steps_acc)
+    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
+}
+
 /* ---- synthetic inputs / verification helpers ------------------------------------------------ */
 __global__ void __launch_bounds__(256)
 k_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo, double xw, double ylo,
@@ -244,15 +368,38 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
     }
   cudaError_t e = cudaMemsetAsync(cfg.counters + GSI_CNT_DEFERRED, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  const int g1 = grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm);
   if (cfg.ev_locate0) cudaEventRecord(cfg.ev_locate0, st);
-  if (cfg.stats)
-    k_locate<SRC, true><<<g1, GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list,
-                                                          list_cap, cfg.counters, cfg.max_steps);
+  if (cfg.kernel == GSI_KERNEL_WALK)
+    {
+      const int ctas = cfg.sm_count * cfg.walk_ctas_per_sm;
+      const size_t n_warps = (size_t) ctas * (GSI_WALK_THREADS / 32);
+      /* per-warp chunk: ~8 chunks per warp for balance, 256..8192 queries, multiple of 32 */
+      size_t chunk = (nq / (n_warps * 8) + 31) & ~(size_t) 31;
+      if (chunk < 256) chunk = 256;
+      if (chunk > 8192) chunk = 8192;
+      if (cfg.walk_chunk) chunk = cfg.walk_chunk;
+      const size_t n_chunks = (nq + chunk - 1) / chunk;
+      const int g = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas
+                               ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
+                               : (size_t) ctas);
+#define GSI_LAUNCH_WALK(STATS, ONE)                                                             \
+  k_walk<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out,  \
+                                                          ld, cfg.list, list_cap, cfg.counters,      \
+                                                          cfg.max_steps)
+      if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALK(true, true);
+      else if (cfg.stats) GSI_LAUNCH_WALK(true, false);
+      else if (V.n_fields == 1) GSI_LAUNCH_WALK(false, true);
+      else GSI_LAUNCH_WALK(false, false);
+#undef GSI_LAUNCH_WALK
+    }
+  else if (cfg.stats)
+    k_locate<SRC, true><<<grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
+                          GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list, list_cap,
+                                                       cfg.counters, cfg.max_steps);
   else
-    k_locate<SRC, false><<<g1, GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld,
-                                                           cfg.list, list_cap, cfg.counters,
-                                                           cfg.max_steps);
+    k_locate<SRC, false><<<grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
+                           GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list,
+                                                        list_cap, cfg.counters, cfg.max_steps);
   if (cfg.ev_locate1) cudaEventRecord(cfg.ev_locate1, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -9,6 +9,7 @@
 #include "gsi_layout.h"
 
 #define GSI_LOCATE_THREADS 256
+#define GSI_WALK_THREADS 128
 
 /* device counters (unsigned[16]) */
 #define GSI_CNT_DEFERRED 0       /* u32: length of the deferred list of the current launch */
@@ -20,6 +21,9 @@
 #define GSI_MODE_FAST 0  /* grid-seeded walk + exact replay of the deferred queries */
 #define GSI_MODE_EXACT 1 /* exact DAG replay on every query */
 
+#define GSI_KERNEL_WALK 0   /* k_walk: lanes decoupled from queries (default) */
+#define GSI_KERNEL_SIMPLE 1 /* k_locate: one thread per query, kept for A/B measurements */
+
 struct gsi_launch_cfg
 {
   int mode = GSI_MODE_FAST;
@@ -27,6 +31,9 @@ struct gsi_launch_cfg
   int max_steps = 256;
   int sm_count = 148;
   int locate_ctas_per_sm = 8;
+  int kernel = GSI_KERNEL_WALK;
+  int walk_ctas_per_sm = 5;
+  size_t walk_chunk = 0; /* 0 = derive from the launch size */
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
   size_t list_capacity = 0;     /* deferred-list entries; overflow is resolved in place */
   unsigned *counters = nullptr; /* GSI_CNT_WORDS words */

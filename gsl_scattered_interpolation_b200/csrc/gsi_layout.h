@@ -6,14 +6,14 @@
  *   header   gsi_slab_header
  *   dag      gsi_rec[n_dag]     history-DAG nodes in the reference's node-id order (exact
  *                               replay kernel; a leaf's lnk[0] holds its compact slot)
- *   leaf     gsi_rec[n_leaves]  leaves only, sorted along a Morton curve of their centroids;
- *                               lnk[] = slot of the neighbour opposite vertex i, -1 = none
- *                               (hull of the cage); meta = float margin | swap sign bit
- *   aux      int32[4][n_leaves] {vertex slot of POINT(leaf,0..2) or -1 for a cage seed,
- *                               reference node id}  -- read once per query, 128-bit load
+ *   leaf     gsi_leaf[n_leaves] leaves only (96 B), sorted along a Morton curve of their
+ *                               centroids; r.lnk[] = slot of the neighbour opposite vertex i,
+ *                               -1 = none (hull of the cage); r.meta = float margin | swap
+ *                               sign bit; tail = reference node id + vertex slots (or, with
+ *                               one field, the three vertex values themselves)
  *   z        double[n_points][n_fields]  vertex values, vertex-major so the F fields of a
- *                               vertex are contiguous (F = 16 -> one 128-byte line), vertices
- *                               sorted along the same Morton curve
+ *                               vertex are contiguous (F = 16 -> one 128-byte line, four
+ *                               256-bit loads), vertices sorted along the same Morton curve
  *   seeds    int32[G*G]         uniform grid over the data bounding box in standardised
  *                               coordinates: leaf slot containing the cell centre
  *                               (filled on the device by the exact-replay kernel)
@@ -29,7 +29,37 @@
 #include "gsi_core.h"
 
 #define GSI_SLAB_MAGIC 0x3142414c53495347ull /* "GSISLAB1" */
-#define GSI_SLAB_VERSION 1u
+#define GSI_SLAB_VERSION 2u
+
+/* One compacted leaf: 96 bytes = three 32-byte sectors, each fetched with one 256-bit load
+ * (LDG.E.256 on sm_100a).  A walk step reads r (sectors 0-1); only the accepted leaf's tail
+ * (sector 2) is read.  With one field the three vertex values live in the tail itself, so an
+ * accepted query costs no further gather. */
+typedef union
+{
+  struct
+  {
+    int32_t node; /* reference simplex_index (history-DAG node id) */
+    int32_t v[3]; /* vertex slots into z (vertex-major), -1 = cage seed vertex */
+    double pad[2];
+  } g; /* n_fields > 1 */
+  struct
+  {
+    int32_t node;
+    uint32_t vflags; /* bit i set: POINT(leaf,i) is a data vertex (not a cage seed) */
+    double z[3];     /* values of POINT(leaf,0..2) */
+  } s; /* n_fields == 1 */
+} gsi_leaf_tail;
+
+typedef struct
+#if defined(__CUDACC__)
+    __align__(32)
+#endif
+    gsi_leaf
+{
+  gsi_rec r; /* lnk[] = neighbour slot opposite vertex i (-1 = none), meta = tau | swap bit */
+  gsi_leaf_tail t;
+} gsi_leaf;
 
 typedef struct
 {
@@ -45,7 +75,7 @@ typedef struct
   /* grid mapping in standardised coordinates: cell = floor((u - u0) * inv_du) */
   double u0, v0, inv_du, inv_dv;
   double delta; /* absolute safety margin (standardised units) behind the per-leaf tau */
-  uint64_t off_dag, off_leaf, off_aux, off_z, off_seeds;
+  uint64_t off_dag, off_leaf, off_z, off_seeds;
   uint64_t total_bytes;
   uint64_t reserved[8];
 } gsi_slab_header;
@@ -55,8 +85,7 @@ typedef struct
 {
   gsi_xform xf;
   const gsi_rec *dag;
-  const gsi_rec *leaf;
-  const int32_t *aux; /* 4 per leaf */
+  const gsi_leaf *leaf;
   const double *z;
   const int32_t *seeds;
   double u0, v0, inv_du, inv_dv;
@@ -73,8 +102,7 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   gsi_view v;
   v.xf = h->xf;
   v.dag = (const gsi_rec *) (b + h->off_dag);
-  v.leaf = (const gsi_rec *) (b + h->off_leaf);
-  v.aux = (const int32_t *) (b + h->off_aux);
+  v.leaf = (const gsi_leaf *) (b + h->off_leaf);
   v.z = (const double *) (b + h->off_z);
   v.seeds = (const int32_t *) (b + h->off_seeds);
   v.u0 = h->u0; v.v0 = h->v0; v.inv_du = h->inv_du; v.inv_dv = h->inv_dv;

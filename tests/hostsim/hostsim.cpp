@@ -75,13 +75,6 @@ hostsim_free(hostsim *h)
 size_t hostsim_n_leaves(const hostsim *h) { return (size_t) h->hdr.n_leaves; }
 size_t hostsim_grid_g(const hostsim *h) { return (size_t) h->hdr.grid_g; }
 
-/* leaf vertex rows (original data row ids, -1 = cage) for test-input generation */
-void
-hostsim_leaf_aux(const hostsim *h, int32_t *aux4)
-{
-  std::memcpy(aux4, h->view.aux, (size_t) h->hdr.n_leaves * 4 * sizeof(int32_t));
-}
-
 /* mode 0: k_locate + k_exact_list protocol; mode 1: k_exact_all.
  * stats[0] = deferred, stats[1] = walk steps of accepted queries, stats[2] = outside cage */
 int
