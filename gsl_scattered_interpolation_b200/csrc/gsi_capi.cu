@@ -108,6 +108,7 @@ struct gsl_scattered_cuda
   gsi_flatten_params fprm;
   int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
   int kernel = GSI_KERNEL_WALK, walk_ctas_per_sm = 5;
+  int l2_fetch = 32; /* cudaLimitMaxL2FetchGranularity: random 32-byte sector gathers */
   size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
   double list_fraction = 1.0 / 16;
@@ -181,6 +182,19 @@ make_replica(int dev, replica **out)
       CU(cudaEventCreateWithFlags(&r->st[b].ev_out, cudaEventDisableTiming));
     }
   return 0;
+}
+
+/* The eval path gathers isolated 32-byte sectors from a structure that exceeds the L2 at
+ * 10^6 nodes; the default 64-byte L2 fetch granularity would double the DRAM traffic of every
+ * miss.  Device-wide hint (cudaLimitMaxL2FetchGranularity); 0 = leave the driver default. */
+void
+apply_l2_fetch(const gsl_scattered_cuda *w)
+{
+  if (w->l2_fetch > 0)
+    {
+      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) w->l2_fetch) != cudaSuccess)
+        cudaGetLastError();
+    }
 }
 
 replica *
@@ -431,6 +445,7 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
       int s = make_replica(d, &r);
       if (r) w->reps.push_back(r);
       if (s) return s;
+      apply_l2_fetch(w);
       CU(cudaMalloc(&r->slab, w->hdr.total_bytes));
       r->view = gsi_view_of(r->slab, &w->hdr);
     }
@@ -525,6 +540,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "grid_g" && value >= 0 && value <= 32768) w->fprm.grid_g = (uint32_t) value;
   else if (k == "max_steps" && value >= 1) w->max_steps = (int) value;
   else if (k == "delta" && value > 0) w->fprm.delta = value;
+  else if (k == "leaf_stride" && (value == 96 || value == 128)) w->fprm.leaf_stride = (uint32_t) value;
   else if (k == "mode" && (value == 0 || value == 1)) w->mode = (int) value;
   else if (k == "stats") w->stats = value != 0;
   else if (k == "chunk" && value >= 1) w->chunk = (size_t) value;
@@ -532,6 +548,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "ctas_per_sm" && value >= 1) w->ctas_per_sm = (int) value;
   else if (k == "profile") w->profile = value != 0;
   else if (k == "kernel" && (value == 0 || value == 1)) w->kernel = (int) value;
+  else if (k == "l2_fetch" && (value == 0 || value == 32 || value == 64 || value == 128)) w->l2_fetch = (int) value;
   else if (k == "walk_ctas_per_sm" && value >= 1) w->walk_ctas_per_sm = (int) value;
   else if (k == "walk_chunk" && value >= 0) w->walk_chunk = ((size_t) value + 31) & ~(size_t) 31;
   else if (k == "list_fraction" && value > 0 && value <= 1) w->list_fraction = value;
@@ -877,6 +894,7 @@ gsl_scattered_cuda_init_from_slab_device(gsl_scattered_cuda *w, const void *d_sr
       int s = make_replica(d, &r);
       if (r) w->reps.push_back(r);
       if (s) return s;
+      apply_l2_fetch(w);
       CU(cudaMalloc(&r->slab, bytes));
       r->view = gsi_view_of(r->slab, &w->hdr);
       CU(cudaMemcpy(r->slab, d_src, bytes, cudaMemcpyDefault));

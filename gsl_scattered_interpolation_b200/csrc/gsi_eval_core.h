@@ -183,7 +183,7 @@ gsi_exact_one(const gsi_view *V, double qx, double qy, double *val, int *leaf_ou
   if (val)
     {
       gsi_leaf_tail t;
-      gsi_fetch_tail(&t, V->leaf + slot);
+      gsi_fetch_tail(&t, gsi_leaf_at(V, slot));
       gsi_blend_store(V, &t, c0, c1, val, ld, q);
     }
   return slot;
@@ -257,7 +257,7 @@ gsi_locate_one(const gsi_view *V, double qx, double qy, int max_steps, double *v
     {
       gsi_rec r;
       double c0, c1;
-      const gsi_leaf *lf = V->leaf + slot;
+      const gsi_leaf *lf = gsi_leaf_at(V, slot);
       gsi_fetch_rec(&r, lf);
       *steps = step + 1;
       const int st = gsi_walk_step(&V->xf, &r, qx, qy, &slot, &c0, &c1);

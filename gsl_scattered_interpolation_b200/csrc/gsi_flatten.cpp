@@ -154,7 +154,9 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   h.delta = prm.delta;
   uint64_t off = align256(sizeof h);
   h.off_dag = off;   off = align256(off + N * sizeof(gsi_rec));
-  h.off_leaf = off;  off = align256(off + L * sizeof(gsi_leaf));
+  const size_t leaf_stride = prm.leaf_stride == 128 ? 128 : sizeof(gsi_leaf);
+  h.leaf_stride = (uint32_t) leaf_stride;
+  h.off_leaf = off;  off = align256(off + L * leaf_stride);
   h.off_z = off;     off = align256(off + std::max<size_t>(1, n) * n_fields * sizeof(double));
   h.off_seeds = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
   h.total_bytes = off;
@@ -163,7 +165,7 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   char *base = image->data();
   std::memcpy(base, &h, sizeof h);
   gsi_rec *dag = (gsi_rec *) (base + h.off_dag);
-  gsi_leaf *leaf = (gsi_leaf *) (base + h.off_leaf);
+  char *leaf_base = base + h.off_leaf;
   double *z = (double *) (base + h.off_z);
 
   /* --- DAG records --------------------------------------------------------------------- */
@@ -240,8 +242,10 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
             tail.g.v[i] = p < 0 ? -1 : vslot_of_row[(size_t) t.shuffle[(size_t) p]];
         }
       tail.g.node = (int32_t) node; /* same offset in both views */
-      leaf[k].r = r;
-      leaf[k].t = tail;
+      gsi_leaf lf;
+      lf.r = r;
+      lf.t = tail;
+      std::memcpy(leaf_base + k * leaf_stride, &lf, sizeof lf);
     }
 
   /* --- values -------------------------------------------------------------------------- */

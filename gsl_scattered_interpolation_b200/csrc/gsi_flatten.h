@@ -14,6 +14,7 @@ struct gsi_flatten_params
   uint32_t grid_g = 0;          /* explicit G (0 = derive from cells_per_leaf) */
   double delta = 3.725290298461914e-09; /* 2^-28: absolute edge margin, standardised units */
   double tau_floor = 9.094947017729282e-13; /* 2^-40 */
+  uint32_t leaf_stride = 96;    /* 96 = packed records, 128 = one 128-byte line per leaf */
 };
 
 /* za: n_fields x n_points, field-major (may be NULL: values left zero).

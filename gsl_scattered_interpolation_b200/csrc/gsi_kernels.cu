@@ -220,7 +220,7 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
                 defer = true;
               else
                 {
-                  const gsi_leaf *lf = V.leaf + cur_slot;
+                  const gsi_leaf *lf = gsi_leaf_at(&V, cur_slot);
                   gsi_rec r;
                   gsi_leaf_tail t;
                   gsi_fetch_rec(&r, lf);

@@ -70,7 +70,7 @@ typedef struct
   uint64_t n_dag;
   uint64_t n_leaves;
   uint32_t grid_g;
-  uint32_t reserved0;
+  uint32_t leaf_stride; /* bytes between leaf records: 96 (packed) or 128 (one cache line each) */
   gsi_xform xf;
   /* grid mapping in standardised coordinates: cell = floor((u - u0) * inv_du) */
   double u0, v0, inv_du, inv_dv;
@@ -85,7 +85,7 @@ typedef struct
 {
   gsi_xform xf;
   const gsi_rec *dag;
-  const gsi_leaf *leaf;
+  const char *leaf; /* gsi_leaf records, leaf_stride bytes apart */
   const double *z;
   const int32_t *seeds;
   double u0, v0, inv_du, inv_dv;
@@ -93,7 +93,19 @@ typedef struct
   int32_t n_fields;
   int32_t n_dag;
   int32_t n_leaves;
+  int32_t leaf_stride;
 } gsi_view;
+
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+static inline
+#endif
+const gsi_leaf *
+gsi_leaf_at(const gsi_view *v, int slot)
+{
+  return (const gsi_leaf *) (v->leaf + (size_t) slot * (size_t) v->leaf_stride);
+}
 
 static inline gsi_view
 gsi_view_of(const void *slab_base, const gsi_slab_header *h)
@@ -102,7 +114,8 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   gsi_view v;
   v.xf = h->xf;
   v.dag = (const gsi_rec *) (b + h->off_dag);
-  v.leaf = (const gsi_leaf *) (b + h->off_leaf);
+  v.leaf = b + h->off_leaf;
+  v.leaf_stride = (int32_t) h->leaf_stride;
   v.z = (const double *) (b + h->off_z);
   v.seeds = (const int32_t *) (b + h->off_seeds);
   v.u0 = h->u0; v.v0 = h->v0; v.inv_du = h->inv_du; v.inv_dv = h->inv_dv;
