@@ -29,6 +29,12 @@ except Exception:
     pass
 
 
+def split_ms(w, launches):
+    """per-launch device time of the fast-path kernel and of the exact-replay kernel"""
+    inf = w.info()
+    return {"locate_ms": 1e3 * inf["locate_seconds"] / launches, "exact_ms": 1e3 * inf["exact_seconds"] / launches}
+
+
 def timed(fn, steps=5, warmup=3):
     st = torch.cuda.Stream(device=DEV)
     for _ in range(warmup):
@@ -47,6 +53,10 @@ def build(xa, ya, za, **params):
     za = np.atleast_2d(za)
     n = len(xa)
     w = g.ScatteredCuda(n, za.shape[0])
+    w.set_param("profile", 1)
+    for kv in filter(None, os.environ.get("GSI_PARAMS", "").split(",")):
+        k, v = kv.split("=")
+        params[k] = float(v)
     for k, v in params.items():
         w.set_param(k, v)
     t0 = time.perf_counter()
@@ -81,7 +91,9 @@ def config2():
     dx = torch.empty(nq, dtype=torch.float64, device=DEV); dy = torch.empty_like(dx)
     dz = torch.empty((F, nq), dtype=torch.float64, device=DEV); dl = torch.empty(nq, dtype=torch.int32, device=DEV)
     w.generate_uniform_device(0, synth.SEED_QUERIES, 0, nq, 0.0, 1.0, 0.0, 1.0, dx.data_ptr(), dy.data_ptr())
+    w.reset_counters()
     ms = timed(lambda s: w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, dz.data_ptr(), nq, dl.data_ptr(), s))
+    sp = split_ms(w, 8)
     bad = verify_arrays(w, dx, dy, nq, F, dz, dl)
     sub = slice(0, 200_000)
     ob = oracle_subsample(w, xa, ya, za, dx[sub].cpu().numpy(), dy[sub].cpu().numpy(),
@@ -94,7 +106,7 @@ def config2():
            "ms": ms, "achieved_GBps": nq * 28 / (ms * 1e-3) / 1e9, "frac_of_hbm": nq * 28 / (ms * 1e-3) / 1e9 / PEAK,
            "host_buffer_pageable_queries_per_s": nq / t_host, "host_build_s": tb, "upload_s": tu,
            "fast_vs_exact_mismatches": bad, "oracle_port_mismatches_on_2e5": ob,
-           "deferred_total": inf["n_deferred"]}
+           "deferred_total": inf["n_deferred"], **sp, "params": os.environ.get("GSI_PARAMS", "")}
     w.free()
     return out
 
@@ -114,6 +126,11 @@ def config3():
     w.reset_counters()
     ms = timed(lambda s: w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, dz.data_ptr(), nq, dl.data_ptr(), s), steps=3, warmup=2)
     inf = w.info()
+    sp = split_ms(w, 5)
+    w.set_param("stats", 1); w.reset_counters()
+    w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, dz.data_ptr(), nq, dl.data_ptr())
+    i2 = w.info(); w.set_param("stats", 0)
+    sp["walk_steps_per_accepted_query"] = i2["n_steps"] / max(1, nq - i2["n_deferred"])
     bad = verify_arrays(w, dx, dy, nq, F, dz, dl)
     sub = slice(0, 200_000)
     ob = oracle_subsample(w, xa, ya, za, xq[sub], yq[sub], dl[sub].cpu().numpy(), dz[:, sub].cpu().numpy())
@@ -124,7 +141,7 @@ def config3():
            "queries_per_s": nq / (ms * 1e-3), "ms": ms, "achieved_GBps": nq * 28 / (ms * 1e-3) / 1e9,
            "frac_of_hbm": nq * 28 / (ms * 1e-3) / 1e9 / PEAK, "deferred_fraction": inf["n_deferred"] / (5 * nq),
            "fraction_in_cage_leaves": cage, "fast_vs_exact_mismatches": bad, "oracle_port_mismatches_on_2e5": ob,
-           "host_build_s": tb, "upload_s": tu}
+           "host_build_s": tb, "upload_s": tu, **sp, "params": os.environ.get("GSI_PARAMS", "")}
     w.free()
     return out
 
@@ -138,8 +155,10 @@ def config4():
     ddx, ddy = (float(xa.max()) - x0) / nx, (float(ya.max()) - y0) / ny
     npx = nx * ny
     dz = torch.empty((F, npx), dtype=torch.float64, device=DEV); dl = torch.empty(npx, dtype=torch.int32, device=DEV)
+    w.reset_counters()
     ms = timed(lambda s: w.eval_raster_device_e(0, x0, ddx, nx, y0, ddy, ny, dz.data_ptr(), dl.data_ptr(), s), steps=3, warmup=2)
     inf = w.info()
+    sp = split_ms(w, 5)
     vz = torch.empty((F, npx), dtype=torch.float64, device=DEV); vl = torch.empty(npx, dtype=torch.int32, device=DEV)
     w.set_param("mode", 1)
     w.eval_raster_device_e(0, x0, ddx, nx, y0, ddy, ny, vz.data_ptr(), vl.data_ptr())
@@ -158,7 +177,7 @@ def config4():
            "pixels_per_s": npx / (ms * 1e-3), "ms": ms, "achieved_GBps": alg / (ms * 1e-3) / 1e9,
            "frac_of_hbm": alg / (ms * 1e-3) / 1e9 / PEAK, "deferred_total": inf["n_deferred"],
            "fast_vs_exact_mismatches": bad, "oracle_port_mismatches_on_subraster": ob, "host_build_s": tb,
-           "upload_s": tu}
+           "upload_s": tu, **sp, "params": os.environ.get("GSI_PARAMS", "")}
     w.free()
     return out
 
