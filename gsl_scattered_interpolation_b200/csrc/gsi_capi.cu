@@ -85,6 +85,8 @@ struct replica
   cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
   unsigned *list = nullptr;
   size_t list_cap = 0;
+  unsigned *ovf_mask = nullptr; /* overflow bitmask, one bit per query of a launch */
+  size_t ovf_words = 0;
   unsigned *counters = nullptr;
   unsigned long long *scratch2 = nullptr; /* 2 x u64 for checksum / compare */
   stage_buf st[2];
@@ -107,11 +109,11 @@ struct gsl_scattered_cuda
   bool built = false, uploaded = false;
   gsi_flatten_params fprm;
   int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
-  int kernel = GSI_KERNEL_WALK, walk_ctas_per_sm = 5;
+  int kernel = GSI_KERNEL_AUTO, walk_ctas_per_sm = 4;
   int l2_fetch = 32; /* cudaLimitMaxL2FetchGranularity: random 32-byte sector gathers */
   size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
-  double list_fraction = 1.0 / 16;
+  double list_fraction = 1.0 / 8;
   size_t host_chunk = (size_t) 1 << 22;
   std::vector<int> devs;
   std::vector<replica *> reps;
@@ -131,6 +133,7 @@ free_replica(replica *r)
   for (auto &p : r->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   if (r->slab && r->owns_slab) cudaFree(r->slab);
   if (r->list) cudaFree(r->list);
+  if (r->ovf_mask) cudaFree(r->ovf_mask);
   if (r->counters) cudaFree(r->counters);
   if (r->scratch2) cudaFree(r->scratch2);
   for (int b = 0; b < 2; b++)
@@ -206,14 +209,26 @@ find_replica(const gsl_scattered_cuda *w, int dev)
 }
 
 int
-ensure_list(replica *r, size_t cap)
+ensure_list(replica *r, size_t cap, size_t per_launch)
 {
-  if (r->list_cap >= cap) return 0;
-  if (r->list) cudaFree(r->list);
-  r->list = nullptr;
-  r->list_cap = 0;
-  CU(cudaMalloc(&r->list, cap * sizeof(unsigned)));
-  r->list_cap = cap;
+  if (r->list_cap < cap)
+    {
+      if (r->list) cudaFree(r->list);
+      r->list = nullptr;
+      r->list_cap = 0;
+      CU(cudaMalloc(&r->list, cap * sizeof(unsigned)));
+      r->list_cap = cap;
+    }
+  const size_t words = (per_launch + 31) / 32;
+  if (r->ovf_words < words)
+    {
+      if (r->ovf_mask) cudaFree(r->ovf_mask);
+      r->ovf_mask = nullptr;
+      r->ovf_words = 0;
+      CU(cudaMalloc(&r->ovf_mask, words * sizeof(unsigned)));
+      CU(cudaMemset(r->ovf_mask, 0, words * sizeof(unsigned))); /* kernels leave it zero */
+      r->ovf_words = words;
+    }
   return 0;
 }
 
@@ -231,6 +246,7 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r)
   c.walk_chunk = w->walk_chunk;
   c.list = r->list;
   c.list_capacity = r->list_cap;
+  c.ovf_mask = r->ovf_mask;
   c.counters = r->counters;
   return c;
 }
@@ -256,7 +272,7 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
       const size_t per_launch = std::min(chunk, nq);
       const size_t want = std::max<size_t>(std::min<size_t>(per_launch, 65536),
                                            (size_t) (w->list_fraction * (double) per_launch));
-      const int s = ensure_list(r, want);
+      const int s = ensure_list(r, want, per_launch);
       if (s) return s;
     }
   gsi_launch_cfg cfg = cfg_of(w, r);
@@ -280,7 +296,7 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
           cfg.ev_exact0 = ev[2]; cfg.ev_exact1 = ev[3];
           r->prof_exact.emplace_back(ev[2], ev[3]);
         }
-      r->n_launches += (w->mode == GSI_MODE_FAST) ? 3 : 1;
+      r->n_launches += (w->mode == GSI_MODE_FAST) ? 4 : 1;
       if (ras)
         e = gsi_launch_eval_raster(r->view, ras->x0, ras->dx, ras->y0, ras->dy, ras->ny,
                                    ras->first + off, n, d_z ? d_z + off : nullptr,
@@ -547,7 +563,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "host_chunk" && value >= 1) w->host_chunk = (size_t) value;
   else if (k == "ctas_per_sm" && value >= 1) w->ctas_per_sm = (int) value;
   else if (k == "profile") w->profile = value != 0;
-  else if (k == "kernel" && (value == 0 || value == 1)) w->kernel = (int) value;
+  else if (k == "kernel" && (value == 0 || value == 1 || value == 2)) w->kernel = (int) value;
   else if (k == "l2_fetch" && (value == 0 || value == 32 || value == 64 || value == 128)) w->l2_fetch = (int) value;
   else if (k == "walk_ctas_per_sm" && value >= 1) w->walk_ctas_per_sm = (int) value;
   else if (k == "walk_chunk" && value >= 0) w->walk_chunk = ((size_t) value + 31) & ~(size_t) 31;

@@ -112,8 +112,10 @@ gsi_blend_store(const gsi_view *V, const gsi_leaf_tail *t, double c0, double c1,
 #if defined(__CUDA_ARCH__)
   if ((F & 3) == 0)
     {
-      /* the F values of a vertex are contiguous and 32-byte aligned: 256-bit gathers */
-#pragma unroll 2
+      /* the F values of a vertex are contiguous and 32-byte aligned: 256-bit gathers
+         (not unrolled: 24 live registers per group is enough latency cover, and the kernels
+         need the occupancy more) */
+#pragma unroll 1
       for (int f = 0; f < F; f += 4)
         {
           unsigned long long a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, x[4] = {0, 0, 0, 0};
@@ -134,7 +136,7 @@ gsi_blend_store(const gsi_view *V, const gsi_leaf_tail *t, double c0, double c1,
       const double2 *pa = reinterpret_cast<const double2 *>(za);
       const double2 *pb = reinterpret_cast<const double2 *>(zb);
       const double2 *px = reinterpret_cast<const double2 *>(zx);
-#pragma unroll 4
+#pragma unroll 1
       for (int f = 0; f < F; f += 2)
         {
           double2 a = make_double2(0, 0), b = a, x = a;

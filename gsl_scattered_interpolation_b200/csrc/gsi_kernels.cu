@@ -27,6 +27,7 @@ namespace
 /* ---- query sources -------------------------------------------------------------------- */
 struct src_arrays
 {
+  static constexpr bool coherent = false; /* arbitrary order: lanes-decoupled kernel by default */
   const double *x, *y;
   __device__ __forceinline__ void get(size_t q, double &qx, double &qy) const
   {
@@ -39,6 +40,7 @@ struct src_arrays
  * two roundings, x outer / y inner, result x-major */
 struct src_raster
 {
+  static constexpr bool coherent = true; /* neighbouring indices are neighbouring points */
   double x0, dx, y0, dy;
   unsigned long long ny, first;
   __device__ __forceinline__ void get(size_t q, double &qx, double &qy) const
@@ -51,7 +53,7 @@ struct src_raster
 
 /* exact replay on every query of a source */
 template <class SRC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_exact_all(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out, size_t ld,
             unsigned *counters)
 {
@@ -67,7 +69,7 @@ k_exact_all(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_o
 
 /* exact replay on the deferred list written by k_locate */
 template <class SRC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_exact_list(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, double *val,
              int *leaf_out, size_t ld, unsigned *counters)
 {
@@ -80,6 +82,33 @@ k_exact_list(const gsi_view V, const SRC src, const unsigned *list, unsigned lis
       src.get(q, qx, qy);
       if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
         atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+    }
+}
+
+/* exact replay of the queries marked in the overflow bitmask (deferred list was full) */
+template <class SRC>
+__global__ void __launch_bounds__(128, 4)
+k_exact_overflow(const gsi_view V, const SRC src, size_t nq, unsigned *mask, double *val,
+                 int *leaf_out, size_t ld, unsigned *counters)
+{
+  if (counters[GSI_CNT_OVERFLOW] == 0) return;
+  const size_t n_words = (nq + 31) >> 5;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t w = (size_t) blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride)
+    {
+      unsigned m = mask[w];
+      if (!m) continue;
+      mask[w] = 0;
+      while (m)
+        {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const size_t q = (w << 5) + (size_t) b;
+          double qx, qy;
+          src.get(q, qx, qy);
+          if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
+            atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+        }
     }
 }
 
@@ -99,30 +128,67 @@ k_seed_cells(const gsi_view V, int32_t *seeds)
     }
 }
 
-/* ---- fast path ----------------------------------------------------------------------------- */
+/* rare: the deferred list is full -- mark the query in the overflow bitmask; k_exact_overflow
+ * resolves the marked queries after the main kernel (no exact replay inside the hot loops) */
+__device__ __forceinline__ void
+mark_overflow(unsigned *mask, size_t q, unsigned *counters)
+{
+  atomicOr(mask + (q >> 5), 1u << (unsigned) (q & 31));
+  atomicAdd(counters + GSI_CNT_OVERFLOW, 1u);
+}
+
+/* ---- fast path, one thread per query (coherent query sets: rasters, sorted queries) --------------
+ * Two phases per batch of 32 queries so that the expensive part stays converged: (1) the walk
+ * (lanes may take different numbers of steps), (2) tail fetch + blend + stores for all accepted
+ * lanes together -- consecutive lanes are consecutive queries, so every store instruction
+ * writes full 32-byte sectors of one output plane. */
 template <class SRC, bool STATS>
-__global__ void __launch_bounds__(GSI_LOCATE_THREADS)
+__global__ void __launch_bounds__(GSI_LOCATE_THREADS, 2)
 k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out, size_t ld,
-         unsigned *list, unsigned list_cap, unsigned *counters, int max_steps)
+         unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters, int max_steps)
 {
   const size_t stride = (size_t) gridDim.x * blockDim.x;
   const unsigned lane = threadIdx.x & 31u;
+  unsigned long long steps_acc = 0;
   /* warp-uniform trip count so the ballot below is always converged */
   for (size_t base = (size_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nq;
        base += stride)
     {
       const size_t q = base + lane;
-      bool defer = false;
+      int status = GSI_STEP_MOVE; /* = not a live query */
+      int slot = 0;
+      double qx = 0, qy = 0, c0 = 0, c1 = 0;
       if (q < nq)
         {
-          double qx, qy;
-          int steps;
           src.get(q, qx, qy);
-          defer = !gsi_locate_one(&V, qx, qy, max_steps, val, leaf_out, ld, q, &steps);
-          if (STATS && !defer)
-            atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS),
-                      (unsigned long long) steps);
+          status = GSI_STEP_DEFER;
+          if (isfinite(qx) && isfinite(qy))
+            {
+              slot = __ldg(V.seeds + gsi_cell_of(&V, qx, qy));
+              for (int step = 0; step < max_steps; step++)
+                {
+                  gsi_rec r;
+                  int at = slot;
+                  gsi_fetch_rec(&r, gsi_leaf_at(&V, at));
+                  const int st = gsi_walk_step(&V.xf, &r, qx, qy, &slot, &c0, &c1);
+                  if (st != GSI_STEP_MOVE)
+                    {
+                      status = st;
+                      slot = at;
+                      if (STATS && st == GSI_STEP_ACCEPT) steps_acc += (unsigned) step + 1u;
+                      break;
+                    }
+                }
+            }
         }
+      if (status == GSI_STEP_ACCEPT)
+        {
+          gsi_leaf_tail t;
+          gsi_fetch_tail(&t, gsi_leaf_at(&V, slot));
+          if (leaf_out) leaf_out[q] = t.g.node;
+          if (val) gsi_blend_store(&V, &t, c0, c1, val, ld, q);
+        }
+      const bool defer = status == GSI_STEP_DEFER;
       /* warp-aggregated append to the deferred list */
       const unsigned mask = __ballot_sync(0xffffffffu, defer);
       if (mask)
@@ -134,28 +200,16 @@ k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out,
           pos = __shfl_sync(0xffffffffu, pos, leader);
           if (defer)
             {
-              const unsigned slot = pos + __popc(mask & ((1u << lane) - 1u));
-              if (slot < list_cap)
-                list[slot] = (unsigned) q;
+              const unsigned at = pos + __popc(mask & ((1u << lane) - 1u));
+              if (at < list_cap)
+                list[at] = (unsigned) q;
               else
-                {
-                  /* list full (far more deferred queries than budgeted): resolve in place */
-                  double qx, qy;
-                  src.get(q, qx, qy);
-                  if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
-                    atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
-                }
+                mark_overflow(ovf_mask, q, counters);
             }
         }
     }
-}
-
-/* rare: the deferred list is full; kept out of line so it does not inflate the hot loop */
-__device__ __noinline__ void
-exact_in_place(const gsi_view &V, double qx, double qy, double *val, int *leaf_out, size_t ld,
-               size_t q, unsigned *counters)
-{
-  if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0) atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+  if (STATS && steps_acc)
+    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
 }
 
 /* ---- fast path, lanes decoupled from queries -------------------------------------------------
@@ -167,9 +221,10 @@ exact_in_place(const gsi_view &V, double qx, double qy, double *val, int *leaf_o
  * being loaded) and `nxt` (seed cell being loaded) -- so the only exposed latency per iteration
  * is the leaf fetch itself. */
 template <class SRC, bool STATS, bool ONE_FIELD>
-__global__ void __launch_bounds__(GSI_WALK_THREADS)
+__global__ void __launch_bounds__(GSI_WALK_THREADS, 4)
 k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
-       size_t ld, unsigned *list, unsigned list_cap, unsigned *counters, int max_steps)
+       size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
+       int max_steps)
 {
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
@@ -265,7 +320,7 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
                   if (at < list_cap)
                     list[at] = (unsigned) q;
                   else
-                    exact_in_place(V, cur_x, cur_y, val, leaf_out, ld, q, counters);
+                    mark_overflow(ovf_mask, q, counters);
                 }
             }
         }
@@ -340,6 +395,7 @@ k_accumulate_deferred(unsigned *counters)
   const unsigned c = counters[GSI_CNT_DEFERRED];
   unsigned long long *tot = reinterpret_cast<unsigned long long *>(counters + GSI_CNT_DEFERRED_TOTAL);
   *tot += c;
+  counters[GSI_CNT_OVERFLOW] = 0;
 }
 
 inline int
@@ -369,7 +425,7 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   cudaError_t e = cudaMemsetAsync(cfg.counters + GSI_CNT_DEFERRED, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   if (cfg.ev_locate0) cudaEventRecord(cfg.ev_locate0, st);
-  if (cfg.kernel == GSI_KERNEL_WALK)
+  if (cfg.kernel == GSI_KERNEL_WALK || (cfg.kernel == GSI_KERNEL_AUTO && !SRC::coherent))
     {
       const int ctas = cfg.sm_count * cfg.walk_ctas_per_sm;
       const size_t n_warps = (size_t) ctas * (GSI_WALK_THREADS / 32);
@@ -384,8 +440,8 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
                                : (size_t) ctas);
 #define GSI_LAUNCH_WALK(STATS, ONE)                                                             \
   k_walk<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out,  \
-                                                          ld, cfg.list, list_cap, cfg.counters,      \
-                                                          cfg.max_steps)
+                                                          ld, cfg.list, list_cap, cfg.ovf_mask,      \
+                                                          cfg.counters, cfg.max_steps)
       if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALK(true, true);
       else if (cfg.stats) GSI_LAUNCH_WALK(true, false);
       else if (V.n_fields == 1) GSI_LAUNCH_WALK(false, true);
@@ -395,17 +451,20 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   else if (cfg.stats)
     k_locate<SRC, true><<<grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
                           GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list, list_cap,
-                                                       cfg.counters, cfg.max_steps);
+                                                       cfg.ovf_mask, cfg.counters, cfg.max_steps);
   else
     k_locate<SRC, false><<<grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
                            GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list,
-                                                        list_cap, cfg.counters, cfg.max_steps);
+                                                        list_cap, cfg.ovf_mask, cfg.counters,
+                                                        cfg.max_steps);
   if (cfg.ev_locate1) cudaEventRecord(cfg.ev_locate1, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (cfg.ev_exact0) cudaEventRecord(cfg.ev_exact0, st);
   k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld,
                                                       cfg.counters);
+  k_exact_overflow<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, nq, cfg.ovf_mask, val, leaf_out, ld,
+                                                          cfg.counters);
   if (cfg.ev_exact1) cudaEventRecord(cfg.ev_exact1, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -16,13 +16,15 @@
 #define GSI_CNT_OUTSIDE 1        /* u32: queries outside the cage since the last reset */
 #define GSI_CNT_DEFERRED_TOTAL 2 /* u64: deferred queries since the last reset */
 #define GSI_CNT_STEPS 4          /* u64: walk steps of accepted queries (stats launches only) */
+#define GSI_CNT_OVERFLOW 8       /* u32: deferred queries of the current launch that did not fit the list */
 #define GSI_CNT_WORDS 16
 
 #define GSI_MODE_FAST 0  /* grid-seeded walk + exact replay of the deferred queries */
 #define GSI_MODE_EXACT 1 /* exact DAG replay on every query */
 
 #define GSI_KERNEL_WALK 0   /* k_walk: lanes decoupled from queries (default) */
-#define GSI_KERNEL_SIMPLE 1 /* k_locate: one thread per query, kept for A/B measurements */
+#define GSI_KERNEL_SIMPLE 1 /* k_locate: one thread per query, two-phase (coherent query sets) */
+#define GSI_KERNEL_AUTO 2   /* k_walk for query arrays, k_locate for rasters (default) */
 
 struct gsi_launch_cfg
 {
@@ -31,11 +33,12 @@ struct gsi_launch_cfg
   int max_steps = 256;
   int sm_count = 148;
   int locate_ctas_per_sm = 8;
-  int kernel = GSI_KERNEL_WALK;
+  int kernel = GSI_KERNEL_AUTO;
   int walk_ctas_per_sm = 5;
   size_t walk_chunk = 0; /* 0 = derive from the launch size */
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
-  size_t list_capacity = 0;     /* deferred-list entries; overflow is resolved in place */
+  size_t list_capacity = 0;     /* deferred-list entries; overflow goes to the bitmask */
+  unsigned *ovf_mask = nullptr; /* one bit per query of a launch (zero between launches) */
   unsigned *counters = nullptr; /* GSI_CNT_WORDS words */
   /* optional profiling events recorded around the two kernels of a launch */
   cudaEvent_t ev_locate0 = nullptr, ev_locate1 = nullptr, ev_exact0 = nullptr, ev_exact1 = nullptr;
