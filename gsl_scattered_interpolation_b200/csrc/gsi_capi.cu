@@ -251,56 +251,77 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r)
   return c;
 }
 
-/* chunked launch of the locate+blend kernels on device arrays (src == NULL: raster) */
+/* a block of whole raster columns: pixel (i, j), i in [i_first, i_first + n_cols), j in [0, ny) */
 struct raster_spec
 {
   double x0, dx, y0, dy;
   size_t ny;
-  size_t first; /* absolute index of the first pixel */
+  size_t i_first, n_cols;
 };
 
+int
+prepare_launch(const gsl_scattered_cuda *w, replica *r, size_t per_launch, cudaEvent_t ev[4],
+               gsi_launch_cfg *cfg)
+{
+  *cfg = cfg_of(w, r);
+  if (w->profile)
+    {
+      for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ev[i]));
+      if (w->mode == GSI_MODE_FAST)
+        {
+          cfg->ev_locate0 = ev[0]; cfg->ev_locate1 = ev[1];
+          r->prof_locate.emplace_back(ev[0], ev[1]);
+        }
+      else
+        {
+          cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+        }
+      cfg->ev_exact0 = ev[2]; cfg->ev_exact1 = ev[3];
+      r->prof_exact.emplace_back(ev[2], ev[3]);
+    }
+  r->n_launches += (w->mode == GSI_MODE_FAST) ? 4 : 1;
+  (void) per_launch;
+  return 0;
+}
+
+/* chunked launch of the locate+blend kernels on device data: either query arrays (ras == NULL)
+ * or a block of raster columns.  d_z / d_leaf point at the first query / pixel of the block. */
 int
 eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const double *d_y,
                const raster_spec *ras, size_t nq, double *d_z, size_t ld, int *d_leaf,
                cudaStream_t st)
 {
   if (nq == 0) return 0;
-  const size_t chunk = std::max<size_t>(1, std::min(w->chunk, (size_t) 0xfffffff0u));
+  size_t chunk = std::max<size_t>(1, std::min(w->chunk, (size_t) 0xfffffff0u));
+  size_t cols_per_chunk = 0;
+  if (ras)
+    {
+      if (ras->ny == 0 || ras->ny > (size_t) 0xfffffff0u) GSI_ERROR("raster column too long", GSL_SCATTERED_EINVAL);
+      cols_per_chunk = std::max<size_t>(1, chunk / ras->ny);
+      chunk = cols_per_chunk * ras->ny;
+    }
   if (w->mode == GSI_MODE_FAST)
     {
-      /* deferred list: a fraction of the launch size (overflow is resolved in place) */
+      /* deferred list: a fraction of the launch size (overflow goes to a bitmask) */
       const size_t per_launch = std::min(chunk, nq);
       const size_t want = std::max<size_t>(std::min<size_t>(per_launch, 65536),
                                            (size_t) (w->list_fraction * (double) per_launch));
       const int s = ensure_list(r, want, per_launch);
       if (s) return s;
     }
-  gsi_launch_cfg cfg = cfg_of(w, r);
   for (size_t off = 0; off < nq; off += chunk)
     {
       const size_t n = std::min(chunk, nq - off);
+      gsi_launch_cfg cfg;
+      cudaEvent_t ev[4];
+      const int s = prepare_launch(w, r, n, ev, &cfg);
+      if (s) return s;
       cudaError_t e;
-      if (w->profile)
-        {
-          cudaEvent_t ev[4];
-          for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ev[i]));
-          if (w->mode == GSI_MODE_FAST)
-            {
-              cfg.ev_locate0 = ev[0]; cfg.ev_locate1 = ev[1];
-              r->prof_locate.emplace_back(ev[0], ev[1]);
-            }
-          else
-            {
-              cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
-            }
-          cfg.ev_exact0 = ev[2]; cfg.ev_exact1 = ev[3];
-          r->prof_exact.emplace_back(ev[2], ev[3]);
-        }
-      r->n_launches += (w->mode == GSI_MODE_FAST) ? 4 : 1;
       if (ras)
         e = gsi_launch_eval_raster(r->view, ras->x0, ras->dx, ras->y0, ras->dy, ras->ny,
-                                   ras->first + off, n, d_z ? d_z + off : nullptr,
-                                   d_leaf ? d_leaf + off : nullptr, ld, cfg, st);
+                                   ras->i_first + off / ras->ny, n / ras->ny,
+                                   d_z ? d_z + off : nullptr, d_leaf ? d_leaf + off : nullptr, ld,
+                                   cfg, st);
       else
         e = gsi_launch_eval_arrays(r->view, d_x + off, d_y + off, n, d_z ? d_z + off : nullptr,
                                    d_leaf ? d_leaf + off : nullptr, ld, cfg, st);
@@ -356,7 +377,9 @@ eval_host_slice(const gsl_scattered_cuda *w, replica *r, const double *xq, const
   std::lock_guard<std::mutex> lock(r->mu);
   CU(cudaSetDevice(r->dev));
   const size_t F = w->n_fields;
-  const size_t C = std::max<size_t>(1, std::min(w->host_chunk, nq));
+  size_t C = std::max<size_t>(1, std::min(w->host_chunk, nq));
+  if (ras) C = std::max<size_t>(1, w->host_chunk / ras->ny) * ras->ny; /* whole columns */
+  if (C > nq) C = nq;
   int s = ensure_stage(r, C, F);
   if (s) return s;
   unsigned c0[GSI_CNT_WORDS], c1[GSI_CNT_WORDS];
@@ -379,7 +402,8 @@ eval_host_slice(const gsl_scattered_cuda *w, replica *r, const double *xq, const
       if (ras)
         {
           rs = *ras;
-          rs.first += off;
+          rs.i_first += off / ras->ny;
+          rs.n_cols = n / ras->ny;
         }
       s = eval_on_device(w, r, b.x, b.y, ras ? &rs : nullptr, n, zq ? b.z : nullptr, C,
                          leaf ? b.leaf : nullptr, r->s_k);
@@ -412,12 +436,17 @@ eval_host(const gsl_scattered_cuda *w, const double *xq, const double *yq, const
   std::vector<int> status(R, 0);
   std::vector<unsigned> outside(R, 0);
   auto run = [&](size_t i) {
-    const size_t q0 = nq * i / R, q1 = nq * (i + 1) / R;
+    size_t q0 = nq * i / R, q1 = nq * (i + 1) / R;
     raster_spec rs;
     if (ras)
       {
+        /* split a raster by whole columns */
+        const size_t c0 = ras->n_cols * i / R, c1 = ras->n_cols * (i + 1) / R;
         rs = *ras;
-        rs.first += q0;
+        rs.i_first += c0;
+        rs.n_cols = c1 - c0;
+        q0 = c0 * ras->ny;
+        q1 = c1 * ras->ny;
       }
     status[i] = eval_host_slice(w, w->reps[i], ras ? nullptr : xq + q0, ras ? nullptr : yq + q0,
                                 ras ? &rs : nullptr, q1 - q0, zq ? zq + q0 : nullptr, nq,
@@ -712,7 +741,7 @@ gsl_scattered_cuda_eval_raster_e(const gsl_scattered_cuda *w, double x0, double 
 {
   if (nx && ny && nx > std::numeric_limits<size_t>::max() / ny)
     GSI_ERROR("raster too large", GSL_SCATTERED_EINVAL);
-  raster_spec rs{x0, dx, y0, dy, ny, 0};
+  raster_spec rs{x0, dx, y0, dy, ny, 0, nx};
   return eval_host(w, nullptr, nullptr, &rs, nx * ny, zq, leaf);
 }
 
@@ -755,7 +784,7 @@ gsl_scattered_cuda_eval_raster_device_e(const gsl_scattered_cuda *w, int dev, do
   std::lock_guard<std::mutex> lock(r->mu);
   CU(cudaSetDevice(dev));
   cudaStream_t st = stream ? (cudaStream_t) stream : r->s_k;
-  raster_spec rs{x0, dx, y0, dy, ny, 0};
+  raster_spec rs{x0, dx, y0, dy, ny, 0, nx};
   unsigned c0[GSI_CNT_WORDS], c1[GSI_CNT_WORDS];
   int s;
   if (!stream && (s = read_counters(r, c0))) return s;

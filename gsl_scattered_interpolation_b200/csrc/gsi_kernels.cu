@@ -24,30 +24,65 @@
 namespace
 {
 
-/* ---- query sources -------------------------------------------------------------------- */
+/* ---- query sources --------------------------------------------------------------------
+ * get(t, q, x, y): launch index t -> output index q and coordinates; false = padding (no query).
+ * n_launch(nq)   : number of launch indices needed to cover nq queries. */
 struct src_arrays
 {
   static constexpr bool coherent = false; /* arbitrary order: lanes-decoupled kernel by default */
   const double *x, *y;
-  __device__ __forceinline__ void get(size_t q, double &qx, double &qy) const
+  __device__ __forceinline__ bool get(size_t t, size_t &q, double &qx, double &qy) const
+  {
+    q = t;
+    qx = __ldg(x + t);
+    qy = __ldg(y + t);
+    return true;
+  }
+  __device__ __forceinline__ void get_linear(size_t q, double &qx, double &qy) const
   {
     qx = __ldg(x + q);
     qy = __ldg(y + q);
   }
+  __host__ __device__ size_t n_launch(size_t nq) const { return nq; }
 };
 
 /* the reference's raster driver, scattered_interp_example.c:184-199: x = min + step*i with
- * two roundings, x outer / y inner, result x-major */
+ * two roundings, x outer / y inner, result x-major (pixel = i*ny + j).  A launch covers the
+ * columns [i_first, i_first + n_cols); launch indices enumerate 8 x 32 pixel tiles (8 columns
+ * x 32 consecutive rows) so that a 256-thread CTA works on a compact patch of the plane
+ * (leaf and value lines are reused from L1) while every warp still writes 32 consecutive
+ * pixels of one column (full-sector stores). */
 struct src_raster
 {
   static constexpr bool coherent = true; /* neighbouring indices are neighbouring points */
   double x0, dx, y0, dy;
-  unsigned long long ny, first;
-  __device__ __forceinline__ void get(size_t q, double &qx, double &qy) const
+  unsigned long long ny, i_first, n_cols;
+  __device__ __forceinline__ void coords(unsigned long long i, unsigned long long j, double &qx,
+                                         double &qy) const
   {
-    const unsigned long long p = first + q, i = p / ny, j = p - i * ny;
-    qx = __dadd_rn(x0, __dmul_rn(dx, (double) i));
+    qx = __dadd_rn(x0, __dmul_rn(dx, (double) (i_first + i)));
     qy = __dadd_rn(y0, __dmul_rn(dy, (double) j));
+  }
+  __device__ __forceinline__ bool get(size_t t, size_t &q, double &qx, double &qy) const
+  {
+    const unsigned long long tiles_j = (ny + 31) >> 5;
+    const unsigned long long tile = t >> 8, within = t & 255;
+    const unsigned long long ti = tile / tiles_j, tj = tile - ti * tiles_j;
+    const unsigned long long i = (ti << 3) + (within >> 5), j = (tj << 5) + (within & 31);
+    if (i >= n_cols || j >= ny) return false;
+    q = i * ny + j;
+    coords(i, j, qx, qy);
+    return true;
+  }
+  __device__ __forceinline__ void get_linear(size_t q, double &qx, double &qy) const
+  {
+    const unsigned long long i = q / ny, j = q - i * ny;
+    coords(i, j, qx, qy);
+  }
+  __host__ __device__ size_t n_launch(size_t nq) const
+  {
+    (void) nq;
+    return (size_t) (((n_cols + 7) >> 3) * ((ny + 31) >> 5)) << 8;
   }
 };
 
@@ -61,7 +96,7 @@ k_exact_all(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_o
   for (size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride)
     {
       double qx, qy;
-      src.get(q, qx, qy);
+      src.get_linear(q, qx, qy);
       if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
         atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
     }
@@ -79,7 +114,7 @@ k_exact_list(const gsi_view V, const SRC src, const unsigned *list, unsigned lis
     {
       const size_t q = list[t];
       double qx, qy;
-      src.get(q, qx, qy);
+      src.get_linear(q, qx, qy);
       if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
         atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
     }
@@ -105,7 +140,7 @@ k_exact_overflow(const gsi_view V, const SRC src, size_t nq, unsigned *mask, dou
           m &= m - 1;
           const size_t q = (w << 5) + (size_t) b;
           double qx, qy;
-          src.get(q, qx, qy);
+          src.get_linear(q, qx, qy);
           if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
             atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
         }
@@ -151,16 +186,17 @@ k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out,
   const unsigned lane = threadIdx.x & 31u;
   unsigned long long steps_acc = 0;
   /* warp-uniform trip count so the ballot below is always converged */
-  for (size_t base = (size_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nq;
+  const size_t n_launch = src.n_launch(nq);
+  for (size_t base = (size_t) blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_launch;
        base += stride)
     {
-      const size_t q = base + lane;
+      const size_t t = base + lane;
+      size_t q = 0;
       int status = GSI_STEP_MOVE; /* = not a live query */
       int slot = 0;
       double qx = 0, qy = 0, c0 = 0, c1 = 0;
-      if (q < nq)
+      if (t < n_launch && src.get(t, q, qx, qy))
         {
-          src.get(q, qx, qy);
           status = GSI_STEP_DEFER;
           if (isfinite(qx) && isfinite(qy))
             {
@@ -181,6 +217,10 @@ k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out,
                 }
             }
         }
+      /* independent thread scheduling does not promise that the lanes which left the walk early
+         wait here for the others: without this barrier phase 2 runs several times with partial
+         lane masks (measured: 15 of 32 lanes active on average) */
+      __syncwarp();
       if (status == GSI_STEP_ACCEPT)
         {
           gsi_leaf_tail t;
@@ -261,7 +301,7 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
               if (nn_v)
                 {
                   nn_q = off;
-                  src.get(q0 + off, nn_x, nn_y);
+                  src.get_linear(q0 + off, nn_x, nn_y);
                 }
             }
           next += __popc(take);
@@ -449,11 +489,11 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
 #undef GSI_LAUNCH_WALK
     }
   else if (cfg.stats)
-    k_locate<SRC, true><<<grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
+    k_locate<SRC, true><<<grid_for(src.n_launch(nq), GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
                           GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list, list_cap,
                                                        cfg.ovf_mask, cfg.counters, cfg.max_steps);
   else
-    k_locate<SRC, false><<<grid_for(nq, GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
+    k_locate<SRC, false><<<grid_for(src.n_launch(nq), GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
                            GSI_LOCATE_THREADS, 0, st>>>(V, src, nq, val, leaf_out, ld, cfg.list,
                                                         list_cap, cfg.ovf_mask, cfg.counters,
                                                         cfg.max_steps);
@@ -484,10 +524,11 @@ gsi_launch_eval_arrays(const gsi_view &V, const double *xq, const double *yq, si
 
 cudaError_t
 gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, double y0, double dy,
-                       unsigned long long ny, size_t q_first, size_t nq, double *val,
-                       int *leaf_out, size_t ld, const gsi_launch_cfg &cfg, cudaStream_t st)
+                       unsigned long long ny, unsigned long long i_first, unsigned long long n_cols,
+                       double *val, int *leaf_out, size_t ld, const gsi_launch_cfg &cfg,
+                       cudaStream_t st)
 {
-  return launch_eval(V, src_raster{x0, dx, y0, dy, ny, (unsigned long long) q_first}, nq, val,
+  return launch_eval(V, src_raster{x0, dx, y0, dy, ny, i_first, n_cols}, (size_t) (n_cols * ny), val,
                      leaf_out, ld, cfg, st);
 }
 

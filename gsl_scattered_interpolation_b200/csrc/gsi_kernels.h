@@ -50,12 +50,12 @@ cudaError_t gsi_launch_eval_arrays(const gsi_view &V, const double *xq, const do
                                    size_t nq, double *val, int *leaf_out, size_t ld,
                                    const gsi_launch_cfg &cfg, cudaStream_t st);
 
-/* same for pixels [q_first, q_first+nq) of an nx x ny raster (x-major, pixel = i*ny + j);
- * val / leaf_out point at pixel q_first */
+/* same for the columns [i_first, i_first + n_cols) of an nx x ny raster (x-major, pixel =
+ * i*ny + j); val / leaf_out point at pixel i_first*ny */
 cudaError_t gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, double y0, double dy,
-                                   unsigned long long ny, size_t q_first, size_t nq, double *val,
-                                   int *leaf_out, size_t ld, const gsi_launch_cfg &cfg,
-                                   cudaStream_t st);
+                                   unsigned long long ny, unsigned long long i_first,
+                                   unsigned long long n_cols, double *val, int *leaf_out, size_t ld,
+                                   const gsi_launch_cfg &cfg, cudaStream_t st);
 
 cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count,
                                   cudaStream_t st);

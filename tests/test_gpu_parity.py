@@ -238,6 +238,26 @@ def test_sixteen_fields_raster_vs_port():
     w.free()
 
 
+@pytest.mark.parametrize("kernel", [0, 1, 2])
+def test_raster_odd_shapes_and_chunking(golden, kernel):
+    """rasters whose sides are not multiples of the 8 x 32 launch tile, evaluated in several
+    device launches and several host pipeline stages, with every kernel variant"""
+    xa, ya = synth.uniform_nodes(1000)
+    za = synth.values(1000, 4)
+    w = make(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000), kernel=kernel,
+             chunk=700, host_chunk=300)
+    port = refimpl.PortTree({k: golden["cfg1_" + k] for k in
+                             ("pts3", "lnk3", "type", "shuffle", "shift", "scale", "seed_points")}, xa, ya)
+    for nx, ny in [(37, 53), (1, 100), (100, 1), (9, 33), (64, 64)]:
+        x0, y0, dx, dy = -0.05, 0.02, 1.1 / nx, 0.97 / ny
+        st, rz, rl = w.eval_raster_e(x0, dx, nx, y0, dy, ny)
+        gx, gy = x0 + dx * np.arange(nx), y0 + dy * np.arange(ny)
+        pl, pv, _ = port.eval(np.repeat(gx, ny), np.tile(gy, nx), za)
+        assert np.array_equal(rl.ravel(), pl), (nx, ny)
+        assert refimpl.same_bits(rz.reshape(4, -1), pv), (nx, ny)
+    w.free()
+
+
 def test_init_from_reference_tree_and_slab_replication(golden):
     """true drop-in: adopt the arrays of a tree built by the reference's simplex_tree_init;
     then replicate the device slab into a second workspace"""
