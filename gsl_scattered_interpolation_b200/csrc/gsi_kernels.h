@@ -10,6 +10,8 @@
 
 #define GSI_LOCATE_THREADS 256
 #define GSI_WALK_THREADS 128
+#define GSI_STAGE_THREADS 128
+#define GSI_STAGE_WINDOW 256
 
 /* device counters (unsigned[16]) */
 #define GSI_CNT_DEFERRED 0       /* u32: length of the deferred list of the current launch */
@@ -25,6 +27,7 @@
 #define GSI_KERNEL_WALK 0   /* k_walk: lanes decoupled from queries (default) */
 #define GSI_KERNEL_SIMPLE 1 /* k_locate: one thread per query, two-phase (coherent query sets) */
 #define GSI_KERNEL_AUTO 2   /* k_walk for query arrays, k_locate for rasters (default) */
+#define GSI_KERNEL_STAGE 3  /* k_stage: decoupled walk staged in shared memory + converged blend */
 
 struct gsi_launch_cfg
 {

@@ -238,7 +238,34 @@ def test_sixteen_fields_raster_vs_port():
     w.free()
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2])
+@pytest.mark.parametrize("kernel", [0, 1, 3])
+def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel):
+    """k_walk (0), k_locate (1) and k_stage (3) on config 1 (1 field) and the config-3 mix (3 fields)"""
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
+             kernel=kernel)
+    xq, yq = synth.uniform_queries(10000)
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq, golden["cfg1_val"])
+    # queries only, values only
+    st, zq, _ = w.eval_e(xq, yq, want_leaf=False)
+    assert refimpl.same_bits(zq, golden["cfg1_val"])
+    st, _, leaf = w.eval_e(xq, yq, want_values=False)
+    assert np.array_equal(leaf, golden["cfg1_leaf"])
+    w.free()
+    n = 3000
+    xa, ya = synth.clustered_nodes(n)
+    w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), kernel=kernel)
+    xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
+    xq[:3] = [np.nan, np.inf, 1e300]                    # non-finite / outside the cage
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert st == g.EDOM and leaf[2] == -1
+    assert np.array_equal(leaf[3:], golden["cfg3_leaf"][3:])
+    assert refimpl.same_bits(zq[:, 3:], golden["cfg3_val"][:, 3:])
+    w.free()
+
+
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
 def test_raster_odd_shapes_and_chunking(golden, kernel):
     """rasters whose sides are not multiples of the 8 x 32 launch tile, evaluated in several
     device launches and several host pipeline stages, with every kernel variant"""
