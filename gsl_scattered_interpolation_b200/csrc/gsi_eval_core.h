@@ -112,9 +112,34 @@ gsi_blend_store(const gsi_view *V, const gsi_leaf_tail *t, double c0, double c1,
 #if defined(__CUDA_ARCH__)
   if ((F & 3) == 0)
     {
-      /* the F values of a vertex are contiguous and 32-byte aligned: 256-bit gathers
-         (not unrolled: 24 live registers per group is enough latency cover, and the kernels
-         need the occupancy more) */
+      /* the F values of a vertex are contiguous and 32-byte aligned: 256-bit gathers */
+      double *out = val + q;
+      if (ha & hb & hx)
+        {
+          /* common case (no cage vertex): straight-line code, same operations as gsi_blend:
+             ((0 + c0*za) + c1*zb) + (1 - (c0 + c1))*zx.  Not unrolled: measured on the 8192^2 x
+             16-field raster, occupancy (78 vs 92 registers) beats a second group of loads in
+             flight (3.99 ms vs 4.61 ms). */
+          const double w2 = GSI_SUB(1.0, GSI_ADD(GSI_ADD(0.0, c0), c1));
+#pragma unroll 1
+          for (int f = 0; f < F; f += 4)
+            {
+              unsigned long long a[4], b[4], x[4];
+              gsi_ld256(za + f, a[0], a[1], a[2], a[3]);
+              gsi_ld256(zb + f, b[0], b[1], b[2], b[3]);
+              gsi_ld256(zx + f, x[0], x[1], x[2], x[3]);
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                {
+                  double v = GSI_ADD(0.0, GSI_MUL(c0, __longlong_as_double((long long) a[k])));
+                  v = GSI_ADD(v, GSI_MUL(c1, __longlong_as_double((long long) b[k])));
+                  v = GSI_ADD(v, GSI_MUL(w2, __longlong_as_double((long long) x[k])));
+                  *out = v;
+                  out += ld;
+                }
+            }
+          return;
+        }
 #pragma unroll 1
       for (int f = 0; f < F; f += 4)
         {
@@ -124,10 +149,12 @@ gsi_blend_store(const gsi_view *V, const gsi_leaf_tail *t, double c0, double c1,
           if (hx) gsi_ld256(zx + f, x[0], x[1], x[2], x[3]);
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            val[(size_t) (f + k) * ld + q] =
-                gsi_blend(c0, c1, ha, __longlong_as_double((long long) a[k]), hb,
-                          __longlong_as_double((long long) b[k]), hx,
-                          __longlong_as_double((long long) x[k]));
+            {
+              *out = gsi_blend(c0, c1, ha, __longlong_as_double((long long) a[k]), hb,
+                               __longlong_as_double((long long) b[k]), hx,
+                               __longlong_as_double((long long) x[k]));
+              out += ld;
+            }
         }
       return;
     }

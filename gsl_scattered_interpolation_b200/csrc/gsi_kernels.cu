@@ -192,7 +192,7 @@ mark_overflow(unsigned *mask, size_t q, unsigned *counters)
  * lanes together -- consecutive lanes are consecutive queries, so every store instruction
  * writes full 32-byte sectors of one output plane. */
 template <class SRC, bool STATS>
-__global__ void __launch_bounds__(GSI_LOCATE_THREADS, 2)
+__global__ void __launch_bounds__(GSI_LOCATE_THREADS, 4)
 k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out, size_t ld,
          unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters, int max_steps)
 {
