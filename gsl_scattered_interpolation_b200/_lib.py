@@ -11,6 +11,8 @@ from ctypes import (POINTER, c_char_p, c_double, c_int, c_size_t, c_ulong, c_ulo
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgsl_scattered_cuda.so")
+# A/B experiments only (scripts/): load another build of the same library
+LIB_PATH = os.environ.get("GSI_LIB_PATH", LIB_PATH)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gsl_scattered_cuda.h")
 
 SUCCESS, EDOM, EINVAL, EFAILED, ENOMEM, EBADLEN = 0, 1, 4, 5, 8, 19
@@ -25,6 +27,7 @@ class Info(ctypes.Structure):
         ("upload_seconds", c_double), ("n_deferred", c_ulonglong), ("n_outside", c_ulonglong),
         ("n_steps", c_ulonglong), ("n_kernel_launches", c_ulonglong),
         ("locate_seconds", c_double), ("exact_seconds", c_double),
+        ("n_reordered", c_ulonglong),
     ]
 
 

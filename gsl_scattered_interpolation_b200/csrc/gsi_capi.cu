@@ -91,10 +91,12 @@ struct replica
   unsigned long long *scratch2 = nullptr; /* 2 x u64 for checksum / compare */
   stage_buf st[2];
   size_t st_cap = 0, st_fields = 0;
+  gsi_reorder_scratch ro; /* reorder pipeline scratch (lazily sized) */
+  size_t ro_fields = 0, ro_off_entries = 0;
   /* profiling (param "profile"): timed event pairs around every kernel launch */
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_locate, prof_exact;
   double locate_seconds = 0, exact_seconds = 0;
-  unsigned long long n_launches = 0;
+  unsigned long long n_launches = 0, n_reordered = 0;
   std::mutex mu;
 };
 
@@ -111,6 +113,13 @@ struct gsl_scattered_cuda
   int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
   int kernel = GSI_KERNEL_AUTO, walk_ctas_per_sm = 4;
   int l2_fetch = 32; /* cudaLimitMaxL2FetchGranularity: random 32-byte sector gathers */
+  /* reorder pipeline (gsi_kernels.cu): 0 = off (default: measured slower than the direct walk on
+     B200), 1 = always for query arrays, 2 = auto (large batches of few
+     fields on a triangulation whose fast-path structure exceeds the L2) */
+  int reorder = 0;
+  size_t reorder_window = (size_t) 1 << 27, reorder_min = (size_t) 1 << 22;
+  int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_shift = -1, tile_ranges = 4, tile_leaves = 1024;
+  size_t reorder_max_fields = 2;
   size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
   double list_fraction = 1.0 / 8;
@@ -125,6 +134,20 @@ namespace
 {
 
 void
+free_reorder(replica *r)
+{
+  gsi_reorder_scratch &o = r->ro;
+  if (o.bx) cudaFree(o.bx);
+  if (o.by) cudaFree(o.by);
+  if (o.bi) cudaFree(o.bi);
+  if (o.off) cudaFree(o.off);
+  if (o.zb) cudaFree(o.zb);
+  if (o.lb) cudaFree(o.lb);
+  o = gsi_reorder_scratch();
+  r->ro_fields = r->ro_off_entries = 0;
+}
+
+void
 free_replica(replica *r)
 {
   if (!r) return;
@@ -136,6 +159,7 @@ free_replica(replica *r)
   if (r->ovf_mask) cudaFree(r->ovf_mask);
   if (r->counters) cudaFree(r->counters);
   if (r->scratch2) cudaFree(r->scratch2);
+  free_reorder(r);
   for (int b = 0; b < 2; b++)
     {
       stage_buf &s = r->st[b];
@@ -251,6 +275,87 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r)
   return c;
 }
 
+/* Does a batch of nq incoherent queries go through the reorder pipeline? */
+bool
+want_reorder(const gsl_scattered_cuda *w, size_t nq)
+{
+  if (w->mode != GSI_MODE_FAST || w->reorder == 0 || nq == 0) return false;
+  if (w->reorder == 1) return true;
+  return nq >= w->reorder_min && w->n_fields <= w->reorder_max_fields && w->hdr.n_leaves >= 32768;
+}
+
+/* tile geometry of the reorder pipeline: tiles of 2^shift x 2^shift seed-grid cells holding
+ * about tile_leaves leaves each (one tile's leaf records + seed cells should fit an SM's L1),
+ * Morton id with at most GSI_TILE_BITS_MAX bits per axis */
+void
+tile_geometry(const gsl_scattered_cuda *w, int *shift, int *bits)
+{
+  const double G = (double) std::max<uint32_t>(1, w->hdr.grid_g);
+  const double L = (double) std::max<uint64_t>(1, w->hdr.n_leaves);
+  int s = w->tile_shift;
+  if (s < 0)
+    {
+      const double cells_per_tile = std::max(1.0, (double) w->tile_leaves * G * G / L);
+      s = (int) std::lround(0.5 * std::log2(cells_per_tile));
+    }
+  s = std::max(0, std::min(s, 15));
+  for (;;)
+    {
+      const uint32_t per_axis = (w->hdr.grid_g + (1u << s) - 1) >> s;
+      int b = 0;
+      while ((1u << b) < per_axis) b++;
+      if (b <= GSI_TILE_BITS_MAX)
+        {
+          *shift = s;
+          *bits = b;
+          return;
+        }
+      s++;
+    }
+}
+
+int
+ensure_reorder(const gsl_scattered_cuda *w, replica *r, size_t window, bool want_z, bool want_leaf)
+{
+  gsi_reorder_scratch &o = r->ro;
+  int shift, bits;
+  tile_geometry(w, &shift, &bits);
+  const int S = std::max(32, std::min(w->reorder_chunk, GSI_BIN_CHUNK_MAX)) & ~31;
+  const size_t nt = (size_t) 1 << (2 * bits);
+  const size_t n_chunks = (window + (size_t) S - 1) / (size_t) S;
+  const size_t off_entries = n_chunks * (nt + 2);
+  const size_t F = w->n_fields;
+  if (o.cap < window || o.chunk != S)
+    {
+      free_reorder(r);
+      CU(cudaMalloc(&o.bx, window * sizeof(double)));
+      CU(cudaMalloc(&o.by, window * sizeof(double)));
+      CU(cudaMalloc(&o.bi, window * sizeof(unsigned short)));
+      o.cap = window;
+      o.chunk = S;
+    }
+  if (r->ro_off_entries < off_entries)
+    {
+      if (o.off) cudaFree(o.off);
+      o.off = nullptr;
+      r->ro_off_entries = 0;
+      CU(cudaMalloc(&o.off, off_entries * sizeof(unsigned short)));
+      r->ro_off_entries = off_entries;
+    }
+  if (want_z && (!o.zb || r->ro_fields < F))
+    {
+      if (o.zb) cudaFree(o.zb);
+      o.zb = nullptr;
+      CU(cudaMalloc(&o.zb, o.cap * F * sizeof(double)));
+      r->ro_fields = F;
+    }
+  if (want_leaf && !o.lb) CU(cudaMalloc(&o.lb, o.cap * sizeof(int)));
+  o.tile_shift = shift;
+  o.tile_bits = bits;
+  o.ranges = std::max(1, w->tile_ranges);
+  return 0;
+}
+
 /* a block of whole raster columns: pixel (i, j), i in [i_first, i_first + n_cols), j in [0, ny) */
 struct raster_spec
 {
@@ -293,6 +398,13 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
 {
   if (nq == 0) return 0;
   size_t chunk = std::max<size_t>(1, std::min(w->chunk, (size_t) 0xfffffff0u));
+  const bool reorder = !ras && want_reorder(w, nq);
+  if (reorder)
+    {
+      chunk = std::min(chunk, std::max<size_t>(w->reorder_window, 32));
+      const int s = ensure_reorder(w, r, std::min(chunk, nq), d_z != nullptr, d_leaf != nullptr);
+      if (s) return s;
+    }
   size_t cols_per_chunk = 0;
   if (ras)
     {
@@ -316,6 +428,12 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
       cudaEvent_t ev[4];
       const int s = prepare_launch(w, r, n, ev, &cfg);
       if (s) return s;
+      if (reorder)
+        {
+          cfg.reorder = &r->ro;
+          r->n_reordered += n;
+          r->n_launches += 2; /* k_bin + k_tile_locate + k_unpermute instead of one locate kernel */
+        }
       cudaError_t e;
       if (ras)
         e = gsi_launch_eval_raster(r->view, ras->x0, ras->dx, ras->y0, ras->dy, ras->ny,
@@ -597,6 +715,14 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "walk_ctas_per_sm" && value >= 1) w->walk_ctas_per_sm = (int) value;
   else if (k == "walk_chunk" && value >= 0) w->walk_chunk = ((size_t) value + 31) & ~(size_t) 31;
   else if (k == "list_fraction" && value > 0 && value <= 1) w->list_fraction = value;
+  else if (k == "reorder" && (value == 0 || value == 1 || value == 2)) w->reorder = (int) value;
+  else if (k == "reorder_window" && value >= 32) w->reorder_window = (size_t) value;
+  else if (k == "reorder_min" && value >= 0) w->reorder_min = (size_t) value;
+  else if (k == "reorder_chunk" && value >= 32 && value <= GSI_BIN_CHUNK_MAX) w->reorder_chunk = (int) value;
+  else if (k == "reorder_max_fields" && value >= 0) w->reorder_max_fields = (size_t) value;
+  else if (k == "tile_shift" && value >= -1 && value <= 15) w->tile_shift = (int) value;
+  else if (k == "tile_ranges" && value >= 1 && value <= 64) w->tile_ranges = (int) value;
+  else if (k == "tile_leaves" && value >= 1) w->tile_leaves = (int) value;
   else GSI_ERROR("unknown parameter or value out of range", GSL_SCATTERED_EINVAL);
   return GSL_SCATTERED_SUCCESS;
 }
@@ -848,6 +974,7 @@ gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info
       info->locate_seconds += r->locate_seconds;
       info->exact_seconds += r->exact_seconds;
       info->n_kernel_launches += r->n_launches;
+      info->n_reordered += r->n_reordered;
     }
   return GSL_SCATTERED_SUCCESS;
 }
@@ -868,6 +995,7 @@ gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w)
       r->prof_exact.clear();
       r->locate_seconds = r->exact_seconds = 0;
       r->n_launches = 0;
+      r->n_reordered = 0;
     }
   return GSL_SCATTERED_SUCCESS;
 }

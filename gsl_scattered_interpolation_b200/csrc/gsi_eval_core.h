@@ -35,16 +35,37 @@ gsi_bits_to_float_host(uint32_t u)
 #define GSI_BITS_TO_FLOAT(u) gsi_bits_to_float_host(u)
 #endif
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
+/* L2 fill-size hint of the structure gathers (leaf records, seed cells).  Measured on B200
+ * (scripts/gather_probe3.cu, profiles/): without a hint every L2 miss fills a whole 128-byte
+ * line from HBM whatever cudaLimitMaxL2FetchGranularity says; ".L2::64B" halves the fill. */
+#ifndef GSI_GATHER_HINT
+#define GSI_GATHER_HINT ""
+#endif
 /* one 32-byte sector with a single 256-bit load (LDG.E.256, sm_100+); read-only path */
 __device__ __forceinline__ void
 gsi_ld256(const void *p, unsigned long long &a, unsigned long long &b, unsigned long long &c,
           unsigned long long &d)
 {
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc" GSI_GATHER_HINT ".v4.u64 {%0,%1,%2,%3}, [%4];"
                : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
                : "l"(p));
 }
+
+__device__ __forceinline__ int
+gsi_ld_seed(const int32_t *p)
+{
+  int v;
+  asm volatile("ld.global.nc" GSI_GATHER_HINT ".s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+#if defined(GSI_STREAM_HINTS)
+#define GSI_LD_QUERY(p) __ldcs(p)
+#define GSI_ST_RESULT(p, v) __stcs((p), (v))
+#else
+#define GSI_LD_QUERY(p) __ldg(p)
+#define GSI_ST_RESULT(p, v) (*(p) = (v))
+#endif
 #endif
 
 /* the 64-byte LU/link part of a record (DAG node or leaf): two sectors */

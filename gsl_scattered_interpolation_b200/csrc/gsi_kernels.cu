@@ -34,14 +34,14 @@ struct src_arrays
   __device__ __forceinline__ bool get(size_t t, size_t &q, double &qx, double &qy) const
   {
     q = t;
-    qx = __ldg(x + t);
-    qy = __ldg(y + t);
+    qx = GSI_LD_QUERY(x + t);
+    qy = GSI_LD_QUERY(y + t);
     return true;
   }
   __device__ __forceinline__ void get_linear(size_t q, double &qx, double &qy) const
   {
-    qx = __ldg(x + q);
-    qy = __ldg(y + q);
+    qx = GSI_LD_QUERY(x + q);
+    qy = GSI_LD_QUERY(y + q);
   }
   __device__ __forceinline__ bool out_index(size_t t, size_t &q) const
   {
@@ -214,7 +214,7 @@ k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out,
           status = GSI_STEP_DEFER;
           if (isfinite(qx) && isfinite(qy))
             {
-              slot = __ldg(V.seeds + gsi_cell_of(&V, qx, qy));
+              slot = gsi_ld_seed(V.seeds + gsi_cell_of(&V, qx, qy));
               for (int step = 0; step < max_steps; step++)
                 {
                   gsi_rec r;
@@ -305,7 +305,7 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
               cur_v = nxt_v; cur_q = nxt_q; cur_x = nxt_x; cur_y = nxt_y;
               cur_slot = nxt_seed; cur_steps = 0;
               nxt_v = nn_v; nxt_q = nn_q; nxt_x = nn_x; nxt_y = nn_y;
-              if (nxt_v) nxt_seed = __ldg(V.seeds + gsi_cell_of(&V, nxt_x, nxt_y));
+              if (nxt_v) nxt_seed = gsi_ld_seed(V.seeds + gsi_cell_of(&V, nxt_x, nxt_y));
             }
           const unsigned take = __ballot_sync(FULL, need);
           if (need)
@@ -340,13 +340,13 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
                   if (st == GSI_STEP_ACCEPT)
                     {
                       const size_t q = q0 + cur_q;
-                      if (leaf_out) leaf_out[q] = t.g.node;
+                      if (leaf_out) GSI_ST_RESULT(leaf_out + q, t.g.node);
                       if (val)
                         {
                           if (ONE_FIELD)
-                            val[q] = gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0],
+                            GSI_ST_RESULT(val + q, gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0],
                                                (int) (t.s.vflags & 2u), t.s.z[1],
-                                               (int) (t.s.vflags & 4u), t.s.z[2]);
+                                               (int) (t.s.vflags & 4u), t.s.z[2]));
                           else
                             gsi_blend_store(&V, &t, c0, c1, val, ld, q);
                         }
@@ -434,7 +434,7 @@ k_stage(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val,
                   cur_v = nxt_v; cur_i = nxt_i; cur_x = nxt_x; cur_y = nxt_y;
                   cur_slot = nxt_seed; cur_steps = 0;
                   nxt_v = nn_v; nxt_i = nn_i; nxt_x = nn_x; nxt_y = nn_y;
-                  if (nxt_v) nxt_seed = __ldg(V.seeds + gsi_cell_of(&V, nxt_x, nxt_y));
+                  if (nxt_v) nxt_seed = gsi_ld_seed(V.seeds + gsi_cell_of(&V, nxt_x, nxt_y));
                 }
               const unsigned take = __ballot_sync(FULL, need);
               if (need)
@@ -525,6 +525,319 @@ k_stage(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val,
     atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
 }
 
+/* ---- reorder pipeline: k_bin -> k_tile_locate -> k_unpermute ---------------------------------
+ * Uniformly random queries make every leaf fetch an isolated L2/DRAM access.  The pipeline
+ * gives the walk spatial coherence without a global sort and without scattered global writes:
+ *   k_bin          one CTA per chunk of <= 8192 consecutive queries: counting sort by spatial
+ *                  tile (Morton id of a block of seed-grid cells) entirely in shared memory,
+ *                  then coalesced stores of the binned coordinates, the 16-bit in-chunk index
+ *                  of every binned query and the chunk's run table (start of each tile's run);
+ *   k_tile_locate  tile-major: the CTAs of tile t gather t's run from every chunk (32 chunks
+ *                  per warp step, lane-parallel prefix over the run lengths) and walk them, so
+ *                  the tile's ~1000 leaves and its seed cells stay in that SM's L1; results go
+ *                  to the binned slots (neighbouring tiles are resident together, so the runs'
+ *                  shared sectors merge in L2);
+ *   k_unpermute    one CTA per chunk: the inverse permutation through shared memory, coalesced
+ *                  loads and stores.
+ * The arithmetic per query is the one of k_locate (gsi_walk_step), so accepted results are
+ * bit-identical; deferred queries go to the same list (original query index) and are replayed
+ * after k_unpermute. */
+__device__ __forceinline__ unsigned
+spread8(unsigned x) /* abcdefgh -> 0a0b0c0d0e0f0g0h */
+{
+  x &= 0xffu;
+  x = (x | (x << 4)) & 0x0f0fu;
+  x = (x | (x << 2)) & 0x3333u;
+  x = (x | (x << 1)) & 0x5555u;
+  return x;
+}
+
+__device__ __forceinline__ unsigned
+compact8(unsigned x)
+{
+  x &= 0x5555u;
+  x = (x | (x >> 1)) & 0x3333u;
+  x = (x | (x >> 2)) & 0x0f0fu;
+  x = (x | (x >> 4)) & 0x00ffu;
+  return x;
+}
+
+/* Morton id of the tile (2^shift x 2^shift seed-grid cells) of a query; the cell is the one of
+ * gsi_cell_of, so non-finite coordinates land in tile 0 and are deferred by the walk */
+__device__ __forceinline__ unsigned
+tile_of(const gsi_view &V, double qx, double qy, int shift)
+{
+  const double u = (qx - V.xf.cx) * V.xf.sx, v = (qy - V.xf.cy) * V.xf.sy;
+  const double gmax = (double) (V.grid_g - 1);
+  const int ix = __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du, 0.0), gmax));
+  const int iy = __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv, 0.0), gmax));
+  return spread8((unsigned) ix >> shift) | (spread8((unsigned) iy >> shift) << 1);
+}
+
+__global__ void __launch_bounds__(GSI_BIN_THREADS, 1)
+k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict__ yq, size_t nq, int S,
+      int shift, int nt, double *__restrict__ bx, double *__restrict__ by,
+      unsigned short *__restrict__ bi, unsigned short *__restrict__ off)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sx = reinterpret_cast<double *>(smem_raw);
+  double *sy = sx + S;
+  unsigned *hist = reinterpret_cast<unsigned *>(sy + S);
+  unsigned short *si = reinterpret_cast<unsigned short *>(hist + nt);
+  __shared__ unsigned warp_sum[32];
+  const unsigned FULL = 0xffffffffu;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
+  const size_t ntp = (size_t) nt + 2;
+  const unsigned per = ((unsigned) nt + GSI_BIN_THREADS - 1) / GSI_BIN_THREADS; /* 1 or 4 */
+  constexpr int KPT = GSI_BIN_CHUNK_MAX / GSI_BIN_THREADS;
+  for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
+    {
+      const size_t q0 = c * (size_t) S;
+      const unsigned n = (unsigned) (nq - q0 < (size_t) S ? nq - q0 : (size_t) S);
+      for (unsigned i = tid; i < (unsigned) nt; i += GSI_BIN_THREADS) hist[i] = 0;
+      __syncthreads();
+      /* tile and arrival rank inside the tile of every query of the chunk */
+      unsigned pk[KPT];
+#pragma unroll
+      for (int k = 0; k < KPT; k++)
+        {
+          const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+          pk[k] = 0xffffffffu;
+          if (i < n)
+            {
+              const unsigned t = tile_of(V, __ldg(xq + q0 + i), __ldg(yq + q0 + i), shift);
+              pk[k] = t | (atomicAdd(hist + t, 1u) << 12);
+            }
+        }
+      __syncthreads();
+      /* exclusive scan of the histogram, in place; the starts are the chunk's run table */
+      unsigned loc[4], sum = 0;
+      const unsigned b = tid * per;
+#pragma unroll
+      for (unsigned j = 0; j < 4; j++)
+        {
+          loc[j] = (j < per && b + j < (unsigned) nt) ? hist[b + j] : 0u;
+          sum += loc[j];
+        }
+      unsigned inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        {
+          const unsigned v = __shfl_up_sync(FULL, inc, o);
+          if (lane >= (unsigned) o) inc += v;
+        }
+      if (lane == 31) warp_sum[wid] = inc;
+      __syncthreads();
+      if (wid == 0)
+        {
+          const unsigned v = warp_sum[lane];
+          unsigned iv = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+            {
+              const unsigned u = __shfl_up_sync(FULL, iv, o);
+              if (lane >= (unsigned) o) iv += u;
+            }
+          warp_sum[lane] = iv - v;
+        }
+      __syncthreads();
+      unsigned run = warp_sum[wid] + inc - sum;
+      unsigned short *row = off + c * ntp;
+#pragma unroll
+      for (unsigned j = 0; j < 4; j++)
+        if (j < per && b + j < (unsigned) nt)
+          {
+            hist[b + j] = run;
+            row[b + j] = (unsigned short) run;
+            run += loc[j];
+          }
+      if (tid == 0) row[nt] = (unsigned short) n;
+      __syncthreads();
+      /* permute in shared memory (the coordinates come back from L2) */
+#pragma unroll
+      for (int k = 0; k < KPT; k++)
+        if (pk[k] != 0xffffffffu)
+          {
+            const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+            const unsigned pos = hist[pk[k] & 0xfffu] + (pk[k] >> 12);
+            sx[pos] = __ldg(xq + q0 + i);
+            sy[pos] = __ldg(yq + q0 + i);
+            si[pos] = (unsigned short) i;
+          }
+      __syncthreads();
+      for (unsigned i = tid; i < n; i += GSI_BIN_THREADS)
+        {
+          __stcs(bx + q0 + i, sx[i]);
+          __stcs(by + q0 + i, sy[i]);
+          bi[q0 + i] = si[i];
+        }
+      __syncthreads();
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(GSI_TILE_THREADS, 2)
+k_tile_locate(const gsi_view V, const double *__restrict__ bx, const double *__restrict__ by,
+              const unsigned short *__restrict__ bi, const unsigned short *__restrict__ off,
+              unsigned n_chunks, int S, int nt, int shift, int ranges, double *zb, int *lb, size_t ldb,
+              unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters, int max_steps)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned t = blockIdx.x / (unsigned) ranges, r = blockIdx.x - t * (unsigned) ranges;
+  /* Morton ids whose cells all lie beyond the grid hold no query */
+  if ((compact8(t) << shift) >= (unsigned) V.grid_g || (compact8(t >> 1) << shift) >= (unsigned) V.grid_g)
+    return;
+  constexpr unsigned WPC = GSI_TILE_THREADS / 32;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned n_blocks = (n_chunks + 31u) >> 5;
+  const size_t ntp = (size_t) nt + 2;
+  unsigned long long steps_acc = 0;
+  for (unsigned cb = r * WPC + warp; cb < n_blocks; cb += (unsigned) ranges * WPC)
+    {
+      /* lane <-> chunk: this tile's run in each of 32 consecutive chunks */
+      const unsigned c = (cb << 5) + lane;
+      unsigned o0 = 0, len = 0;
+      if (c < n_chunks)
+        {
+          const unsigned short *row = off + (size_t) c * ntp + t;
+          o0 = row[0];
+          len = (unsigned) row[1] - o0;
+        }
+      unsigned incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+        {
+          const unsigned v = __shfl_up_sync(FULL, incl, o);
+          if (lane >= (unsigned) o) incl += v;
+        }
+      const unsigned total = __shfl_sync(FULL, incl, 31);
+      for (unsigned base = 0; base < total; base += 32)
+        {
+          const bool live = base + lane < total;
+          const unsigned k = live ? base + lane : total - 1;
+          /* j = number of chunks whose inclusive prefix is <= k = the chunk holding item k */
+          unsigned j = 0;
+#pragma unroll
+          for (unsigned step = 16; step; step >>= 1)
+            {
+              const unsigned v = __shfl_sync(FULL, incl, j + step - 1);
+              if (v <= k) j += step;
+            }
+          const unsigned incl_j = __shfl_sync(FULL, incl, j), len_j = __shfl_sync(FULL, len, j),
+                         o0_j = __shfl_sync(FULL, o0, j);
+          const size_t cbase = (size_t) ((cb << 5) + j) * (size_t) S;
+          const size_t pos = cbase + o0_j + (k - (incl_j - len_j));
+          int status = GSI_STEP_MOVE; /* = not a live query */
+          int slot = 0;
+          double c0 = 0, c1 = 0;
+          if (live)
+            {
+              const double qx = __ldcs(bx + pos), qy = __ldcs(by + pos);
+              status = GSI_STEP_DEFER;
+              if (isfinite(qx) && isfinite(qy))
+                {
+                  slot = gsi_ld_seed(V.seeds + gsi_cell_of(&V, qx, qy));
+                  for (int step = 0; step < max_steps; step++)
+                    {
+                      gsi_rec rec;
+                      const int at = slot;
+                      gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
+                      const int st = gsi_walk_step(&V.xf, &rec, qx, qy, &slot, &c0, &c1);
+                      if (st != GSI_STEP_MOVE)
+                        {
+                          status = st;
+                          slot = at;
+                          if (STATS && st == GSI_STEP_ACCEPT) steps_acc += (unsigned) step + 1u;
+                          break;
+                        }
+                    }
+                }
+            }
+          __syncwarp();
+          if (status == GSI_STEP_ACCEPT)
+            {
+              gsi_leaf_tail tl;
+              gsi_fetch_tail(&tl, gsi_leaf_at(&V, slot));
+              if (lb) lb[pos] = tl.g.node;
+              if (zb) gsi_blend_store(&V, &tl, c0, c1, zb, ldb, pos);
+            }
+          const bool defer = status == GSI_STEP_DEFER;
+          const unsigned dm = __ballot_sync(FULL, defer);
+          if (dm)
+            {
+              const int leader = __ffs(dm) - 1;
+              unsigned at0 = 0;
+              if (lane == (unsigned) leader)
+                at0 = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+              at0 = __shfl_sync(FULL, at0, leader);
+              if (defer)
+                {
+                  const size_t q = cbase + bi[pos];
+                  const unsigned at = at0 + __popc(dm & lt_mask);
+                  if (at < list_cap)
+                    list[at] = (unsigned) q;
+                  else
+                    mark_overflow(ovf_mask, q, counters);
+                }
+            }
+        }
+    }
+  if (STATS && steps_acc)
+    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
+}
+
+__global__ void __launch_bounds__(GSI_BIN_THREADS, 2)
+k_unpermute(const double *__restrict__ zb, const int *__restrict__ lb, const unsigned short *__restrict__ bi,
+            size_t nq, int S, int n_fields, size_t ldb, double *__restrict__ val, size_t ld,
+            int *__restrict__ leaf_out)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sz = reinterpret_cast<double *>(smem_raw);
+  int *sl = reinterpret_cast<int *>(sz + S);
+  const unsigned tid = threadIdx.x;
+  const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
+  constexpr int KPT = GSI_BIN_CHUNK_MAX / GSI_BIN_THREADS;
+  for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
+    {
+      const size_t q0 = c * (size_t) S;
+      const unsigned n = (unsigned) (nq - q0 < (size_t) S ? nq - q0 : (size_t) S);
+      unsigned short idx[KPT];
+#pragma unroll
+      for (int k = 0; k < KPT; k++)
+        {
+          const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+          idx[k] = 0;
+          if (i < n)
+            {
+              idx[k] = bi[q0 + i];
+              if (leaf_out) sl[idx[k]] = __ldcs(lb + q0 + i);
+            }
+        }
+      const int passes = val ? n_fields : 1;
+      for (int f = 0; f < passes; f++)
+        {
+          if (val)
+            {
+#pragma unroll
+              for (int k = 0; k < KPT; k++)
+                {
+                  const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+                  if (i < n) sz[idx[k]] = __ldcs(zb + (size_t) f * ldb + q0 + i);
+                }
+            }
+          __syncthreads();
+          for (unsigned i = tid; i < n; i += GSI_BIN_THREADS)
+            {
+              if (val) __stcs(val + (size_t) f * ld + q0 + i, sz[i]);
+              if (f == 0 && leaf_out) __stcs(leaf_out + q0 + i, sl[i]);
+            }
+          __syncthreads();
+        }
+    }
+}
+
 /* ---- synthetic inputs / verification helpers ------------------------------------------------ */
 __global__ void __launch_bounds__(256)
 k_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo, double xw, double ylo,
@@ -602,6 +915,52 @@ grid_for(size_t n, int threads, int sm_count, int per_sm)
   return (int) (want < cap ? (want ? want : 1) : cap);
 }
 
+/* the reorder pipeline applies to query arrays only (rasters are coherent by construction) */
+inline bool
+launch_reordered(const gsi_view &, const src_raster &, size_t, double *, int *, size_t,
+                 const gsi_launch_cfg &, unsigned, cudaStream_t)
+{
+  return false;
+}
+
+inline bool
+launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *val, int *leaf_out,
+                 size_t ld, const gsi_launch_cfg &cfg, unsigned list_cap, cudaStream_t st)
+{
+  const gsi_reorder_scratch *R = cfg.reorder;
+  if (!R || nq > R->cap || R->chunk < 32 || R->chunk > GSI_BIN_CHUNK_MAX) return false;
+  const int S = R->chunk, nt = 1 << (2 * R->tile_bits);
+  const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
+  const size_t smem_bin = (size_t) S * 18 + (size_t) nt * 4, smem_unp = (size_t) S * 12;
+  static bool attr_done = false;
+  if (!attr_done)
+    {
+      cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 18 + 4096 * 4);
+      cudaFuncSetAttribute(k_unpermute, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 12);
+      attr_done = true;
+    }
+  const int g_bin = (int) (n_chunks < (size_t) cfg.sm_count ? n_chunks : (size_t) cfg.sm_count);
+  k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(V, src.x, src.y, nq, S, R->tile_shift, nt, R->bx, R->by,
+                                                  R->bi, R->off);
+  /* CTAs per tile: every warp of a CTA should get a few 32-chunk blocks, else one CTA per tile */
+  const size_t n_blocks = (n_chunks + 31) / 32;
+  int ranges = (int) (n_blocks / (4 * (GSI_TILE_THREADS / 32)));
+  if (ranges > R->ranges) ranges = R->ranges;
+  if (ranges < 1) ranges = 1;
+  if (cfg.stats)
+    k_tile_locate<true><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
+        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, val ? R->zb : nullptr,
+        leaf_out ? R->lb : nullptr, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+  else
+    k_tile_locate<false><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
+        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, val ? R->zb : nullptr,
+        leaf_out ? R->lb : nullptr, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+  const int g_unp = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
+  k_unpermute<<<g_unp, GSI_BIN_THREADS, smem_unp, st>>>(R->zb, R->lb, R->bi, nq, S, V.n_fields, R->cap, val, ld,
+                                                        leaf_out);
+  return true;
+}
+
 template <class SRC>
 cudaError_t
 launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf_out, size_t ld,
@@ -621,7 +980,9 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   cudaError_t e = cudaMemsetAsync(cfg.counters + GSI_CNT_DEFERRED, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   if (cfg.ev_locate0) cudaEventRecord(cfg.ev_locate0, st);
-  if (cfg.kernel == GSI_KERNEL_STAGE)
+  if (launch_reordered(V, src, nq, val, leaf_out, ld, cfg, list_cap, st))
+    ;
+  else if (cfg.kernel == GSI_KERNEL_STAGE)
     {
       const int ctas = cfg.sm_count * cfg.walk_ctas_per_sm;
       const size_t n_warps = (size_t) ctas * (GSI_STAGE_THREADS / 32);

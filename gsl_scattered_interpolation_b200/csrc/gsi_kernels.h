@@ -12,6 +12,10 @@
 #define GSI_WALK_THREADS 128
 #define GSI_STAGE_THREADS 128
 #define GSI_STAGE_WINDOW 256
+#define GSI_BIN_THREADS 1024    /* k_bin / k_unpermute: one CTA sorts one chunk in shared memory */
+#define GSI_BIN_CHUNK_MAX 8192  /* queries per chunk (16-bit in-chunk indices, 160 KB of shared memory) */
+#define GSI_TILE_THREADS 512    /* k_tile_locate */
+#define GSI_TILE_BITS_MAX 6     /* Morton tile id: <= 6 bits per axis = 4096 tiles */
 
 /* device counters (unsigned[16]) */
 #define GSI_CNT_DEFERRED 0       /* u32: length of the deferred list of the current launch */
@@ -29,6 +33,26 @@
 #define GSI_KERNEL_AUTO 2   /* k_walk for query arrays, k_locate for rasters (default) */
 #define GSI_KERNEL_STAGE 3  /* k_stage: decoupled walk staged in shared memory + converged blend */
 
+/* Scratch of the reorder pipeline (k_bin -> k_tile_locate -> k_unpermute), one per replica.
+ * Queries are processed in windows of `cap` queries; a window is cut into chunks of `chunk`
+ * consecutive queries and every chunk is sorted by spatial tile (Morton id of a 2^shift x
+ * 2^shift block of seed-grid cells) inside shared memory, so both the reorder and its inverse
+ * are chunk-local permutations with coalesced global traffic. */
+struct gsi_reorder_scratch
+{
+  double *bx = nullptr, *by = nullptr; /* query coordinates, tile order inside every chunk */
+  unsigned short *bi = nullptr;        /* position of the binned query inside its chunk */
+  unsigned short *off = nullptr;       /* [n_chunks][nt + 2]: first binned slot of every tile's
+                                          run inside the chunk; entry nt = chunk length */
+  double *zb = nullptr;                /* results in binned order, field-major, ld = cap */
+  int *lb = nullptr;
+  size_t cap = 0;     /* queries per window */
+  int chunk = 0;      /* queries per chunk */
+  int tile_shift = 0; /* tile edge = 2^tile_shift grid cells */
+  int tile_bits = 0;  /* bits per axis of the Morton tile id (nt = 4^tile_bits) */
+  int ranges = 4;     /* k_tile_locate CTAs per tile, each taking a share of the chunks */
+};
+
 struct gsi_launch_cfg
 {
   int mode = GSI_MODE_FAST;
@@ -43,6 +67,7 @@ struct gsi_launch_cfg
   size_t list_capacity = 0;     /* deferred-list entries; overflow goes to the bitmask */
   unsigned *ovf_mask = nullptr; /* one bit per query of a launch (zero between launches) */
   unsigned *counters = nullptr; /* GSI_CNT_WORDS words */
+  const gsi_reorder_scratch *reorder = nullptr; /* non-NULL: query arrays go through the reorder pipeline */
   /* optional profiling events recorded around the two kernels of a launch */
   cudaEvent_t ev_locate0 = nullptr, ev_locate1 = nullptr, ev_exact0 = nullptr, ev_exact1 = nullptr;
 };

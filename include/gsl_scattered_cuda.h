@@ -158,6 +158,7 @@ typedef struct
   unsigned long long n_kernel_launches; /* eval kernels launched since reset */
   double locate_seconds;   /* device time in the fast-path kernel (only with param "profile") */
   double exact_seconds;    /* device time in the exact-replay kernel (only with param "profile") */
+  unsigned long long n_reordered; /* queries that went through the reorder pipeline since reset */
 } gsl_scattered_cuda_info;
 int gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info *info);
 int gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w);

@@ -393,3 +393,109 @@ def test_million_nodes_properties():
     assert np.array_equal(la_d[sub].cpu().numpy(), pl)
     assert refimpl.same_bits(za_d[:, sub].cpu().numpy(), pv)
     w.free()
+
+
+# ---- reorder pipeline (k_bin -> k_tile_locate -> k_unpermute) -------------------------------
+
+@pytest.mark.parametrize("chunk,shift", [(8192, -1), (8192, 0), (4096, 2), (96, 1), (1024, 5)])
+def test_reorder_pipeline_on_the_golden_sets(golden, chunk, shift):
+    """Forced reorder (param reorder=1) on config 1 and on the config-3 mix (3 fields, on-edge /
+    on-vertex / outside-hull queries that are deferred to the exact replay): every chunk and tile
+    geometry must give the reference's leaf ids and value bits."""
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
+             reorder=1, reorder_chunk=chunk, tile_shift=shift)
+    xq, yq = synth.uniform_queries(10000)
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert st == g.SUCCESS
+    assert np.array_equal(leaf, golden["cfg1_leaf"])
+    assert refimpl.same_bits(zq, golden["cfg1_val"])
+    assert w.info()["n_reordered"] == 10000
+    # leaf ids only / values only
+    st, zq2, _ = w.eval_e(xq, yq, want_leaf=False)
+    assert refimpl.same_bits(zq2, golden["cfg1_val"])
+    st, _, leaf2 = w.eval_e(xq, yq, want_values=False)
+    assert np.array_equal(leaf2, golden["cfg1_leaf"])
+    w.free()
+    n = 3000
+    xa, ya = synth.clustered_nodes(n)
+    w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n),
+             reorder=1, reorder_chunk=chunk, tile_shift=shift)
+    xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert st == g.SUCCESS
+    assert np.array_equal(leaf, golden["cfg3_leaf"])
+    assert refimpl.same_bits(zq, golden["cfg3_val"])
+    assert w.info()["n_deferred"] > 0
+    w.free()
+
+
+def test_reorder_pipeline_edge_cases(golden):
+    """non-finite queries, every query in one tile (run length = chunk), tiny deferred list
+    (overflow bitmask), windows that do not divide the batch, outside-cage status"""
+    xa, ya = synth.uniform_nodes(1000)
+    za = synth.values(1000, 1)
+    order = g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000)
+    port = refimpl.PortTree({k: golden["cfg1_" + k] for k in
+                             ("pts3", "lnk3", "type", "shuffle", "shift", "scale", "seed_points")}, xa, ya)
+    w = make(xa, ya, za, g.DEFAULT, order, reorder=1, reorder_window=7001, tile_shift=1)
+    bx = np.array([np.nan, np.inf, -np.inf, 0.5, 1e300, 0.25])
+    by = np.array([0.5, 0.5, 0.5, np.nan, 0.5, 0.75])
+    st, zq, leaf = w.eval_e(bx, by)
+    pl, pv, _ = port.eval(bx, by, za)
+    assert np.array_equal(leaf, pl) and refimpl.same_bits(zq, pv)
+    # one hot spot: 30000 copies of one point plus the golden set, window 7001 (4 full + 1 ragged)
+    xq, yq = synth.uniform_queries(10000)
+    hx = np.concatenate([np.full(30000, xq[17]), xq])
+    hy = np.concatenate([np.full(30000, yq[17]), yq])
+    st, zq, leaf = w.eval_e(hx, hy)
+    assert st == g.SUCCESS
+    assert np.all(leaf[:30000] == golden["cfg1_leaf"][17])
+    assert np.array_equal(leaf[30000:], golden["cfg1_leaf"])
+    assert refimpl.same_bits(zq[:, 30000:], golden["cfg1_val"])
+    assert np.all(zq[0, :30000].view(np.uint64) == golden["cfg1_val"].ravel().view(np.uint64)[17])
+    # outside the cage: leaf -1, NaN, EDOM
+    st, zq, leaf = w.eval_e(np.array([0.5, 1e6]), np.array([0.5, 0.0]))
+    assert st == g.EDOM and leaf[1] == -1 and np.isnan(zq[0, 1]) and leaf[0] >= 0
+    w.free()
+    w = make(xa, ya, za, g.DEFAULT, order, reorder=1, cells_per_leaf=0.05, max_steps=1, list_fraction=1e-4)
+    xq2, yq2 = np.tile(xq, 20), np.tile(yq, 20)
+    st, zq, leaf = w.eval_e(xq2, yq2)
+    assert np.array_equal(leaf, np.tile(golden["cfg1_leaf"], 20))
+    assert refimpl.same_bits(zq, np.tile(golden["cfg1_val"], (1, 20)))
+    assert w.info()["n_deferred"] > 65536
+    w.free()
+
+
+@pytest.mark.parametrize("n,nq,window", [(100000, 10_000_000, 3_000_001), (100000, 10_000_000, 1 << 27),
+                                         (1_000_000, 20_000_000, 1 << 27)])
+def test_reorder_pipeline_scale_vs_exact_and_direct(n, nq, window):
+    """10^5 nodes, 10^7 device-generated queries: reorder pipeline == direct fast path == exact
+    DAG replay on 100 % of the queries (leaf ids and value bits), plus the port on a subsample."""
+    torch = _torch()
+    xa, ya = synth.uniform_nodes(n)
+    za = synth.values(n, 1)
+    w = make(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), reorder=1, reorder_window=window)
+    dev = torch.device("cuda:0")
+    dx = torch.empty(nq, dtype=torch.float64, device=dev)
+    dy = torch.empty(nq, dtype=torch.float64, device=dev)
+    w.generate_uniform_device(0, synth.SEED_QUERIES, 0, nq, 0.0, 1.0, 0.0, 1.0, dx.data_ptr(), dy.data_ptr())
+    res = {}
+    for name, params in (("reorder", {"reorder": 1}), ("direct", {"reorder": 0}), ("exact", {"mode": 1})):
+        for k, v in params.items():
+            w.set_param(k, v)
+        z = torch.empty(nq, dtype=torch.float64, device=dev)
+        l = torch.empty(nq, dtype=torch.int32, device=dev)
+        assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, z.data_ptr(), nq, l.data_ptr()) == 0
+        res[name] = (z, l)
+    assert w.info()["n_reordered"] == nq
+    for other in ("direct", "exact"):
+        bad_leaf, bad_val = w.compare_device(0, res["reorder"][1].data_ptr(), res[other][1].data_ptr(),
+                                             res["reorder"][0].data_ptr(), res[other][0].data_ptr(), nq, nq)
+        assert bad_leaf == 0 and bad_val == 0, other
+    sub = torch.arange(0, nq, 997, device=dev)
+    port = refimpl.PortTree(w.get_tree(w.n_simplexes(), n), xa, ya)
+    pl, pv, _ = port.eval(dx[sub].cpu().numpy(), dy[sub].cpu().numpy(), za)
+    assert np.array_equal(res["reorder"][1][sub].cpu().numpy(), pl)
+    assert refimpl.same_bits(res["reorder"][0][sub].cpu().numpy().reshape(1, -1), pv)
+    w.free()
