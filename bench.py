@@ -339,6 +339,20 @@ def main_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
+        reordered = inf.get("n_reordered", 0) > 0
+        kernel_name = "k_bin + k_tile_locate + k_unpermute (reorder pipeline)" if reordered else "k_walk"
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per query,
+        # scaled to this launch); only valid for the configuration the capture was taken on
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1c_k_walk_traffic.json")) as f:
+                tj = json.load(f)
+            if not reordered and n == 1_000_000 and F == 1:
+                traffic = tj["dram_bytes_per_query"] * Q
+                traffic_src = (f"{tj['dram_bytes_per_query']:.1f} B/query x {Q} queries; ncu dram__bytes_read+write.sum "
+                               f"of one {tj['queries_per_launch']}-query launch ({tj['source']})")
+        except Exception:
+            pass
         alg = Q * (16 + 4 + 8 * F) + struct_bytes
         achieved = alg / locate_s / 1e9 if locate_s > 0 else None
         line = {
@@ -355,8 +369,9 @@ def main_ours(args):
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_walk", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel_ms_per_launch": 1e3 * locate_s, "exact_replay_ms_per_step": 1e3 * exact_s},
             "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
