@@ -13,6 +13,7 @@
  * This path is gather/latency bound: no tensor cores, no FMA contraction (gsi_core.h).
  */
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math_constants.h>
 #include <stdint.h>
 
@@ -574,35 +575,37 @@ tile_of(const gsi_view &V, double qx, double qy, int shift)
   return spread8((unsigned) ix >> shift) | (spread8((unsigned) iy >> shift) << 1);
 }
 
-__global__ void __launch_bounds__(GSI_BIN_THREADS, 1)
+/* One coordinate is staged at a time (96 KB of shared memory for 8192-query chunks) so that two
+ * CTAs share an SM and one CTA's global loads overlap the other's scan / copy-out. */
+__global__ void __launch_bounds__(GSI_BIN_THREADS, 2)
 k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict__ yq, size_t nq, int S,
-      int shift, int nt, double *__restrict__ bx, double *__restrict__ by,
-      unsigned short *__restrict__ bi, unsigned short *__restrict__ off)
+       int shift, int nt, double *__restrict__ bx, double *__restrict__ by,
+       unsigned short *__restrict__ bi, unsigned short *__restrict__ off)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *sx = reinterpret_cast<double *>(smem_raw);
-  double *sy = sx + S;
-  unsigned *hist = reinterpret_cast<unsigned *>(sy + S);
+  double *sbuf = reinterpret_cast<double *>(smem_raw);
+  unsigned *hist = reinterpret_cast<unsigned *>(sbuf + S);
   unsigned short *si = reinterpret_cast<unsigned short *>(hist + nt);
-  __shared__ unsigned warp_sum[32];
+  constexpr unsigned T = GSI_BIN_THREADS, WPC = T / 32;
+  constexpr int KPT = GSI_BIN_CHUNK_MAX / T;
+  constexpr unsigned PER = 4096 / T; /* histogram entries per thread in the scan, nt <= 4096 */
+  __shared__ unsigned warp_sum[WPC];
   const unsigned FULL = 0xffffffffu;
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
   const size_t ntp = (size_t) nt + 2;
-  const unsigned per = ((unsigned) nt + GSI_BIN_THREADS - 1) / GSI_BIN_THREADS; /* 1 or 4 */
-  constexpr int KPT = GSI_BIN_CHUNK_MAX / GSI_BIN_THREADS;
+  const unsigned per = ((unsigned) nt + T - 1) / T;
   for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
     {
       const size_t q0 = c * (size_t) S;
       const unsigned n = (unsigned) (nq - q0 < (size_t) S ? nq - q0 : (size_t) S);
-      for (unsigned i = tid; i < (unsigned) nt; i += GSI_BIN_THREADS) hist[i] = 0;
+      for (unsigned i = tid; i < (unsigned) nt; i += T) hist[i] = 0;
       __syncthreads();
-      /* tile and arrival rank inside the tile of every query of the chunk */
       unsigned pk[KPT];
 #pragma unroll
       for (int k = 0; k < KPT; k++)
         {
-          const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+          const unsigned i = (unsigned) k * T + tid;
           pk[k] = 0xffffffffu;
           if (i < n)
             {
@@ -611,11 +614,10 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
             }
         }
       __syncthreads();
-      /* exclusive scan of the histogram, in place; the starts are the chunk's run table */
-      unsigned loc[4], sum = 0;
+      unsigned loc[PER], sum = 0;
       const unsigned b = tid * per;
 #pragma unroll
-      for (unsigned j = 0; j < 4; j++)
+      for (unsigned j = 0; j < PER; j++)
         {
           loc[j] = (j < per && b + j < (unsigned) nt) ? hist[b + j] : 0u;
           sum += loc[j];
@@ -629,23 +631,13 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
         }
       if (lane == 31) warp_sum[wid] = inc;
       __syncthreads();
-      if (wid == 0)
-        {
-          const unsigned v = warp_sum[lane];
-          unsigned iv = v;
+      unsigned run = inc - sum;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1)
-            {
-              const unsigned u = __shfl_up_sync(FULL, iv, o);
-              if (lane >= (unsigned) o) iv += u;
-            }
-          warp_sum[lane] = iv - v;
-        }
-      __syncthreads();
-      unsigned run = warp_sum[wid] + inc - sum;
+      for (unsigned w = 0; w < WPC; w++)
+        if (w < wid) run += warp_sum[w];
       unsigned short *row = off + c * ntp;
 #pragma unroll
-      for (unsigned j = 0; j < 4; j++)
+      for (unsigned j = 0; j < PER; j++)
         if (j < per && b + j < (unsigned) nt)
           {
             hist[b + j] = run;
@@ -654,26 +646,147 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
           }
       if (tid == 0) row[nt] = (unsigned short) n;
       __syncthreads();
-      /* permute in shared memory (the coordinates come back from L2) */
+      /* x: permute in shared memory, copy out; then y through the same buffer */
 #pragma unroll
       for (int k = 0; k < KPT; k++)
         if (pk[k] != 0xffffffffu)
           {
-            const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+            const unsigned i = (unsigned) k * T + tid;
             const unsigned pos = hist[pk[k] & 0xfffu] + (pk[k] >> 12);
-            sx[pos] = __ldg(xq + q0 + i);
-            sy[pos] = __ldg(yq + q0 + i);
+            pk[k] = pos;
+            sbuf[pos] = __ldg(xq + q0 + i);
             si[pos] = (unsigned short) i;
           }
       __syncthreads();
-      for (unsigned i = tid; i < n; i += GSI_BIN_THREADS)
+      for (unsigned i = tid; i < n; i += T)
         {
-          __stcs(bx + q0 + i, sx[i]);
-          __stcs(by + q0 + i, sy[i]);
+          __stcs(bx + q0 + i, sbuf[i]);
           bi[q0 + i] = si[i];
         }
       __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KPT; k++)
+        if (pk[k] != 0xffffffffu)
+          {
+            const unsigned i = (unsigned) k * T + tid;
+            sbuf[pk[k]] = __ldg(yq + q0 + i);
+          }
+      __syncthreads();
+      for (unsigned i = tid; i < n; i += T) __stcs(by + q0 + i, sbuf[i]);
+      __syncthreads();
     }
+}
+
+/* one converged warp step of the tile kernels: every live lane walks the binned query at slot
+ * `pos` of the window (chunk base `cbase`) and stores its result to the binned outputs;
+ * deferred queries are appended to the list under their original index */
+template <bool STATS>
+__device__ __forceinline__ void
+tile_direct_step(const gsi_view &V, const double *__restrict__ bx, const double *__restrict__ by,
+                 const unsigned short *__restrict__ bi, bool live, size_t pos, size_t cbase, double *zb,
+                 int *lb, size_t ldb, unsigned *list, unsigned list_cap, unsigned *ovf_mask,
+                 unsigned *counters, int max_steps, unsigned long long &steps_acc)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  int status = GSI_STEP_MOVE; /* = not a live query */
+  int slot = 0;
+  double c0 = 0, c1 = 0;
+  if (live)
+    {
+      const double qx = __ldcs(bx + pos), qy = __ldcs(by + pos);
+      status = GSI_STEP_DEFER;
+      if (isfinite(qx) && isfinite(qy))
+        {
+          slot = gsi_ld_seed(V.seeds + gsi_cell_of(&V, qx, qy));
+          for (int step = 0; step < max_steps; step++)
+            {
+              gsi_rec rec;
+              const int at = slot;
+              gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
+              const int st = gsi_walk_step(&V.xf, &rec, qx, qy, &slot, &c0, &c1);
+              if (st != GSI_STEP_MOVE)
+                {
+                  status = st;
+                  slot = at;
+                  if (STATS && st == GSI_STEP_ACCEPT) steps_acc += (unsigned) step + 1u;
+                  break;
+                }
+            }
+        }
+    }
+  __syncwarp();
+  if (status == GSI_STEP_ACCEPT)
+    {
+      gsi_leaf_tail tl;
+      gsi_fetch_tail(&tl, gsi_leaf_at(&V, slot));
+      if (lb) lb[pos] = tl.g.node;
+      if (zb) gsi_blend_store(&V, &tl, c0, c1, zb, ldb, pos);
+    }
+  const bool defer = status == GSI_STEP_DEFER;
+  const unsigned dm = __ballot_sync(FULL, defer);
+  if (dm)
+    {
+      const int leader = __ffs(dm) - 1;
+      unsigned at0 = 0;
+      if (lane == (unsigned) leader) at0 = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+      at0 = __shfl_sync(FULL, at0, leader);
+      if (defer)
+        {
+          const size_t q = cbase + bi[pos];
+          const unsigned at = at0 + __popc(dm & ((1u << lane) - 1u));
+          if (at < list_cap)
+            list[at] = (unsigned) q;
+          else
+            mark_overflow(ovf_mask, q, counters);
+        }
+    }
+}
+
+/* lane <-> chunk: load tile t's run in chunk (cb*32 + lane) and the inclusive prefix of the run
+ * lengths over the warp; returns the warp's total */
+__device__ __forceinline__ unsigned
+tile_runs(const unsigned short *__restrict__ off, size_t ntp, unsigned t, unsigned cb, unsigned n_blocks,
+          unsigned n_chunks, unsigned &o0, unsigned &len, unsigned &incl)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned c = (cb << 5) + lane;
+  o0 = 0;
+  len = 0;
+  if (cb < n_blocks && c < n_chunks)
+    {
+      const unsigned short *row = off + (size_t) c * ntp + t;
+      o0 = row[0];
+      len = (unsigned) row[1] - o0;
+    }
+  incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    {
+      const unsigned v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= (unsigned) o) incl += v;
+    }
+  return __shfl_sync(FULL, incl, 31);
+}
+
+/* item k (< total) of the warp's concatenated runs -> binned slot of the window; *cbase = first
+ * slot of the item's chunk.  Must be called by the whole warp. */
+__device__ __forceinline__ size_t
+tile_item(unsigned k, unsigned cb, int S, unsigned o0, unsigned len, unsigned incl, size_t *cbase)
+{
+  const unsigned FULL = 0xffffffffu;
+  unsigned j = 0; /* number of chunks whose inclusive prefix is <= k = the chunk holding item k */
+#pragma unroll
+  for (unsigned step = 16; step; step >>= 1)
+    {
+      const unsigned v = __shfl_sync(FULL, incl, j + step - 1);
+      if (v <= k) j += step;
+    }
+  const unsigned incl_j = __shfl_sync(FULL, incl, j), len_j = __shfl_sync(FULL, len, j),
+                 o0_j = __shfl_sync(FULL, o0, j);
+  *cbase = (size_t) ((cb << 5) + j) * (size_t) S;
+  return *cbase + o0_j + (k - (incl_j - len_j));
 }
 
 template <bool STATS>
@@ -683,112 +796,33 @@ k_tile_locate(const gsi_view V, const double *__restrict__ bx, const double *__r
               unsigned n_chunks, int S, int nt, int shift, int ranges, double *zb, int *lb, size_t ldb,
               unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters, int max_steps)
 {
-  const unsigned FULL = 0xffffffffu;
   const unsigned t = blockIdx.x / (unsigned) ranges, r = blockIdx.x - t * (unsigned) ranges;
   /* Morton ids whose cells all lie beyond the grid hold no query */
   if ((compact8(t) << shift) >= (unsigned) V.grid_g || (compact8(t >> 1) << shift) >= (unsigned) V.grid_g)
     return;
   constexpr unsigned WPC = GSI_TILE_THREADS / 32;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned n_blocks = (n_chunks + 31u) >> 5;
   const size_t ntp = (size_t) nt + 2;
   unsigned long long steps_acc = 0;
   for (unsigned cb = r * WPC + warp; cb < n_blocks; cb += (unsigned) ranges * WPC)
     {
-      /* lane <-> chunk: this tile's run in each of 32 consecutive chunks */
-      const unsigned c = (cb << 5) + lane;
-      unsigned o0 = 0, len = 0;
-      if (c < n_chunks)
-        {
-          const unsigned short *row = off + (size_t) c * ntp + t;
-          o0 = row[0];
-          len = (unsigned) row[1] - o0;
-        }
-      unsigned incl = len;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-        {
-          const unsigned v = __shfl_up_sync(FULL, incl, o);
-          if (lane >= (unsigned) o) incl += v;
-        }
-      const unsigned total = __shfl_sync(FULL, incl, 31);
+      unsigned o0, len, incl;
+      const unsigned total = tile_runs(off, ntp, t, cb, n_blocks, n_chunks, o0, len, incl);
       for (unsigned base = 0; base < total; base += 32)
         {
           const bool live = base + lane < total;
-          const unsigned k = live ? base + lane : total - 1;
-          /* j = number of chunks whose inclusive prefix is <= k = the chunk holding item k */
-          unsigned j = 0;
-#pragma unroll
-          for (unsigned step = 16; step; step >>= 1)
-            {
-              const unsigned v = __shfl_sync(FULL, incl, j + step - 1);
-              if (v <= k) j += step;
-            }
-          const unsigned incl_j = __shfl_sync(FULL, incl, j), len_j = __shfl_sync(FULL, len, j),
-                         o0_j = __shfl_sync(FULL, o0, j);
-          const size_t cbase = (size_t) ((cb << 5) + j) * (size_t) S;
-          const size_t pos = cbase + o0_j + (k - (incl_j - len_j));
-          int status = GSI_STEP_MOVE; /* = not a live query */
-          int slot = 0;
-          double c0 = 0, c1 = 0;
-          if (live)
-            {
-              const double qx = __ldcs(bx + pos), qy = __ldcs(by + pos);
-              status = GSI_STEP_DEFER;
-              if (isfinite(qx) && isfinite(qy))
-                {
-                  slot = gsi_ld_seed(V.seeds + gsi_cell_of(&V, qx, qy));
-                  for (int step = 0; step < max_steps; step++)
-                    {
-                      gsi_rec rec;
-                      const int at = slot;
-                      gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
-                      const int st = gsi_walk_step(&V.xf, &rec, qx, qy, &slot, &c0, &c1);
-                      if (st != GSI_STEP_MOVE)
-                        {
-                          status = st;
-                          slot = at;
-                          if (STATS && st == GSI_STEP_ACCEPT) steps_acc += (unsigned) step + 1u;
-                          break;
-                        }
-                    }
-                }
-            }
-          __syncwarp();
-          if (status == GSI_STEP_ACCEPT)
-            {
-              gsi_leaf_tail tl;
-              gsi_fetch_tail(&tl, gsi_leaf_at(&V, slot));
-              if (lb) lb[pos] = tl.g.node;
-              if (zb) gsi_blend_store(&V, &tl, c0, c1, zb, ldb, pos);
-            }
-          const bool defer = status == GSI_STEP_DEFER;
-          const unsigned dm = __ballot_sync(FULL, defer);
-          if (dm)
-            {
-              const int leader = __ffs(dm) - 1;
-              unsigned at0 = 0;
-              if (lane == (unsigned) leader)
-                at0 = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
-              at0 = __shfl_sync(FULL, at0, leader);
-              if (defer)
-                {
-                  const size_t q = cbase + bi[pos];
-                  const unsigned at = at0 + __popc(dm & lt_mask);
-                  if (at < list_cap)
-                    list[at] = (unsigned) q;
-                  else
-                    mark_overflow(ovf_mask, q, counters);
-                }
-            }
+          size_t cbase;
+          const size_t pos = tile_item(live ? base + lane : total - 1, cb, S, o0, len, incl, &cbase);
+          tile_direct_step<STATS>(V, bx, by, bi, live, pos, cbase, zb, lb, ldb, list, list_cap, ovf_mask,
+                                  counters, max_steps, steps_acc);
         }
     }
   if (STATS && steps_acc)
     atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
 }
 
-__global__ void __launch_bounds__(GSI_BIN_THREADS, 2)
+__global__ void __launch_bounds__(GSI_UNPERMUTE_THREADS, 2)
 k_unpermute(const double *__restrict__ zb, const int *__restrict__ lb, const unsigned short *__restrict__ bi,
             size_t nq, int S, int n_fields, size_t ldb, double *__restrict__ val, size_t ld,
             int *__restrict__ leaf_out)
@@ -798,7 +832,7 @@ k_unpermute(const double *__restrict__ zb, const int *__restrict__ lb, const uns
   int *sl = reinterpret_cast<int *>(sz + S);
   const unsigned tid = threadIdx.x;
   const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
-  constexpr int KPT = GSI_BIN_CHUNK_MAX / GSI_BIN_THREADS;
+  constexpr int KPT = GSI_BIN_CHUNK_MAX / GSI_UNPERMUTE_THREADS;
   for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
     {
       const size_t q0 = c * (size_t) S;
@@ -807,7 +841,7 @@ k_unpermute(const double *__restrict__ zb, const int *__restrict__ lb, const uns
 #pragma unroll
       for (int k = 0; k < KPT; k++)
         {
-          const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+          const unsigned i = (unsigned) k * GSI_UNPERMUTE_THREADS + tid;
           idx[k] = 0;
           if (i < n)
             {
@@ -823,12 +857,12 @@ k_unpermute(const double *__restrict__ zb, const int *__restrict__ lb, const uns
 #pragma unroll
               for (int k = 0; k < KPT; k++)
                 {
-                  const unsigned i = (unsigned) k * GSI_BIN_THREADS + tid;
+                  const unsigned i = (unsigned) k * GSI_UNPERMUTE_THREADS + tid;
                   if (i < n) sz[idx[k]] = __ldcs(zb + (size_t) f * ldb + q0 + i);
                 }
             }
           __syncthreads();
-          for (unsigned i = tid; i < n; i += GSI_BIN_THREADS)
+          for (unsigned i = tid; i < n; i += GSI_UNPERMUTE_THREADS)
             {
               if (val) __stcs(val + (size_t) f * ld + q0 + i, sz[i]);
               if (f == 0 && leaf_out) __stcs(leaf_out + q0 + i, sl[i]);
@@ -931,32 +965,34 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
   if (!R || nq > R->cap || R->chunk < 32 || R->chunk > GSI_BIN_CHUNK_MAX) return false;
   const int S = R->chunk, nt = 1 << (2 * R->tile_bits);
   const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
-  const size_t smem_bin = (size_t) S * 18 + (size_t) nt * 4, smem_unp = (size_t) S * 12;
+  const size_t smem_bin = (size_t) S * 10 + (size_t) nt * 4, smem_unp = (size_t) S * 12;
   static bool attr_done = false;
   if (!attr_done)
     {
-      cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 18 + 4096 * 4);
+      cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 10 + 4096 * 4);
       cudaFuncSetAttribute(k_unpermute, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 12);
       attr_done = true;
     }
-  const int g_bin = (int) (n_chunks < (size_t) cfg.sm_count ? n_chunks : (size_t) cfg.sm_count);
-  k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(V, src.x, src.y, nq, S, R->tile_shift, nt, R->bx, R->by,
-                                                  R->bi, R->off);
+  const int g_bin = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
+  k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(V, src.x, src.y, nq, S, R->tile_shift, nt, R->bx, R->by, R->bi,
+                                                  R->off);
   /* CTAs per tile: every warp of a CTA should get a few 32-chunk blocks, else one CTA per tile */
   const size_t n_blocks = (n_chunks + 31) / 32;
   int ranges = (int) (n_blocks / (4 * (GSI_TILE_THREADS / 32)));
   if (ranges > R->ranges) ranges = R->ranges;
   if (ranges < 1) ranges = 1;
+  double *zb = val ? R->zb : nullptr;
+  int *lb = leaf_out ? R->lb : nullptr;
   if (cfg.stats)
     k_tile_locate<true><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
-        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, val ? R->zb : nullptr,
-        leaf_out ? R->lb : nullptr, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, zb, lb, R->cap,
+        cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
   else
     k_tile_locate<false><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
-        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, val ? R->zb : nullptr,
-        leaf_out ? R->lb : nullptr, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, zb, lb, R->cap,
+        cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
   const int g_unp = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
-  k_unpermute<<<g_unp, GSI_BIN_THREADS, smem_unp, st>>>(R->zb, R->lb, R->bi, nq, S, V.n_fields, R->cap, val, ld,
+  k_unpermute<<<g_unp, GSI_UNPERMUTE_THREADS, smem_unp, st>>>(R->zb, R->lb, R->bi, nq, S, V.n_fields, R->cap, val, ld,
                                                         leaf_out);
   return true;
 }

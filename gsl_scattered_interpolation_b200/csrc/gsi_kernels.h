@@ -12,7 +12,8 @@
 #define GSI_WALK_THREADS 128
 #define GSI_STAGE_THREADS 128
 #define GSI_STAGE_WINDOW 256
-#define GSI_BIN_THREADS 1024    /* k_bin / k_unpermute: one CTA sorts one chunk in shared memory */
+#define GSI_BIN_THREADS 512        /* k_bin: one CTA sorts one chunk in shared memory, two CTAs per SM */
+#define GSI_UNPERMUTE_THREADS 1024 /* k_unpermute */
 #define GSI_BIN_CHUNK_MAX 8192  /* queries per chunk (16-bit in-chunk indices, 160 KB of shared memory) */
 #define GSI_TILE_THREADS 512    /* k_tile_locate */
 #define GSI_TILE_BITS_MAX 6     /* Morton tile id: <= 6 bits per axis = 4096 tiles */
