@@ -66,6 +66,10 @@ _PROTOS = {
     "gsl_scattered_cuda_slab_bytes": (c_size_t, [c_void_p]),
     "gsl_scattered_cuda_slab_export_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "gsl_scattered_cuda_init_from_slab_device": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "gsl_scattered_cuda_save": (c_int, [c_void_p, c_char_p]),
+    "gsl_scattered_cuda_load": (c_int, [c_void_p, c_char_p]),
+    "gsl_scattered_cuda_fwrite": (c_int, [c_void_p, c_void_p]),
+    "gsl_scattered_cuda_fread": (c_int, [c_void_p, c_void_p]),
     "gsl_scattered_cuda_host_alloc": (c_void_p, [c_size_t]),
     "gsl_scattered_cuda_host_free": (None, [c_void_p]),
     "gsl_scattered_cuda_generate_uniform_device": (c_int, [c_void_p, c_int, c_ulonglong,

@@ -7,6 +7,7 @@ tests read like the reference's own driver (scattered_interp_example.c): ``alloc
 addresses (e.g. ``torch.Tensor.data_ptr()``) are device buffers.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -172,6 +173,14 @@ class ScatteredCuda:
         return self._check(st, "eval_raster_device_e", allow=(EDOM,))
 
     # -- helpers ----------------------------------------------------------------------------
+    def save(self, path):
+        """Write the flattened triangulation (slab image) to `path` (gsl_scattered_cuda_save)."""
+        self._check(self._L.gsl_scattered_cuda_save(self._w, os.fsencode(path)), "save")
+
+    def load(self, path):
+        """Restore a slab image written by save(): no host build (gsl_scattered_cuda_load)."""
+        self._check(self._L.gsl_scattered_cuda_load(self._w, os.fsencode(path)), "load")
+
     def info(self):
         inf = Info()
         self._check(self._L.gsl_scattered_cuda_get_info(self._w, ctypes.byref(inf)), "get_info")

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -628,6 +629,60 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
   return 0;
 }
 
+/* FNV-1a over the image with the checksum slot (header.reserved[0]) taken as zero, 8 bytes at
+ * a time (images are multiples of 256 bytes) */
+uint64_t
+slab_checksum(const char *image, size_t bytes)
+{
+  const size_t slot = offsetof(gsi_slab_header, reserved);
+  uint64_t hsh = 0xcbf29ce484222325ull;
+  for (size_t i = 0; i + 8 <= bytes; i += 8)
+    {
+      uint64_t v = 0;
+      if (i != slot) std::memcpy(&v, image + i, 8);
+      hsh = (hsh ^ v) * 0x100000001b3ull;
+    }
+  return hsh;
+}
+
+/* take over a complete slab image (device or host memory; the seed grid is part of it) */
+int
+adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, size_t bytes)
+{
+  if (h.magic != GSI_SLAB_MAGIC || h.version != GSI_SLAB_VERSION || h.total_bytes != bytes)
+    GSI_ERROR("slab header mismatch", GSL_SCATTERED_EINVAL);
+  if (h.n_fields != w->n_fields) GSI_ERROR("n_fields differs from alloc", GSL_SCATTERED_EBADLEN);
+  if (h.off_dag >= bytes || h.off_leaf >= bytes || h.off_z >= bytes || h.off_seeds >= bytes
+      || h.n_dag == 0 || h.grid_g == 0
+      || h.off_dag + h.n_dag * sizeof(gsi_rec) > bytes
+      || h.off_leaf + h.n_leaves * (uint64_t) h.leaf_stride > bytes
+      || h.off_seeds + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes)
+    GSI_ERROR("slab sections out of range", GSL_SCATTERED_EINVAL);
+  drop_replicas(w);
+  w->built = false;
+  w->hdr = h;
+  std::vector<int> devs = w->devs;
+  if (devs.empty())
+    {
+      int cur = 0;
+      CU(cudaGetDevice(&cur));
+      devs.push_back(cur);
+    }
+  for (int d : devs)
+    {
+      replica *r = nullptr;
+      int s = make_replica(d, &r);
+      if (r) w->reps.push_back(r);
+      if (s) return s;
+      apply_l2_fetch(w);
+      CU(cudaMalloc(&r->slab, bytes));
+      r->view = gsi_view_of(r->slab, &w->hdr);
+      CU(cudaMemcpy(r->slab, src, bytes, cudaMemcpyDefault));
+    }
+  w->uploaded = true;
+  return GSL_SCATTERED_SUCCESS;
+}
+
 } // namespace
 
 /* ============================================================================================ */
@@ -1048,32 +1103,90 @@ gsl_scattered_cuda_init_from_slab_device(gsl_scattered_cuda *w, const void *d_sr
     GSI_ERROR("no CUDA device available", GSL_SCATTERED_EFAILED);
   gsi_slab_header h;
   CU(cudaMemcpy(&h, d_src, sizeof h, cudaMemcpyDefault));
-  if (h.magic != GSI_SLAB_MAGIC || h.version != GSI_SLAB_VERSION || h.total_bytes != bytes)
-    GSI_ERROR("slab header mismatch", GSL_SCATTERED_EINVAL);
-  if (h.n_fields != w->n_fields) GSI_ERROR("n_fields differs from alloc", GSL_SCATTERED_EBADLEN);
-  drop_replicas(w);
-  w->built = false;
-  w->hdr = h;
-  std::vector<int> devs = w->devs;
-  if (devs.empty())
+  return adopt_slab(w, h, d_src, bytes);
+}
+
+int
+gsl_scattered_cuda_fwrite(FILE *stream, const gsl_scattered_cuda *w)
+{
+  if (!stream || !w) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  if (!w->uploaded || w->reps.empty()) GSI_ERROR("nothing to write: workspace not initialised", GSL_SCATTERED_EINVAL);
+  replica *r = w->reps[0];
+  std::vector<char> image;
+  try
     {
-      int cur = 0;
-      CU(cudaGetDevice(&cur));
-      devs.push_back(cur);
+      image.resize((size_t) w->hdr.total_bytes);
     }
-  for (int d : devs)
+  catch (const std::bad_alloc &)
     {
-      replica *r = nullptr;
-      int s = make_replica(d, &r);
-      if (r) w->reps.push_back(r);
-      if (s) return s;
-      apply_l2_fetch(w);
-      CU(cudaMalloc(&r->slab, bytes));
-      r->view = gsi_view_of(r->slab, &w->hdr);
-      CU(cudaMemcpy(r->slab, d_src, bytes, cudaMemcpyDefault));
+      GSI_ERROR("out of host memory for the slab image", GSL_SCATTERED_ENOMEM);
     }
-  w->uploaded = true;
+  {
+    std::lock_guard<std::mutex> lock(r->mu);
+    CU(cudaSetDevice(r->dev));
+    CU(cudaStreamSynchronize(r->s_k));
+    CU(cudaMemcpy(image.data(), r->slab, image.size(), cudaMemcpyDeviceToHost));
+  }
+  gsi_slab_header h;
+  std::memcpy(&h, image.data(), sizeof h);
+  h.reserved[0] = slab_checksum(image.data(), image.size());
+  std::memcpy(image.data(), &h, sizeof h);
+  if (fwrite(image.data(), 1, image.size(), stream) != image.size())
+    GSI_ERROR("fwrite failed", GSL_SCATTERED_EFAILED);
   return GSL_SCATTERED_SUCCESS;
+}
+
+int
+gsl_scattered_cuda_fread(FILE *stream, gsl_scattered_cuda *w)
+{
+  if (!stream || !w) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  gsi_slab_header h;
+  if (fread(&h, 1, sizeof h, stream) != sizeof h) GSI_ERROR("fread failed", GSL_SCATTERED_EFAILED);
+  if (h.magic != GSI_SLAB_MAGIC || h.version != GSI_SLAB_VERSION || h.total_bytes < sizeof h
+      || h.total_bytes > ((uint64_t) 1 << 40))
+    GSI_ERROR("not a slab image of this library version", GSL_SCATTERED_EINVAL);
+  if (h.n_fields != w->n_fields) GSI_ERROR("n_fields differs from alloc", GSL_SCATTERED_EBADLEN);
+  std::vector<char> image;
+  try
+    {
+      image.resize((size_t) h.total_bytes);
+    }
+  catch (const std::bad_alloc &)
+    {
+      GSI_ERROR("out of host memory for the slab image", GSL_SCATTERED_ENOMEM);
+    }
+  std::memcpy(image.data(), &h, sizeof h);
+  const size_t rest = image.size() - sizeof h;
+  if (fread(image.data() + sizeof h, 1, rest, stream) != rest) GSI_ERROR("fread failed", GSL_SCATTERED_EFAILED);
+  if (h.reserved[0] != slab_checksum(image.data(), image.size()))
+    GSI_ERROR("slab image checksum mismatch", GSL_SCATTERED_EINVAL);
+  if (gsl_scattered_cuda_device_count() <= 0)
+    GSI_ERROR("no CUDA device available: libgsl_scattered_cuda has no CPU evaluation path",
+              GSL_SCATTERED_EFAILED);
+  return adopt_slab(w, h, image.data(), image.size());
+}
+
+int
+gsl_scattered_cuda_save(const gsl_scattered_cuda *w, const char *path)
+{
+  if (!w || !path) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  if (!w->uploaded || w->reps.empty()) GSI_ERROR("nothing to write: workspace not initialised", GSL_SCATTERED_EINVAL);
+  FILE *f = fopen(path, "wb");
+  if (!f) GSI_ERROR("cannot open file for writing", GSL_SCATTERED_EFAILED);
+  const int s = gsl_scattered_cuda_fwrite(f, w);
+  if (fclose(f) != 0 && s == GSL_SCATTERED_SUCCESS) GSI_ERROR("fclose failed", GSL_SCATTERED_EFAILED);
+  return s;
+}
+
+int
+gsl_scattered_cuda_load(gsl_scattered_cuda *w, const char *path)
+{
+  if (!w || !path) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  FILE *f = fopen(path, "rb");
+  if (!f) GSI_ERROR("cannot open file for reading", GSL_SCATTERED_EFAILED);
+  const int s = gsl_scattered_cuda_fread(f, w);
+  fclose(f);
+  return s;
 }
 
 void *

@@ -92,3 +92,19 @@ def test_build_reports_info_without_gpu():
     assert info["n_nodes"] == 1000 and info["n_simplexes"] == 8967 and info["n_devices"] == 0
     assert info["build_seconds"] > 0
     w.free()
+
+
+def test_slab_file_argument_and_format_checks(tmp_path):
+    """gsl_scattered_cuda_save/load: the host-side checks need no GPU"""
+    L = _lib.load()
+    w = L.gsl_scattered_cuda_alloc(10, 1)
+    assert L.gsl_scattered_cuda_save(w, os.fsencode(tmp_path / "x.gsltri")) == g.EINVAL   # nothing uploaded
+    assert L.gsl_scattered_cuda_load(w, os.fsencode(tmp_path / "missing.gsltri")) == g.EFAILED
+    junk = tmp_path / "junk.gsltri"
+    junk.write_bytes(b"\x00" * 4096)
+    assert L.gsl_scattered_cuda_load(w, os.fsencode(junk)) == g.EINVAL                     # bad magic
+    short = tmp_path / "short.gsltri"
+    short.write_bytes(b"GSISLAB1")
+    assert L.gsl_scattered_cuda_load(w, os.fsencode(short)) == g.EFAILED                   # "fread failed"
+    assert L.gsl_scattered_cuda_save(None, b"x") == g.EINVAL
+    L.gsl_scattered_cuda_free(w)

@@ -499,3 +499,42 @@ def test_reorder_pipeline_scale_vs_exact_and_direct(n, nq, window):
     assert np.array_equal(res["reorder"][1][sub].cpu().numpy(), pl)
     assert refimpl.same_bits(res["reorder"][0][sub].cpu().numpy().reshape(1, -1), pv)
     w.free()
+
+
+def test_slab_save_load_round_trip(golden, tmp_path):
+    """the flattened triangulation written to a file and restored into a
+    fresh workspace (no host build) evaluates bit-identically; a flipped byte is detected."""
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000))
+    path = tmp_path / "cfg1.gsltri"
+    w.save(path)
+    assert path.stat().st_size == w.info()["slab_bytes"]
+    w.free()
+    w2 = g.ScatteredCuda(1000, 1)
+    w2.load(path)
+    xq, yq = synth.uniform_queries(10000)
+    for mode in (0, 1):
+        w2.set_param("mode", mode)
+        st, zq, leaf = w2.eval_e(xq, yq)
+        assert st == g.SUCCESS
+        assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq, golden["cfg1_val"])
+    x0, dx, nx, y0, dy, ny = golden["cfg1_raster_spec"]
+    st, rz, rl = w2.eval_raster_e(x0, dx, int(nx), y0, dy, int(ny))
+    assert np.array_equal(rl, golden["cfg1_raster_leaf"]) and refimpl.same_bits(rz, golden["cfg1_raster_val"])
+    info = w2.info()
+    assert info["n_leaves"] == 2001 and info["n_simplexes"] == 8967
+    w2.free()
+    raw = bytearray(path.read_bytes())
+    raw[len(raw) // 2] ^= 0x40
+    bad = tmp_path / "bad.gsltri"
+    bad.write_bytes(bytes(raw))
+    w3 = g.ScatteredCuda(1000, 1)
+    with pytest.raises(g.GslError) as e:
+        w3.load(bad)
+    assert e.value.status == g.EINVAL
+    w3.free()
+    w4 = g.ScatteredCuda(1000, 2)                       # n_fields differs from the image
+    with pytest.raises(g.GslError) as e:
+        w4.load(path)
+    assert e.value.status == g.EBADLEN
+    w4.free()
