@@ -197,6 +197,8 @@ def main_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if g.device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device: libgsl_scattered_cuda has no CPU path")
     torch.cuda.set_device(local)
@@ -343,12 +345,15 @@ def main_ours(args):
         kernel_name = "k_bin + k_tile_locate + k_unpermute (reorder pipeline)" if reordered else "k_walk"
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per query,
         # scaled to this launch); only valid for the configuration the capture was taken on
-        traffic, traffic_src = None, None
+        traffic, traffic_src, ncu_counters = None, None, None
         try:
             with open(os.path.join(ROOT, "profiles", "r1c_k_walk_traffic.json")) as f:
                 tj = json.load(f)
             if not reordered and n == 1_000_000 and F == 1:
                 traffic = tj["dram_bytes_per_query"] * Q
+                ncu_counters = {k: tj[k] for k in ("dram_throughput_pct_of_peak", "lts_sector_hit_rate_pct",
+                                                   "branch_targets_threads_uniform_pct", "sm_warps_active_pct",
+                                                   "l1_sectors_per_query") if k in tj}
                 traffic_src = (f"{tj['dram_bytes_per_query']:.1f} B/query x {Q} queries; ncu dram__bytes_read+write.sum "
                                f"of one {tj['queries_per_launch']}-query launch ({tj['source']})")
         except Exception:
@@ -371,7 +376,7 @@ def main_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "traffic_source": traffic_src,
+                         "traffic_source": traffic_src, "ncu": ncu_counters,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel_ms_per_launch": 1e3 * locate_s, "exact_replay_ms_per_step": 1e3 * exact_s},
             "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),

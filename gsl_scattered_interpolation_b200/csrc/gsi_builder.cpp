@@ -637,7 +637,7 @@ builder::run(const double *xa, const double *ya, size_t n, int flags, const int6
     {
       int last = -1;
       gsi_rec leaf_rec;
-      const int leaf = descend_view(&view, &T.xf, px_[i], py_[i], &c0_, &c1_, &last, &leaf_rec);
+      const int leaf = descend_view(&view, &T.xf, 0, px_[i], py_[i], &c0_, &c1_, &last, &leaf_rec);
       if (leaf < 0) return fail("given point outside the domain");
       const int st = insert_point(leaf);
       if (st) return st;

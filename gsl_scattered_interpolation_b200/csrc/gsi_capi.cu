@@ -121,6 +121,7 @@ struct gsl_scattered_cuda
   size_t reorder_window = (size_t) 1 << 27, reorder_min = (size_t) 1 << 22;
   int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_shift = -1, tile_ranges = 4, tile_leaves = 1024;
   size_t reorder_max_fields = 2;
+  int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
   size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
   double list_fraction = 1.0 / 8;
@@ -612,10 +613,12 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
       apply_l2_fetch(w);
       CU(cudaMalloc(&r->slab, w->hdr.total_bytes));
       r->view = gsi_view_of(r->slab, &w->hdr);
+      if (!w->exact_entry) r->view.entry = nullptr;
     }
   replica *r0 = w->reps[0];
   CU(cudaSetDevice(r0->dev));
   CU(cudaMemcpyAsync(r0->slab, image.data(), image.size(), cudaMemcpyHostToDevice, r0->s_k));
+  CU(gsi_launch_entry_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_entry), r0->sm_count, r0->s_k));
   CU(gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->sm_count,
                            r0->s_k));
   CU(cudaStreamSynchronize(r0->s_k));
@@ -656,7 +659,8 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       || h.n_dag == 0 || h.grid_g == 0
       || h.off_dag + h.n_dag * sizeof(gsi_rec) > bytes
       || h.off_leaf + h.n_leaves * (uint64_t) h.leaf_stride > bytes
-      || h.off_seeds + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes)
+      || h.off_seeds + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes
+      || h.off_entry >= bytes || h.off_entry + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes)
     GSI_ERROR("slab sections out of range", GSL_SCATTERED_EINVAL);
   drop_replicas(w);
   w->built = false;
@@ -677,6 +681,7 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       apply_l2_fetch(w);
       CU(cudaMalloc(&r->slab, bytes));
       r->view = gsi_view_of(r->slab, &w->hdr);
+      if (!w->exact_entry) r->view.entry = nullptr;
       CU(cudaMemcpy(r->slab, src, bytes, cudaMemcpyDefault));
     }
   w->uploaded = true;
@@ -778,6 +783,12 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "tile_shift" && value >= -1 && value <= 15) w->tile_shift = (int) value;
   else if (k == "tile_ranges" && value >= 1 && value <= 64) w->tile_ranges = (int) value;
   else if (k == "tile_leaves" && value >= 1) w->tile_leaves = (int) value;
+  else if (k == "exact_entry" && (value == 0 || value == 1))
+    {
+      w->exact_entry = (int) value;
+      for (replica *r : w->reps)
+        r->view.entry = value != 0 ? (const int32_t *) (r->slab + w->hdr.off_entry) : nullptr;
+    }
   else GSI_ERROR("unknown parameter or value out of range", GSL_SCATTERED_EINVAL);
   return GSL_SCATTERED_SUCCESS;
 }

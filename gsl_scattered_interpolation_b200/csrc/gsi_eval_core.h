@@ -205,40 +205,6 @@ gsi_blend_store(const gsi_view *V, const gsi_leaf_tail *t, double c0, double c1,
     }
 }
 
-#define GSI_EXACT_OUTSIDE (-1)
-
-/* Exact replay of one query.  Returns the leaf's compact slot (>= 0) or GSI_EXACT_OUTSIDE;
- * writes leaf_out[q] (reference node id, -1 outside) and val (NaN outside) when non-NULL. */
-GSI_HD int
-gsi_exact_one(const gsi_view *V, double qx, double qy, double *val, int *leaf_out, size_t ld,
-              size_t q)
-{
-  double c0 = 0, c1 = 0;
-  int last = -1;
-  gsi_rec lr;
-  const int node = gsi_descend(V->dag, &V->xf, qx, qy, &c0, &c1, &last, &lr);
-  if (node < 0)
-    {
-      if (leaf_out) leaf_out[q] = -1;
-      if (val)
-        for (int f = 0; f < V->n_fields; f++) val[(size_t) f * ld + q] = GSI_NAN;
-      return GSI_EXACT_OUTSIDE;
-    }
-  const int slot = lr.lnk[0];
-  /* interp_point recomputes the leaf's coordinates unless the leaf is singular, in which
-     case accel->coords keeps whatever the descent left there (linear_simplex.c:641-642,687) */
-  if (!(lr.meta & GSI_META_SINGULAR) && last != node)
-    gsi_solve(&V->xf, &lr, (int) (lr.meta & GSI_META_SWAP), qx, qy, &c0, &c1);
-  if (leaf_out) leaf_out[q] = node;
-  if (val)
-    {
-      gsi_leaf_tail t;
-      gsi_fetch_tail(&t, gsi_leaf_at(V, slot));
-      gsi_blend_store(V, &t, c0, c1, val, ld, q);
-    }
-  return slot;
-}
-
 /* grid cell of a query in standardised coordinates (a hint only: no exactness needed;
  * fmin/fmax drop NaN so non-finite queries land in cell 0) */
 GSI_HD size_t
@@ -261,6 +227,142 @@ gsi_cell_centre(const gsi_view *V, size_t cell, double *qx, double *qy)
   const double v = V->v0 + ((double) iy + 0.5) / V->inv_dv;
   *qx = V->xf.cx + u / V->xf.sx;
   *qy = V->xf.cy + v / V->xf.sy;
+}
+
+/* ---- entry nodes of the exact replay ------------------------------------------------------------
+ * The reference descends ~50 history-DAG levels per query at 10^6 nodes, and every level costs
+ * up to three divergent 64-byte record fetches.  Most of those levels decide nothing for a
+ * small neighbourhood: if a whole grid cell lies inside child j of a node with a safety margin,
+ * and outside every earlier sibling with the same margin, then the reference's test sequence
+ * (children in link order, first closed-interval pass wins, linear_simplex.c:363-373) takes
+ * child j for EVERY point of the cell.  gsi_entry_of_cell follows such certified steps from the
+ * root and returns the last node reached; a query of that cell may start its replay there with
+ * accel->coords = that node's coordinates, exactly the state the reference arrives with.
+ *
+ * Certificates (barycentric weights are affine, so the four corners of the slightly enlarged
+ * cell bound the whole cell): PASS = all three weights of all four corners >= 2*tau, FAIL = one
+ * weight index whose value is <= -2*tau at all four corners, tau = delta * Lmax / |det| being
+ * the weight change of a `delta` move towards an edge line (same margin as the fast path's
+ * acceptance; delta = 2^-28 standardised units, four orders above the rounding error of the
+ * solve).  Children that are singular or have link 0 fail in the reference without a test
+ * (linear_simplex.c:366, 641-642).  Anything else stops the walk.  Border cells also receive
+ * the clamped queries from outside the grid (and the non-finite ones), so they keep the root. */
+GSI_HD double
+gsi_rec_tau(const gsi_rec *r, double delta)
+{
+  /* columns of the edge matrix (a - x0, b - x0) up to the row swap, which does not change
+     lengths: M = L*U */
+  const double m00 = r->u00, m01 = r->u01;
+  const double m10 = r->l10 * r->u00, m11 = r->u11 + r->l10 * r->u01;
+  const double e0 = sqrt(m00 * m00 + m10 * m10), e1 = sqrt(m01 * m01 + m11 * m11);
+  const double dx = m00 - m01, dy = m10 - m11;
+  const double e2 = sqrt(dx * dx + dy * dy);
+  double lmax = e0 > e1 ? e0 : e1;
+  if (e2 > lmax) lmax = e2;
+  const double det = fabs(r->u00 * r->u11);
+  return delta * lmax / det; /* NaN / inf for degenerate records: never certified */
+}
+
+/* 1 = the cell certainly passes record r, -1 = certainly fails, 0 = undecided */
+GSI_HD int
+gsi_cell_vs_rec(const gsi_xform *xf, const gsi_rec *r, double delta, const double cx[4],
+                const double cy[4])
+{
+  const double tau2 = 2.0 * gsi_rec_tau(r, delta);
+  if (!(tau2 < 0.5)) return 0;
+  int all_in = 1, out0 = 1, out1 = 1, out2 = 1;
+  for (int k = 0; k < 4; k++)
+    {
+      double c0, c1;
+      gsi_solve(xf, r, (int) (r->meta & GSI_META_SWAP), cx[k], cy[k], &c0, &c1);
+      const double c2 = 1.0 - (c0 + c1);
+      if (!(c0 >= tau2 && c1 >= tau2 && c2 >= tau2)) all_in = 0;
+      if (!(c0 <= -tau2)) out0 = 0;
+      if (!(c1 <= -tau2)) out1 = 0;
+      if (!(c2 <= -tau2)) out2 = 0;
+    }
+  if (all_in) return 1;
+  return (out0 | out1 | out2) ? -1 : 0;
+}
+
+GSI_HD int
+gsi_entry_of_cell(const gsi_view *V, size_t cell)
+{
+  const size_t g = (size_t) V->grid_g;
+  const size_t iy = cell / g, ix = cell - iy * g;
+  if (ix == 0 || iy == 0 || ix + 1 >= g || iy + 1 >= g) return 0;
+  const double pad = 1.0 / 1024; /* of a cell: covers the rounding of gsi_cell_of by far */
+  double cx[4], cy[4];
+  for (int k = 0; k < 4; k++)
+    {
+      const double u = V->u0 + ((double) ix + ((k & 1) ? 1.0 + pad : -pad)) / V->inv_du;
+      const double v = V->v0 + ((double) iy + ((k & 2) ? 1.0 + pad : -pad)) / V->inv_dv;
+      cx[k] = V->xf.cx + u / V->xf.sx;
+      cy[k] = V->xf.cy + v / V->xf.sy;
+    }
+  const gsi_rec *dag = V->dag;
+  gsi_rec cur;
+  GSI_FETCH_DAG(cur, 0);
+  if (cur.meta & GSI_META_SINGULAR) return 0;
+  if (gsi_cell_vs_rec(&V->xf, &cur, V->delta, cx, cy) != 1) return 0;
+  int node = 0;
+  for (int guard = 0; guard < GSI_MAX_DESCENT; guard++)
+    {
+      const uint32_t type = cur.meta & GSI_META_TYPE_MASK;
+      if (type == GSI_LEAF) break;
+      const int nch = (type == GSI_SUB_DPLUS1) ? 3 : 2;
+      int chosen = 0;
+      gsi_rec rc;
+      for (int i = 0; i < nch; i++)
+        {
+          const int k = GSI_LNK(cur, i);
+          if (!k) continue;                          /* link 0: fails without a test */
+          GSI_FETCH_DAG(rc, k);
+          if (rc.meta & GSI_META_SINGULAR) continue; /* singular: fails without a test */
+          const int verdict = gsi_cell_vs_rec(&V->xf, &rc, V->delta, cx, cy);
+          if (verdict == 1) chosen = k;
+          if (verdict != -1) break;                  /* taken, or undecided: stop looking */
+        }
+      if (!chosen) break;
+      node = chosen;
+      cur = rc;
+    }
+  return node;
+}
+
+#define GSI_EXACT_OUTSIDE (-1)
+
+/* Exact replay of one query.  Returns the leaf's compact slot (>= 0) or GSI_EXACT_OUTSIDE;
+ * writes leaf_out[q] (reference node id, -1 outside) and val (NaN outside) when non-NULL. */
+GSI_HD int
+gsi_exact_one(const gsi_view *V, double qx, double qy, double *val, int *leaf_out, size_t ld,
+              size_t q)
+{
+  double c0 = 0, c1 = 0;
+  int last = -1;
+  gsi_rec lr;
+  const int start = V->entry ? GSI_LDG(V->entry + gsi_cell_of(V, qx, qy)) : 0;
+  const int node = gsi_descend(V->dag, &V->xf, start, qx, qy, &c0, &c1, &last, &lr);
+  if (node < 0)
+    {
+      if (leaf_out) leaf_out[q] = -1;
+      if (val)
+        for (int f = 0; f < V->n_fields; f++) val[(size_t) f * ld + q] = GSI_NAN;
+      return GSI_EXACT_OUTSIDE;
+    }
+  const int slot = lr.lnk[0];
+  /* interp_point recomputes the leaf's coordinates unless the leaf is singular, in which
+     case accel->coords keeps whatever the descent left there (linear_simplex.c:641-642,687) */
+  if (!(lr.meta & GSI_META_SINGULAR) && last != node)
+    gsi_solve(&V->xf, &lr, (int) (lr.meta & GSI_META_SWAP), qx, qy, &c0, &c1);
+  if (leaf_out) leaf_out[q] = node;
+  if (val)
+    {
+      gsi_leaf_tail t;
+      gsi_fetch_tail(&t, gsi_leaf_at(V, slot));
+      gsi_blend_store(V, &t, c0, c1, val, ld, q);
+    }
+  return slot;
 }
 
 #define GSI_STEP_ACCEPT 0 /* strictly inside with margin: the leaf is the answer */

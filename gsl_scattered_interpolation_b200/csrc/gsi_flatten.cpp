@@ -159,6 +159,7 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   h.off_leaf = off;  off = align256(off + L * leaf_stride);
   h.off_z = off;     off = align256(off + std::max<size_t>(1, n) * n_fields * sizeof(double));
   h.off_seeds = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
+  h.off_entry = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
   h.total_bytes = off;
 
   image->assign((size_t) h.total_bytes, 0);

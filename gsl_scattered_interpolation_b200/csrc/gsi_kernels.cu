@@ -178,6 +178,17 @@ k_seed_cells(const gsi_view V, int32_t *seeds)
     }
 }
 
+/* entry[cell] = deepest DAG node every query of the cell is certain to pass (gsi_eval_core.h) */
+__global__ void __launch_bounds__(128)
+k_entry_cells(const gsi_view V, int32_t *entry)
+{
+  const unsigned g = (unsigned) V.grid_g;
+  const size_t ncell = (size_t) g * g;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += stride)
+    entry[q] = gsi_entry_of_cell(&V, q);
+}
+
 /* rare: the deferred list is full -- mark the query in the overflow bitmask; k_exact_overflow
  * resolves the marked queries after the main kernel (no exact replay inside the hot loops) */
 __device__ __forceinline__ void
@@ -1111,6 +1122,14 @@ gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count, cudaStrea
 {
   const size_t ncell = (size_t) V.grid_g * V.grid_g;
   k_seed_cells<<<grid_for(ncell, 128, sm_count, 16), 128, 0, st>>>(V, seeds);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_entry_cells(const gsi_view &V, int32_t *entry, int sm_count, cudaStream_t st)
+{
+  const size_t ncell = (size_t) V.grid_g * V.grid_g;
+  k_entry_cells<<<grid_for(ncell, 128, sm_count, 16), 128, 0, st>>>(V, entry);
   return cudaGetLastError();
 }
 

@@ -89,6 +89,10 @@ cudaError_t gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, doub
 cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count,
                                   cudaStream_t st);
 
+/* fill the entry section (per-cell start node of the exact replay); run before the seeding */
+cudaError_t gsi_launch_entry_cells(const gsi_view &V, int32_t *entry, int sm_count,
+                                   cudaStream_t st);
+
 cudaError_t gsi_launch_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo,
                                    double xhi, double ylo, double yhi, double *xq, double *yq,
                                    int sm_count, cudaStream_t st);

@@ -17,6 +17,10 @@
  *   seeds    int32[G*G]         uniform grid over the data bounding box in standardised
  *                               coordinates: leaf slot containing the cell centre
  *                               (filled on the device by the exact-replay kernel)
+ *   entry    int32[G*G]         per grid cell, the deepest history-DAG node that the reference's
+ *                               descent provably passes through for EVERY point of the cell
+ *                               (0 = root): where the exact replay of a query of that cell
+ *                               starts (filled on the device, gsi_entry_of_cell)
  *
  * Reference data model this flattens: simplex_tree / simplex_tree_node pools,
  * /root/reference/interpolation/linear_simplex.h:16-65 (POINT/LINK/LEAF/DATA_POINT).
@@ -29,7 +33,7 @@
 #include "gsi_core.h"
 
 #define GSI_SLAB_MAGIC 0x3142414c53495347ull /* "GSISLAB1" */
-#define GSI_SLAB_VERSION 2u
+#define GSI_SLAB_VERSION 3u
 
 /* One compacted leaf: 96 bytes = three 32-byte sectors, each fetched with one 256-bit load
  * (LDG.E.256 on sm_100a).  A walk step reads r (sectors 0-1); only the accepted leaf's tail
@@ -77,7 +81,8 @@ typedef struct
   double delta; /* absolute safety margin (standardised units) behind the per-leaf tau */
   uint64_t off_dag, off_leaf, off_z, off_seeds;
   uint64_t total_bytes;
-  uint64_t reserved[8];
+  uint64_t reserved[7]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
+  uint64_t off_entry;
 } gsi_slab_header;
 
 /* what the kernels receive by value */
@@ -88,7 +93,9 @@ typedef struct
   const char *leaf; /* gsi_leaf records, leaf_stride bytes apart */
   const double *z;
   const int32_t *seeds;
+  const int32_t *entry; /* NULL: exact replay always starts at the root */
   double u0, v0, inv_du, inv_dv;
+  double delta;
   int32_t grid_g;
   int32_t n_fields;
   int32_t n_dag;
@@ -118,6 +125,8 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   v.leaf_stride = (int32_t) h->leaf_stride;
   v.z = (const double *) (b + h->off_z);
   v.seeds = (const int32_t *) (b + h->off_seeds);
+  v.entry = (const int32_t *) (b + h->off_entry);
+  v.delta = h->delta;
   v.u0 = h->u0; v.v0 = h->v0; v.inv_du = h->inv_du; v.inv_dv = h->inv_dv;
   v.grid_g = (int32_t) h->grid_g;
   v.n_fields = (int32_t) h->n_fields;

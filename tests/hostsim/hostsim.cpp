@@ -27,7 +27,7 @@ extern "C" {
 
 hostsim *
 hostsim_create(const double *xa, const double *ya, const double *za, size_t n, size_t n_fields,
-               int flags, const size_t *order, double cells_per_leaf, double delta)
+               int flags, const size_t *order, double cells_per_leaf, double delta, int exact_entry)
 {
   hostsim *h = new hostsim();
   gsi_host_tree tree;
@@ -53,9 +53,15 @@ hostsim_create(const double *xa, const double *ya, const double *za, size_t n, s
     }
   std::memcpy(&h->hdr, h->image.data(), sizeof h->hdr);
   h->view = gsi_view_of(h->image.data(), &h->hdr);
+  const size_t ncell = (size_t) h->hdr.grid_g * h->hdr.grid_g;
+  /* what k_entry_cells does on the device (exact_entry = 0: every replay starts at the root) */
+  int32_t *entry = (int32_t *) (h->image.data() + h->hdr.off_entry);
+  if (exact_entry)
+    for (size_t c = 0; c < ncell; c++) entry[c] = gsi_entry_of_cell(&h->view, c);
+  else
+    h->view.entry = nullptr;
   /* what k_seed_cells does on the device */
   int32_t *seeds = (int32_t *) (h->image.data() + h->hdr.off_seeds);
-  const size_t ncell = (size_t) h->hdr.grid_g * h->hdr.grid_g;
   for (size_t c = 0; c < ncell; c++)
     {
       double qx, qy;
@@ -74,6 +80,9 @@ hostsim_free(hostsim *h)
 
 size_t hostsim_n_leaves(const hostsim *h) { return (size_t) h->hdr.n_leaves; }
 size_t hostsim_grid_g(const hostsim *h) { return (size_t) h->hdr.grid_g; }
+const int32_t *hostsim_entry(const hostsim *h) { return (const int32_t *) (h->image.data() + h->hdr.off_entry); }
+/* depth of DAG node `node` below the root is not stored; report the node type instead */
+int hostsim_node_is_leaf(const hostsim *h, int node) { return (h->view.dag[node].meta & GSI_META_TYPE_MASK) == GSI_LEAF; }
 
 /* mode 0: k_locate + k_exact_list protocol; mode 1: k_exact_all.
  * stats[0] = deferred, stats[1] = walk steps of accepted queries, stats[2] = outside cage */

@@ -19,7 +19,11 @@ def lib():
         H = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
         H.hostsim_create.restype = c_void_p
         H.hostsim_create.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_void_p,
-                                     c_double, c_double]
+                                     c_double, c_double, c_int]
+        H.hostsim_entry.restype = c_void_p
+        H.hostsim_entry.argtypes = [c_void_p]
+        H.hostsim_node_is_leaf.restype = c_int
+        H.hostsim_node_is_leaf.argtypes = [c_void_p, c_int]
         H.hostsim_free.argtypes = [c_void_p]
         H.hostsim_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int,
                                    c_int, c_void_p]
@@ -32,7 +36,7 @@ def lib():
 
 
 class HostSim:
-    def __init__(self, xa, ya, za, flags=0, order=None, cells_per_leaf=0.0, delta=0.0):
+    def __init__(self, xa, ya, za, flags=0, order=None, cells_per_leaf=0.0, delta=0.0, exact_entry=1):
         self.H = lib()
         xa = np.ascontiguousarray(xa, dtype=np.float64)
         ya = np.ascontiguousarray(ya, dtype=np.float64)
@@ -40,9 +44,18 @@ class HostSim:
         self.F = za.shape[0]
         order = None if order is None else np.ascontiguousarray(order, dtype=np.uint64)
         self.h = self.H.hostsim_create(_p(xa), _p(ya), _p(za), xa.size, self.F, flags, _p(order),
-                                       cells_per_leaf, delta)
+                                       cells_per_leaf, delta, exact_entry)
         if not self.h:
             raise RuntimeError("hostsim_create failed")
+
+    def entry(self):
+        """per-cell start node of the exact replay (what k_entry_cells computes on the device)"""
+        g = self.H.hostsim_grid_g(self.h)
+        buf = (ctypes.c_int32 * (g * g)).from_address(self.H.hostsim_entry(self.h))
+        return np.frombuffer(buf, dtype=np.int32).copy()
+
+    def node_is_leaf(self, node):
+        return bool(self.H.hostsim_node_is_leaf(self.h, int(node)))
 
     def close(self):
         if self.h:

@@ -128,3 +128,54 @@ def test_linear_precision_property():
     want = xq + 1000.0 * yq
     assert np.max(np.abs(val[0] - want) / np.abs(want)) < 1e-12
     hs.close()
+
+
+@pytest.mark.parametrize("kind,cpl", [("uniform", 4.0), ("uniform", 32.0), ("clustered", 4.0), ("grid10", 16.0)])
+def test_logic_entry_nodes_shortcut_is_transparent(golden, kind, cpl):
+    """The exact replay started at the per-cell entry node (gsi_entry_of_cell) must return what
+    the replay from the root returns -- for random queries, queries on vertices and edge
+    midpoints, and queries on the grid-cell borders where the cell assignment flips -- and the
+    shortcut must be real (most cells start well below the root)."""
+    rng = np.random.default_rng(11)
+    if kind == "uniform":
+        n = 1000
+        xa, ya = synth.uniform_nodes(n)
+        flags, order = g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
+    elif kind == "clustered":
+        n = 3000
+        xa, ya = synth.clustered_nodes(n)
+        flags, order = g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
+    else:
+        n = 100
+        xa, ya = (np.arange(100) % 10).astype(float), (np.arange(100) // 10).astype(float)
+        flags, order = g.NOSTANDARDIZE, None
+    za = synth.values(n, 2)
+    a = HostSim(xa, ya, za, flags, order, cells_per_leaf=cpl, exact_entry=1)
+    b = HostSim(xa, ya, za, flags, order, cells_per_leaf=cpl, exact_entry=0)
+    G = a.H.hostsim_grid_g(a.h)
+    x0, x1, y0, y1 = xa.min(), xa.max(), ya.min(), ya.max()
+    k = rng.integers(0, n, (4000, 2))
+    border = np.arange(0, G + 1) / G
+    bx = x0 + (x1 - x0) * np.repeat(border, 8)
+    by = y0 + (y1 - y0) * rng.uniform(0, 1, bx.size)
+    xq = np.concatenate([rng.uniform(x0 - 0.2 * (x1 - x0), x1 + 0.2 * (x1 - x0), 20000), xa,
+                         0.5 * (xa[k[:, 0]] + xa[k[:, 1]]), bx, by * 0 + rng.uniform(x0, x1, bx.size),
+                         np.nextafter(bx, np.inf), np.nextafter(bx, -np.inf)])
+    yq = np.concatenate([rng.uniform(y0 - 0.2 * (y1 - y0), y1 + 0.2 * (y1 - y0), 20000), ya,
+                         0.5 * (ya[k[:, 0]] + ya[k[:, 1]]), by, y0 + (y1 - y0) * np.repeat(border, 8),
+                         by, by])
+    for mode in (1, 0):
+        la, va, _ = a.eval(xq, yq, mode)
+        lb, vb, _ = b.eval(xq, yq, mode)
+        assert np.array_equal(la, lb)
+        assert refimpl.same_bits(va, vb)
+    ent = a.entry()
+    interior = ent.reshape(G, G)[1:-1, 1:-1].ravel()
+    assert (ent.reshape(G, G)[0] == 0).all() and (ent.reshape(G, G)[:, -1] == 0).all()   # border cells: root
+    assert (b.entry() == 0).all()
+    if kind != "grid10":
+        assert (interior != 0).mean() > 0.9
+        if cpl > 8:                                  # fine cells often sit inside one leaf
+            assert any(a.node_is_leaf(e) for e in interior[:: max(1, interior.size // 2000)])
+    a.close()
+    b.close()
