@@ -538,3 +538,38 @@ def test_slab_save_load_round_trip(golden, tmp_path):
         w4.load(path)
     assert e.value.status == g.EBADLEN
     w4.free()
+
+
+def test_exact_replay_entry_nodes_are_transparent_on_device(golden):
+    """k_entry_cells: the exact replay started at the per-cell entry node equals the replay from
+    the root on 100 % of 10^7 device-generated queries (10^5 nodes) and on the config-3 mix
+    (on-vertex / on-edge / outside-hull queries), and the golden vectors hold in both modes."""
+    torch = _torch()
+    n, nq = 100000, 10_000_000
+    xa, ya = synth.uniform_nodes(n)
+    w = make(xa, ya, synth.values(n, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), mode=1)
+    dev = torch.device("cuda:0")
+    dx = torch.empty(nq, dtype=torch.float64, device=dev)
+    dy = torch.empty(nq, dtype=torch.float64, device=dev)
+    # queries over an inflated box: cage leaves and the clamped border cells are exercised too
+    w.generate_uniform_device(0, synth.SEED_QUERIES, 0, nq, -0.1, 1.1, -0.1, 1.1, dx.data_ptr(), dy.data_ptr())
+    out = []
+    for entry in (1, 0):
+        w.set_param("exact_entry", entry)
+        z = torch.empty(nq, dtype=torch.float64, device=dev)
+        l = torch.empty(nq, dtype=torch.int32, device=dev)
+        assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, z.data_ptr(), nq, l.data_ptr()) == 0
+        out.append((z, l))
+    bad_leaf, bad_val = w.compare_device(0, out[0][1].data_ptr(), out[1][1].data_ptr(),
+                                         out[0][0].data_ptr(), out[1][0].data_ptr(), nq, nq)
+    assert bad_leaf == 0 and bad_val == 0
+    w.free()
+    n = 3000
+    xa, ya = synth.clustered_nodes(n)
+    xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
+    for entry in (1, 0):
+        w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n),
+                 mode=1, exact_entry=entry)
+        st, zq, leaf = w.eval_e(xq, yq)
+        assert np.array_equal(leaf, golden["cfg3_leaf"]) and refimpl.same_bits(zq, golden["cfg3_val"])
+        w.free()
