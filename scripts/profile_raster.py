@@ -8,7 +8,7 @@ from gsl_scattered_interpolation_b200 import synth
 n = 1_000_000; F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 nx = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 ny = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
-kernel = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+kernel = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 xa, ya = synth.uniform_nodes(n); za = synth.values(n, F)
 w = g.ScatteredCuda(n, F); w.set_param("kernel", kernel)
 w.init(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n))
