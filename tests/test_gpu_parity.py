@@ -573,3 +573,30 @@ def test_exact_replay_entry_nodes_are_transparent_on_device(golden):
         st, zq, leaf = w.eval_e(xq, yq)
         assert np.array_equal(leaf, golden["cfg3_leaf"]) and refimpl.same_bits(zq, golden["cfg3_val"])
         w.free()
+
+
+@pytest.mark.parametrize("kernel", [2, 0])
+@pytest.mark.parametrize("F,nx,ny", [(1, 1024, 2048), (16, 512, 1024), (4, 300, 1028), (2, 257, 516)])
+def test_raster_kernel_vs_exact_replay_on_device(F, nx, ny, kernel):
+    """the raster kernels (k_locate by default, k_walk on request) against the exact DAG replay on
+    every pixel, for a raster over a box that sticks out of the data hull (cage leaves, cage
+    vertices in the blend) and a fine one inside it."""
+    torch = _torch()
+    n = 100000
+    xa, ya = synth.uniform_nodes(n)
+    w = make(xa, ya, synth.values(n, F), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), kernel=kernel)
+    dev = torch.device("cuda:0")
+    for (x0, x1, y0, y1) in [(-0.02, 1.02, -0.02, 1.02), (0.4, 0.45, 0.3, 0.35)]:
+        dx, dy = (x1 - x0) / nx, (y1 - y0) / ny
+        res = []
+        for mode in (0, 1):
+            w.set_param("mode", mode)
+            z = torch.empty((F, nx * ny), dtype=torch.float64, device=dev)
+            l = torch.empty(nx * ny, dtype=torch.int32, device=dev)
+            assert w.eval_raster_device_e(0, x0, dx, nx, y0, dy, ny, z.data_ptr(), l.data_ptr()) == 0
+            res.append((z, l))
+        w.set_param("mode", 0)
+        bad_leaf, bad_val = w.compare_device(0, res[0][1].data_ptr(), res[1][1].data_ptr(),
+                                             res[0][0].data_ptr(), res[1][0].data_ptr(), nx * ny, F * nx * ny)
+        assert bad_leaf == 0 and bad_val == 0, (x0, x1)
+    w.free()
