@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -185,7 +185,7 @@ def main_reference(args):
         "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main_ours(args):
@@ -197,8 +197,6 @@ def main_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if g.device_count() <= 0:
         raise SystemExit("bench.py needs a CUDA device: libgsl_scattered_cuda has no CPU path")
     torch.cuda.set_device(local)
@@ -390,15 +388,50 @@ def main_ours(args):
                                             "reference_build_seconds": cb["build_seconds"]}
         if stats:
             line["walk_stats"] = stats
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+class OnlyJsonOnStdout:
+    """stdout must carry exactly one JSON line; native libraries (NCCL's version banner under
+    torchrun) write to file descriptor 1 behind Python's back.  Everything written to fd 1 while
+    this is active goes to stderr; emit() writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+OUT = None
+
+
+def emit(line):
+    text = json.dumps(line)
+    if OUT is not None:
+        OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        main_reference(a)
-    else:
-        main_ours(a)
+    with OnlyJsonOnStdout() as OUT:
+        if a.impl == "reference":
+            main_reference(a)
+        else:
+            main_ours(a)
+    sys.exit(0)
+
