@@ -770,7 +770,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "host_chunk" && value >= 1) w->host_chunk = (size_t) value;
   else if (k == "ctas_per_sm" && value >= 1) w->ctas_per_sm = (int) value;
   else if (k == "profile") w->profile = value != 0;
-  else if (k == "kernel" && (value == 0 || value == 1 || value == 2 || value == 3)) w->kernel = (int) value;
+  else if (k == "kernel" && (value == 0 || value == 1 || value == 2)) w->kernel = (int) value;
   else if (k == "l2_fetch" && (value == 0 || value == 32 || value == 64 || value == 128)) w->l2_fetch = (int) value;
   else if (k == "walk_ctas_per_sm" && value >= 1) w->walk_ctas_per_sm = (int) value;
   else if (k == "walk_chunk" && value >= 0) w->walk_chunk = ((size_t) value + 31) & ~(size_t) 31;

@@ -44,11 +44,6 @@ struct src_arrays
     qx = GSI_LD_QUERY(x + q);
     qy = GSI_LD_QUERY(y + q);
   }
-  __device__ __forceinline__ bool out_index(size_t t, size_t &q) const
-  {
-    q = t;
-    return true;
-  }
   __host__ __device__ size_t n_launch(size_t nq) const { return nq; }
 };
 
@@ -79,15 +74,6 @@ struct src_raster
     q = i * ny + j;
     coords(i, j, qx, qy);
     return true;
-  }
-  __device__ __forceinline__ bool out_index(size_t t, size_t &q) const
-  {
-    const unsigned long long tiles_j = (ny + 31) >> 5;
-    const unsigned long long tile = t >> 8, within = t & 255;
-    const unsigned long long ti = tile / tiles_j, tj = tile - ti * tiles_j;
-    const unsigned long long i = (ti << 3) + (within >> 5), j = (tj << 5) + (within & 31);
-    q = i * ny + j;
-    return i < n_cols && j < ny;
   }
   __device__ __forceinline__ void get_linear(size_t q, double &qx, double &qy) const
   {
@@ -389,148 +375,6 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
                     mark_overflow(ovf_mask, q, counters);
                 }
             }
-        }
-    }
-  if (STATS && steps_acc)
-    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
-}
-
-/* ---- fast path, staged: decoupled walk into shared memory, converged blend -----------------------
- * Each warp takes windows of GSI_STAGE_WINDOW consecutive launch indices.
- *   phase 1  the lanes-decoupled walk of k_walk (a lane that finished its query takes the next
- *            one of the window at once; two queries are kept in flight behind the current one),
- *            but only the outcome -- leaf slot and the two reference weights -- is parked in
- *            shared memory;
- *   phase 2  converged: lane l handles window entries l, l+32, ...: tail fetch, blend, stores.
- *            Consecutive lanes are consecutive queries, so every store writes full sectors, and
- *            only the accepted leaf's tail is ever read.
- * Deferred queries are appended to the list in phase 2. */
-template <class SRC, bool STATS>
-__global__ void __launch_bounds__(GSI_STAGE_THREADS, 4)
-k_stage(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
-        size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
-        int max_steps)
-{
-  __shared__ double s_c0[GSI_STAGE_THREADS / 32][GSI_STAGE_WINDOW];
-  __shared__ double s_c1[GSI_STAGE_THREADS / 32][GSI_STAGE_WINDOW];
-  __shared__ int s_slot[GSI_STAGE_THREADS / 32][GSI_STAGE_WINDOW];
-  const unsigned FULL = 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  double *c0s = s_c0[wib], *c1s = s_c1[wib];
-  int *slots = s_slot[wib];
-  const size_t warp_id = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t n_warps = ((size_t) gridDim.x * blockDim.x) >> 5;
-  const size_t n_launch = src.n_launch(nq);
-  const size_t n_chunks = (n_launch + chunk - 1) / chunk;
-  unsigned long long steps_acc = 0;
-  for (size_t ch = warp_id; ch < n_chunks; ch += n_warps)
-    {
-      const size_t ch0 = ch * (size_t) chunk;
-      const size_t ch1 = ch0 + chunk < n_launch ? ch0 + chunk : n_launch;
-      for (size_t w0 = ch0; w0 < ch1; w0 += GSI_STAGE_WINDOW)
-        {
-          const unsigned total = (unsigned) (ch1 - w0 < (size_t) GSI_STAGE_WINDOW ? ch1 - w0
-                                                                                 : (size_t) GSI_STAGE_WINDOW);
-          /* ---------------- phase 1: decoupled walk ---------------- */
-          unsigned next = 0;
-          bool cur_v = false, nxt_v = false, nn_v = false;
-          unsigned cur_i = 0, nxt_i = 0, nn_i = 0;
-          double cur_x = 0, cur_y = 0, nxt_x = 0, nxt_y = 0, nn_x = 0, nn_y = 0;
-          int cur_slot = 0, nxt_seed = 0, cur_steps = 0;
-          for (;;)
-            {
-              const bool need = !cur_v;
-              if (need)
-                {
-                  cur_v = nxt_v; cur_i = nxt_i; cur_x = nxt_x; cur_y = nxt_y;
-                  cur_slot = nxt_seed; cur_steps = 0;
-                  nxt_v = nn_v; nxt_i = nn_i; nxt_x = nn_x; nxt_y = nn_y;
-                  if (nxt_v) nxt_seed = gsi_ld_seed(V.seeds + gsi_cell_of(&V, nxt_x, nxt_y));
-                }
-              const unsigned take = __ballot_sync(FULL, need);
-              if (need)
-                {
-                  const unsigned off = next + __popc(take & lt_mask);
-                  nn_v = false;
-                  if (off < total)
-                    {
-                      size_t q;
-                      nn_i = off;
-                      nn_v = src.get(w0 + off, q, nn_x, nn_y);
-                      if (!nn_v) slots[off] = -2; /* padding: no query behind this launch index */
-                      else if (!(isfinite(nn_x) && isfinite(nn_y)))
-                        {
-                          slots[off] = -1;
-                          nn_v = false;
-                        }
-                    }
-                }
-              next += __popc(take);
-              if (next > total) next = total;
-              if (!__any_sync(FULL, cur_v || nxt_v || nn_v))
-                {
-                  /* lanes whose take returned padding/non-finite may still have work queued */
-                  if (next >= total) break;
-                  continue;
-                }
-              if (cur_v)
-                {
-                  gsi_rec r;
-                  gsi_fetch_rec(&r, gsi_leaf_at(&V, cur_slot));
-                  const int at = cur_slot;
-                  double c0, c1;
-                  const int st = gsi_walk_step(&V.xf, &r, cur_x, cur_y, &cur_slot, &c0, &c1);
-                  ++cur_steps;
-                  if (st == GSI_STEP_ACCEPT)
-                    {
-                      slots[cur_i] = at;
-                      c0s[cur_i] = c0;
-                      c1s[cur_i] = c1;
-                      if (STATS) steps_acc += (unsigned) cur_steps;
-                      cur_v = false;
-                    }
-                  else if (st == GSI_STEP_DEFER || cur_steps >= max_steps)
-                    {
-                      slots[cur_i] = -1;
-                      cur_v = false;
-                    }
-                }
-            }
-          __syncwarp();
-          /* ---------------- phase 2: converged blend + stores ---------------- */
-          for (unsigned i = lane; i < GSI_STAGE_WINDOW; i += 32)
-            {
-              const int slot = i < total ? slots[i] : -2;
-              size_t q = 0;
-              if (slot != -2) src.out_index(w0 + i, q);
-              if (slot >= 0)
-                {
-                  gsi_leaf_tail t;
-                  gsi_fetch_tail(&t, gsi_leaf_at(&V, slot));
-                  if (leaf_out) leaf_out[q] = t.g.node;
-                  if (val) gsi_blend_store(&V, &t, c0s[i], c1s[i], val, ld, q);
-                }
-              const bool defer = slot == -1;
-              const unsigned dm = __ballot_sync(FULL, defer);
-              if (dm)
-                {
-                  const int leader = __ffs(dm) - 1;
-                  unsigned pos = 0;
-                  if (lane == (unsigned) leader)
-                    pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
-                  pos = __shfl_sync(FULL, pos, leader);
-                  if (defer)
-                    {
-                      const unsigned at = pos + __popc(dm & lt_mask);
-                      if (at < list_cap)
-                        list[at] = (unsigned) q;
-                      else
-                        mark_overflow(ovf_mask, q, counters);
-                    }
-                }
-            }
-          __syncwarp();
         }
     }
   if (STATS && steps_acc)
@@ -1029,27 +873,6 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   if (cfg.ev_locate0) cudaEventRecord(cfg.ev_locate0, st);
   if (launch_reordered(V, src, nq, val, leaf_out, ld, cfg, list_cap, st))
     ;
-  else if (cfg.kernel == GSI_KERNEL_STAGE)
-    {
-      const int ctas = cfg.sm_count * cfg.walk_ctas_per_sm;
-      const size_t n_warps = (size_t) ctas * (GSI_STAGE_THREADS / 32);
-      const size_t n_launch = src.n_launch(nq);
-      size_t chunk = (n_launch / (n_warps * 8) + GSI_STAGE_WINDOW - 1) / GSI_STAGE_WINDOW * GSI_STAGE_WINDOW;
-      if (chunk < GSI_STAGE_WINDOW) chunk = GSI_STAGE_WINDOW;
-      if (chunk > 8192) chunk = 8192;
-      if (cfg.walk_chunk) chunk = (cfg.walk_chunk + GSI_STAGE_WINDOW - 1) / GSI_STAGE_WINDOW * GSI_STAGE_WINDOW;
-      const size_t n_chunks = (n_launch + chunk - 1) / chunk;
-      const size_t want = (n_chunks + GSI_STAGE_THREADS / 32 - 1) / (GSI_STAGE_THREADS / 32);
-      const int g = (int) (want < (size_t) ctas ? want : (size_t) ctas);
-      if (cfg.stats)
-        k_stage<SRC, true><<<g, GSI_STAGE_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out, ld,
-                                                            cfg.list, list_cap, cfg.ovf_mask, cfg.counters,
-                                                            cfg.max_steps);
-      else
-        k_stage<SRC, false><<<g, GSI_STAGE_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out, ld,
-                                                             cfg.list, list_cap, cfg.ovf_mask, cfg.counters,
-                                                             cfg.max_steps);
-    }
   else if (cfg.kernel == GSI_KERNEL_WALK || (cfg.kernel == GSI_KERNEL_AUTO && !SRC::coherent))
     {
       const int ctas = cfg.sm_count * cfg.walk_ctas_per_sm;

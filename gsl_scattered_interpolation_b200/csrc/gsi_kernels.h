@@ -10,8 +10,6 @@
 
 #define GSI_LOCATE_THREADS 256
 #define GSI_WALK_THREADS 128
-#define GSI_STAGE_THREADS 128
-#define GSI_STAGE_WINDOW 256
 #define GSI_BIN_THREADS 512        /* k_bin: one CTA sorts one chunk in shared memory, two CTAs per SM */
 #define GSI_UNPERMUTE_THREADS 1024 /* k_unpermute */
 #define GSI_BIN_CHUNK_MAX 8192  /* queries per chunk (16-bit in-chunk indices, 160 KB of shared memory) */
@@ -32,7 +30,6 @@
 #define GSI_KERNEL_WALK 0   /* k_walk: lanes decoupled from queries (default) */
 #define GSI_KERNEL_SIMPLE 1 /* k_locate: one thread per query, two-phase (coherent query sets) */
 #define GSI_KERNEL_AUTO 2   /* k_walk for query arrays, k_locate for rasters (default) */
-#define GSI_KERNEL_STAGE 3  /* k_stage: decoupled walk staged in shared memory + converged blend */
 
 /* Scratch of the reorder pipeline (k_bin -> k_tile_locate -> k_unpermute), one per replica.
  * Queries are processed in windows of `cap` queries; a window is cut into chunks of `chunk`
