@@ -821,13 +821,9 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
   const int S = R->chunk, nt = 1 << (2 * R->tile_bits);
   const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
   const size_t smem_bin = (size_t) S * 10 + (size_t) nt * 4, smem_unp = (size_t) S * 12;
-  static bool attr_done = false;
-  if (!attr_done)
-    {
-      cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 10 + 4096 * 4);
-      cudaFuncSetAttribute(k_unpermute, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 12);
-      attr_done = true;
-    }
+  /* per device (the current one), so not cached in a process-wide flag */
+  cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 10 + 4096 * 4);
+  cudaFuncSetAttribute(k_unpermute, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 12);
   const int g_bin = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
   k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(V, src.x, src.y, nq, S, R->tile_shift, nt, R->bx, R->by, R->bi,
                                                   R->off);

@@ -343,6 +343,16 @@ def test_two_devices_if_present(golden):
     st, zq, leaf = w.eval_e(xq, yq)
     assert w.info()["n_devices"] == 2
     assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq, golden["cfg1_val"])
+    # the reorder pipeline (per-device shared-memory attributes, per-replica scratch) and the
+    # raster split by columns on both replicas
+    w.set_param("reorder", 1)
+    st, zq, leaf = w.eval_e(xq, yq)
+    assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq, golden["cfg1_val"])
+    assert w.info()["n_reordered"] == 10000
+    w.set_param("reorder", 0)
+    x0, dx, nx, y0, dy, ny = golden["cfg1_raster_spec"]
+    st, rz, rl = w.eval_raster_e(x0, dx, int(nx), y0, dy, int(ny))
+    assert np.array_equal(rl, golden["cfg1_raster_leaf"]) and refimpl.same_bits(rz, golden["cfg1_raster_val"])
     w.free()
 
 
