@@ -75,7 +75,19 @@ int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_
  * path + exact replay of deferred queries, 1 = exact replay of every query),
  * "stats" (1 = count walk steps), "profile" (1 = time every kernel launch with CUDA events on
  * its own stream), "chunk" (queries per launch), "host_chunk" (queries per pipeline stage
- * of eval_e), "list_fraction" (deferred-list size / launch size), "ctas_per_sm". */
+ * of eval_e), "list_fraction" (deferred-list size / launch size), "ctas_per_sm",
+ * "walk_ctas_per_sm", "walk_chunk", "kernel" (0 = k_walk, 1 = k_locate, 2 = k_walk for query
+ * arrays and k_locate for rasters, default), "leaf_stride" (96 or 128), "l2_fetch".
+ * Exact replay: "exact_entry" (1 = start at the grid cell's certified entry node, default;
+ * 0 = at the root; may be changed at any time).
+ * Reorder pipeline for incoherent query arrays (chunk-local counting sort by spatial tile ->
+ * tile-major walk -> inverse permutation): "reorder" (0 = off, default; 1 = always; 2 = large
+ * few-field batches on triangulations beyond the L2), "reorder_window" (queries per window,
+ * default 2^27), "reorder_chunk" (queries per sorted chunk, <= 8192), "reorder_min",
+ * "reorder_max_fields", "tile_shift" (tile edge = 2^shift grid cells, -1 = from "tile_leaves"),
+ * "tile_leaves" (default 1024), "tile_ranges" (CTAs per tile, default 4).
+ * Calls on one workspace share per-replica scratch (deferred list, counters, reorder buffers):
+ * issue them on one stream at a time per device. */
 int gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double value);
 
 /* order[] for init: what gsl_ran_shuffle(rng, shuffle, n, sizeof(size_t)) leaves in
