@@ -239,7 +239,10 @@ def main_ours(args):
         if rank != 0:
             w.init_from_slab_device(slab.data_ptr(), slab.numel())
         del slab
-    struct_bytes = w.slab_bytes()
+    # the part of the slab the fast path reads: leaf records, vertex values,
+    # seed grid -- not the history DAG / entry table of the exact replay
+    inf0 = w.info()
+    struct_bytes = int(inf0["n_leaves"]) * 96 + n * 8 * F + int(inf0["grid_g"]) ** 2 * 4
 
     # --- queries of this rank: k in [rank*Q, (rank+1)*Q) of the global stream, generated on
     #     the device by an untimed kernel and resident in HBM when the timed region starts
