@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--fields", type=int, default=1)
     ap.add_argument("--cells-per-leaf", type=float, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify-queries", type=int, default=1_100_000_000,
+                    help="cross-check the whole step against the exact replay when it has at most this many queries")
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--stats", action="store_true", help="extra untimed pass counting walk steps")
     ap.add_argument("--param", action="append", default=[], help="library knob name=value (repeatable)")
@@ -115,7 +117,7 @@ def workload_nodes(n, fields):
     return xa, ya, za
 
 
-def cpu_reference_leg(args, steps, warmup, sample_seconds):
+def cpu_reference_leg(args, steps, warmup, sample_seconds, check=None):
     """The reference's own eval loop (find_leaf + interp_point, linear_simplex.c:331-402,
     678-711) from oracle/_ref, forked over all host cores, on bounded samples of the workload."""
     import refimpl
@@ -159,7 +161,18 @@ def cpu_reference_leg(args, steps, warmup, sample_seconds):
         if s >= warmup:
             times.append(dt)
     t = float(np.mean(times))
-    return {"value": per_step / t, "unit": "queries/s", "cores": cores, "kind": kind,
+    parity = None
+    if check is not None:
+        # the GPU's results on a strided subsample of ITS queries against the CPU arm, bit for bit
+        xs, ys, gl, gz = check
+        if kind == "reference":
+            rl, rv, _ = tree.eval(xs, ys, za, nproc=cores)
+        else:
+            rl, rv, _ = port.eval(xs, ys, za)
+        parity = {"queries": int(xs.size), "leaf": int(np.count_nonzero(rl != gl)),
+                  "value_bits": int(np.count_nonzero(np.ascontiguousarray(rv).view(np.uint64)
+                                                     != np.ascontiguousarray(gz).view(np.uint64)))}
+    return {"parity": parity, "value": per_step / t, "unit": "queries/s", "cores": cores, "kind": kind,
             "sample": f"{per_step} uniform queries per step x {steps} steps on the {args.nodes}-node tree, "
                       f"find_leaf + {args.fields} x interp_point, forked over {cores} cores",
             "single_core_qps": rate1, "build_seconds": build_s, "ms_per_step": 1e3 * t,
@@ -289,7 +302,15 @@ def main_ours(args):
 
     # --- verification inside the run: checksum, and fast path == exact replay on a prefix
     chk = w.checksum_device(local, dl.data_ptr(), dz.data_ptr(), Q, sp)
-    nv = min(Q, 20_000_000)
+    # strided subsample of this rank's queries and results for the CPU cross-check (rank 0, N = 1)
+    sample = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        idx = torch.arange(0, Q, max(1, Q // 1_000_000), device=dev)[:1_000_000]
+        sample = (dx[idx].cpu().numpy(), dy[idx].cpu().numpy(), dl[idx].cpu().numpy(),
+                  dz[:, idx].cpu().numpy())
+        del idx
+    # exact DAG replay of EVERY query of the step (all 10^9 by default) against the fast path
+    nv = Q if Q <= args.verify_queries else min(Q, 20_000_000)
     vz = torch.empty((F, nv), dtype=torch.float64, device=dev)
     vl = torch.empty(nv, dtype=torch.int32, device=dev)
     w.set_param("mode", 1)
@@ -338,7 +359,7 @@ def main_ours(args):
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_leg(args, steps=3, warmup=1, sample_seconds=args.cpu_sample_seconds)
+        cb = cpu_reference_leg(args, steps=3, warmup=1, sample_seconds=args.cpu_sample_seconds, check=sample)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -382,7 +403,8 @@ def main_ours(args):
                          "kernel_ms_per_launch": 1e3 * locate_s, "exact_replay_ms_per_step": 1e3 * exact_s},
             "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
             "verify": {"checksum_leaf": chk[0], "checksum_val": chk[1],
-                       "fast_vs_exact_mismatches_on_prefix": {"queries": nv, "leaf": bad[0], "value_bits": bad[1]},
+                       "fast_vs_exact_mismatches": {"queries": nv, "leaf": bad[0], "value_bits": bad[1]},
+                       "cpu_reference_mismatches_on_strided_subsample": (cb or {}).get("parity"),
                        "deferred_queries_per_step": inf["n_deferred"] / max(1, args.steps),
                        "outside_cage": inf["n_outside"]},
         }

@@ -6,7 +6,7 @@ run() { name=$1; shift; timeout 600 $B "$@" > gpurun_out/aa_$name.json 2> gpurun
 import json
 try:
     d=json.load(open("gpurun_out/aa_$name.json"))
-    print("$name", "value %.4e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d["verify"]["fast_vs_exact_mismatches_on_prefix"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+    print("$name", "value %.4e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d["verify"]["fast_vs_exact_mismatches"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 except Exception as e: print("$name failed", e); print(open("gpurun_out/aa_$name.err").read()[-1500:])
 PY
 }

@@ -6,7 +6,7 @@ run() { name=$1; shift; timeout 600 $B "$@" > gpurun_out/d_$name.json 2> gpurun_
 import json
 try:
     d=json.load(open("gpurun_out/d_$name.json"))
-    print("$name", "value %.3e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d.get("walk_stats"), d["verify"]["fast_vs_exact_mismatches_on_prefix"])
+    print("$name", "value %.3e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d.get("walk_stats"), d["verify"]["fast_vs_exact_mismatches"])
 except Exception as e: print("$name failed", e)
 PY
 }

@@ -7,7 +7,7 @@ run() { name=$1; shift; timeout 600 $B "$@" > gpurun_out/q_$name.json 2> gpurun_
 import json
 try:
     d=json.load(open("gpurun_out/q_$name.json"))
-    print("$name", "value %.3e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d["verify"]["fast_vs_exact_mismatches_on_prefix"], d["gpu_launches"])
+    print("$name", "value %.3e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d["verify"]["fast_vs_exact_mismatches"], d["gpu_launches"])
 except Exception as e: print("$name failed", e); print(open("gpurun_out/q_$name.err").read()[-1500:])
 PY
 }

@@ -6,7 +6,7 @@ run() { name=$1; lib=$2; shift; shift; GSI_LIB_PATH=$lib timeout 600 $B "$@" > g
 import json
 try:
     d=json.load(open("gpurun_out/t_$name.json"))
-    print("$name", "value %.3e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d["verify"]["fast_vs_exact_mismatches_on_prefix"])
+    print("$name", "value %.3e"%d["value"], "ms %.3f"%d["ms_per_step"], "frac %.4f"%d["roofline"]["frac"], d["verify"]["fast_vs_exact_mismatches"])
 except Exception as e: print("$name failed", e); print(open("gpurun_out/t_$name.err").read()[-1500:])
 PY
 }
