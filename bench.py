@@ -110,6 +110,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_near_gpu(local):
+    """Run this rank's host threads (and so first-touch its pinned buffers) on the CPUs NVML reports
+    as closest to its GPU, when the container's cpuset contains any of them.  Only affects the
+    host-buffer (e2e) leg.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, 64)
+        near = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        have = os.sched_getaffinity(0)
+        use = sorted(near & have)
+        if use and len(use) < len(have):
+            os.sched_setaffinity(0, use)
+            return f"bound to {len(use)} of {len(have)} cpus near gpu {local}"
+        return f"not bound ({len(near & have)} of {len(have)} visible cpus are near gpu {local})"
+    except Exception as e:                  # pragma: no cover - depends on the box
+        return f"not bound ({type(e).__name__})"
+
+
 def workload_nodes(n, fields):
     from gsl_scattered_interpolation_b200 import synth
     xa, ya = synth.uniform_nodes(n)
@@ -214,6 +234,7 @@ def main_ours(args):
         raise SystemExit("bench.py needs a CUDA device: libgsl_scattered_cuda has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_near_gpu(local) if world > 1 and not os.environ.get("GSI_NO_BIND") else "not bound (single rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -351,7 +372,8 @@ def main_ours(args):
         dt = dist_util.max_over_ranks(time.perf_counter() - t0, dev)
         e2e = {"value": world * Qe * e2e_steps / dt, "unit": "queries/s",
                "h2d_bytes_per_step": Qe * 16, "d2h_bytes_per_step": Qe * (4 + 8 * F),
-               "queries_per_gpu_per_step": Qe, "host_memory": "pinned (gsl_scattered_cuda_host_alloc)"}
+               "queries_per_gpu_per_step": Qe, "host_memory": "pinned (gsl_scattered_cuda_host_alloc)",
+               "cpu_affinity": affinity}
     for p in (hx, hy, hz, hl):
         if p:
             L.gsl_scattered_cuda_host_free(p)
