@@ -1,19 +1,27 @@
 /* gsi_kernels.cu -- sm_100a kernels of libgsl_scattered_cuda.
  *
- *   k_locate  fast path: seed from the uniform grid, walk across the edge with the most
- *             negative barycentric weight, accept the leaf only when all three weights
- *             clear the leaf's safety margin, then blend.  The weights are the reference's
- *             own (calculate_bary_coords, linear_simplex.c:607-651) so the accepted result
- *             is bit-identical to find_leaf + interp_point; everything else is deferred.
- *   k_exact   exact replay of find_leaf/_find_leaf (linear_simplex.c:331-402) on the
- *             flattened history DAG + interp_point (linear_simplex.c:678-711): the
- *             reference's edge/vertex tie-breaks, cage leaves, stale-coords quirk.  Runs on
- *             the deferred list, on grid-cell centres (seeding), or on every query.
+ *   k_walk         fast path for query arrays (default): a warp consumes a chunk of queries through
+ *                  a warp-wide work queue, one walk step per iteration for whatever query each lane
+ *                  holds.  Seed from the uniform grid, cross the edge with the most negative
+ *                  barycentric weight, accept the leaf only when all three weights clear the leaf's
+ *                  safety margin, then blend.  The weights are the reference's own
+ *                  (calculate_bary_coords, linear_simplex.c:607-651), so an accepted result is
+ *                  bit-identical to find_leaf + interp_point; everything else is deferred.
+ *   k_locate       the same per-query logic, one thread per query over compact pixel tiles: the
+ *                  default for rasters (coherent queries).
+ *   k_exact_*      exact replay of find_leaf/_find_leaf (linear_simplex.c:331-402) on the flattened
+ *                  history DAG + interp_point (linear_simplex.c:678-711): the reference's
+ *                  edge/vertex tie-breaks, cage leaves, stale-coords quirk.  Runs on the deferred
+ *                  list, on grid-cell centres (seeding), or on every query; starts at the cell's
+ *                  certified entry node (k_entry_cells).
+ *   k_bin -> k_tile_locate -> k_unpermute
+ *                  opt-in reorder pipeline for incoherent query arrays (chunk-local counting sort
+ *                  by spatial tile, tile-major walk, inverse permutation).
  *
  * This path is gather/latency bound: no tensor cores, no FMA contraction (gsi_core.h).
+ * Measured bounds and the experiments that did not pay off are in DESIGN.md section 4.
  */
 #include <cuda_runtime.h>
-#include <limits.h>
 #include <math_constants.h>
 #include <stdint.h>
 
