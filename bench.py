@@ -313,7 +313,9 @@ def main_ours(args):
         step()
     e1.record(stream)
     barrier()
-    ms_total = dist_util.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_mine = e0.elapsed_time(e1)
+    ms_total = dist_util.max_over_ranks(ms_mine, dev)
+    ms_by_rank = dist_util.gather_over_ranks(ms_mine / args.steps, dev)
     clocks = sampler.stop() if rank == 0 else None
     inf = w.info()
     value = world * Q * args.steps / (ms_total * 1e-3)
@@ -407,6 +409,7 @@ def main_ours(args):
         line = {
             "metric": "interp queries/sec", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "ms_per_step_by_rank": ms_by_rank,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"BASELINE.json configs[4]: {n} uniform-random nodes, {F} field(s), "

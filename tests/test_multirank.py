@@ -53,6 +53,7 @@ def _worker(rank, world, port, out_dir):
     # timing reduction: max over ranks
     m = dist_util.max_over_ranks(10.0 + rank, torch.device("cpu"))
     assert m == 10.0 + world - 1
+    assert dist_util.gather_over_ranks(10.0 + rank, torch.device("cpu")) == [10.0 + r for r in range(world)]
     s0, s1 = dist_util.split_range(rank, world, 1001)
     tot = torch.tensor([s1 - s0]); dist.all_reduce(tot)
     assert int(tot.item()) == 1001
