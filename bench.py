@@ -61,7 +61,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks.mem,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -91,14 +91,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
+        sm, mx, reasons, power, mem = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             c = [x.strip() for x in ln.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3])); mem.append(float(c[4]))
             except ValueError:
                 continue
             for name, v in zip(names, c[5:9]):
@@ -107,6 +107,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
                 "power_w_max": float(max(power)) if power else None,
+                "mem_mhz": float(np.median(mem)) if mem else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -239,6 +240,13 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n, F, Q = args.nodes, args.fields, args.queries
+    # query / result arrays of this rank, allocated before anything else touches the device heap
+    stream = torch.cuda.Stream(device=dev)
+    sp = stream.cuda_stream
+    dx = torch.empty(Q, dtype=torch.float64, device=dev)
+    dy = torch.empty(Q, dtype=torch.float64, device=dev)
+    dz = torch.empty((F, Q), dtype=torch.float64, device=dev)
+    dl = torch.empty(Q, dtype=torch.int32, device=dev)
     w = g.ScatteredCuda(n, F)
     w.set_devices([local])
     if args.cells_per_leaf:
@@ -280,12 +288,6 @@ def main_ours(args):
 
     # --- queries of this rank: k in [rank*Q, (rank+1)*Q) of the global stream, generated on
     #     the device by an untimed kernel and resident in HBM when the timed region starts
-    stream = torch.cuda.Stream(device=dev)
-    sp = stream.cuda_stream
-    dx = torch.empty(Q, dtype=torch.float64, device=dev)
-    dy = torch.empty(Q, dtype=torch.float64, device=dev)
-    dz = torch.empty((F, Q), dtype=torch.float64, device=dev)
-    dl = torch.empty(Q, dtype=torch.int32, device=dev)
     k0, k1 = dist_util.shard_range(rank, world, Q)
     w.generate_uniform_device(local, synth.SEED_QUERIES, k0, k1 - k0, 0.0, 1.0, 0.0, 1.0,
                               dx.data_ptr(), dy.data_ptr(), sp)
@@ -304,8 +306,7 @@ def main_ours(args):
     barrier()
     w.reset_counters()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()                      # every rank samples its own GPU
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -316,7 +317,11 @@ def main_ours(args):
     ms_mine = e0.elapsed_time(e1)
     ms_total = dist_util.max_over_ranks(ms_mine, dev)
     ms_by_rank = dist_util.gather_over_ranks(ms_mine / args.steps, dev)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    sm_by_rank = dist_util.gather_over_ranks(clocks["sm_mhz"] or 0.0, dev)
+    mem_by_rank = dist_util.gather_over_ranks(clocks.get("mem_mhz") or 0.0, dev)
+    pw_by_rank = dist_util.gather_over_ranks(clocks.get("power_w_max") or 0.0, dev)
+    clocks["by_rank"] = {"sm_mhz": sm_by_rank, "mem_mhz": mem_by_rank, "power_w_max": pw_by_rank}
     inf = w.info()
     value = world * Q * args.steps / (ms_total * 1e-3)
     locate_s = inf["locate_seconds"] / max(1, args.steps)          # dominant kernel, per launch

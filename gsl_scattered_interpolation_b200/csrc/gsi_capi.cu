@@ -6,6 +6,7 @@
  * pipeline behind eval_e.  There is no CPU evaluation path in this library: every eval entry
  * point fails with GSL_SCATTERED_EFAILED when no CUDA device is usable.
  */
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -82,6 +83,10 @@ struct replica
   int sm_count = 148;
   char *slab = nullptr;
   bool owns_slab = true;
+  /* slab backed by the virtual-memory-management API (explicit 2 MB physical granularity) */
+  bool slab_vmm = false;
+  unsigned long long slab_handle = 0;
+  size_t slab_mapped = 0;
   gsi_view view;
   cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
   unsigned *list = nullptr;
@@ -122,6 +127,7 @@ struct gsl_scattered_cuda
   int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_shift = -1, tile_ranges = 4, tile_leaves = 1024;
   size_t reorder_max_fields = 2;
   int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
+  int vmm = 1;         /* slab through cuMemCreate/cuMemMap with the recommended granularity (0: cudaMalloc) */
   size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
   double list_fraction = 1.0 / 8;
@@ -134,6 +140,118 @@ struct gsl_scattered_cuda
 
 namespace
 {
+
+/* ---- slab allocation --------------------------------------------------------------------------
+ * The fast path gathers at random from ~224 MB of the slab at 10^6 nodes, right at the reach of
+ * the GPU's TLB with 2 MB pages.  cudaMalloc does not promise a page size, and on B200 the same
+ * kernel was measured at 38 ms or 47 ms (or worse) per 10^9 queries from process to process
+ * (profiles/r1e_*).  The slab is therefore allocated through the driver's virtual-memory-
+ * management API with the recommended granularity, so that every physical chunk is a whole large
+ * page.  The entry points are resolved at run time (cudaGetDriverEntryPoint): the library does
+ * not link to libcuda and still loads on a machine without a driver.  Any failure falls back to
+ * cudaMalloc. */
+struct vmm_api
+{
+  CUresult (*getGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+  CUresult (*reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*setAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*addressFree)(CUdeviceptr, size_t) = nullptr;
+  bool ok = false;
+};
+
+const vmm_api &
+vmm()
+{
+  static vmm_api a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto get = [](const char *name, void **fn) {
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        {
+          cudaGetLastError();
+          *fn = nullptr;
+        }
+      return *fn != nullptr;
+    };
+    a.ok = get("cuMemGetAllocationGranularity", (void **) &a.getGranularity) && get("cuMemCreate", (void **) &a.create)
+           && get("cuMemAddressReserve", (void **) &a.reserve) && get("cuMemMap", (void **) &a.map)
+           && get("cuMemSetAccess", (void **) &a.setAccess) && get("cuMemUnmap", (void **) &a.unmap)
+           && get("cuMemRelease", (void **) &a.release) && get("cuMemAddressFree", (void **) &a.addressFree);
+  });
+  return a;
+}
+
+void
+slab_free(replica *r)
+{
+  if (!r->slab) return;
+  if (r->slab_vmm)
+    {
+      const vmm_api &v = vmm();
+      v.unmap((CUdeviceptr) r->slab, r->slab_mapped);
+      v.release((CUmemGenericAllocationHandle) r->slab_handle);
+      v.addressFree((CUdeviceptr) r->slab, r->slab_mapped);
+    }
+  else if (r->owns_slab)
+    cudaFree(r->slab);
+  r->slab = nullptr;
+  r->slab_vmm = false;
+  r->slab_handle = 0;
+  r->slab_mapped = 0;
+}
+
+/* the current device must be r->dev (make_replica leaves it so) */
+cudaError_t
+slab_alloc(replica *r, size_t bytes, int use_vmm)
+{
+  const vmm_api &v = vmm();
+  if (use_vmm && v.ok)
+    {
+      CUmemAllocationProp prop;
+      std::memset(&prop, 0, sizeof prop);
+      prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+      prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      prop.location.id = r->dev;
+      size_t gran = 0;
+      CUmemGenericAllocationHandle h = 0;
+      CUdeviceptr p = 0;
+      if (v.getGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gran)
+        {
+          const size_t size = (bytes + gran - 1) / gran * gran;
+          if (v.create(&h, size, &prop, 0) == CUDA_SUCCESS)
+            {
+              if (v.reserve(&p, size, gran, 0, 0) == CUDA_SUCCESS)
+                {
+                  CUmemAccessDesc acc;
+                  std::memset(&acc, 0, sizeof acc);
+                  acc.location = prop.location;
+                  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+                  if (v.map(p, size, 0, h, 0) == CUDA_SUCCESS)
+                    {
+                      if (v.setAccess(p, size, &acc, 1) == CUDA_SUCCESS)
+                        {
+                          r->slab = (char *) p;
+                          r->slab_vmm = true;
+                          r->slab_handle = (unsigned long long) h;
+                          r->slab_mapped = size;
+                          return cudaSuccess;
+                        }
+                      v.unmap(p, size);
+                    }
+                  v.addressFree(p, size);
+                }
+              v.release(h);
+            }
+        }
+    }
+  r->slab_vmm = false;
+  return cudaMalloc(&r->slab, bytes);
+}
 
 void
 free_reorder(replica *r)
@@ -156,7 +274,7 @@ free_replica(replica *r)
   cudaSetDevice(r->dev);
   for (auto &p : r->prof_locate) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : r->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  if (r->slab && r->owns_slab) cudaFree(r->slab);
+  slab_free(r);
   if (r->list) cudaFree(r->list);
   if (r->ovf_mask) cudaFree(r->ovf_mask);
   if (r->counters) cudaFree(r->counters);
@@ -611,7 +729,7 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
       if (r) w->reps.push_back(r);
       if (s) return s;
       apply_l2_fetch(w);
-      CU(cudaMalloc(&r->slab, w->hdr.total_bytes));
+      CU(slab_alloc(r, w->hdr.total_bytes, w->vmm));
       r->view = gsi_view_of(r->slab, &w->hdr);
       if (!w->exact_entry) r->view.entry = nullptr;
     }
@@ -679,7 +797,7 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       if (r) w->reps.push_back(r);
       if (s) return s;
       apply_l2_fetch(w);
-      CU(cudaMalloc(&r->slab, bytes));
+      CU(slab_alloc(r, bytes, w->vmm));
       r->view = gsi_view_of(r->slab, &w->hdr);
       if (!w->exact_entry) r->view.entry = nullptr;
       CU(cudaMemcpy(r->slab, src, bytes, cudaMemcpyDefault));
@@ -783,6 +901,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "tile_shift" && value >= -1 && value <= 15) w->tile_shift = (int) value;
   else if (k == "tile_ranges" && value >= 1 && value <= 64) w->tile_ranges = (int) value;
   else if (k == "tile_leaves" && value >= 1) w->tile_leaves = (int) value;
+  else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
   else if (k == "exact_entry" && (value == 0 || value == 1))
     {
       w->exact_entry = (int) value;
