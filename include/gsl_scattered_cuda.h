@@ -31,6 +31,15 @@
 extern "C" {
 #endif
 
+/* 64-bit unsigned counter / seed type.  Strict C89 has no long long; on LP64 (the only data model
+ * CUDA supports on Linux) unsigned long is the same 64-bit type at the ABI level. */
+#if defined(__cplusplus) || (defined(__STDC_VERSION__) && __STDC_VERSION__ >= 199901L)
+typedef unsigned long long gsl_scattered_cuda_u64;
+#else
+typedef unsigned long gsl_scattered_cuda_u64;
+typedef char gsl_scattered_cuda_u64_must_have_64_bits[sizeof (unsigned long) == 8 ? 1 : -1];
+#endif
+
 /* status codes, numerically identical to err/gsl_errno.h:38-75 */
 #define GSL_SCATTERED_SUCCESS 0
 #define GSL_SCATTERED_EDOM 1     /* at least one query lies outside the cage (find_leaf would assert) */
@@ -165,13 +174,13 @@ typedef struct
   double build_seconds;    /* host Delaunay build */
   double flatten_seconds;  /* host flatten */
   double upload_seconds;   /* H2D + device seeding + peer replication */
-  unsigned long long n_deferred; /* queries resolved by the exact replay since reset */
-  unsigned long long n_outside;  /* queries outside the cage since reset */
-  unsigned long long n_steps;    /* walk steps (only with param "stats") */
-  unsigned long long n_kernel_launches; /* eval kernels launched since reset */
+  gsl_scattered_cuda_u64 n_deferred; /* queries resolved by the exact replay since reset */
+  gsl_scattered_cuda_u64 n_outside;  /* queries outside the cage since reset */
+  gsl_scattered_cuda_u64 n_steps;    /* walk steps (only with param "stats") */
+  gsl_scattered_cuda_u64 n_kernel_launches; /* eval kernels launched since reset */
   double locate_seconds;   /* device time in the fast-path kernel (only with param "profile") */
   double exact_seconds;    /* device time in the exact-replay kernel (only with param "profile") */
-  unsigned long long n_reordered; /* queries that went through the reorder pipeline since reset */
+  gsl_scattered_cuda_u64 n_reordered; /* queries that went through the reorder pipeline since reset */
 } gsl_scattered_cuda_info;
 int gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info *info);
 int gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w);
@@ -212,24 +221,24 @@ void gsl_scattered_cuda_host_free(void *p);
  * query k of the stream `seed` is (xlo + (xhi-xlo)*u(seed,2k), ylo + (yhi-ylo)*u(seed,2k+1))
  * with u = splitmix64-based uniform; fills k in [first, first+nq). */
 int gsl_scattered_cuda_generate_uniform_device(const gsl_scattered_cuda *w, int dev,
-                                               unsigned long long seed, unsigned long long first,
+                                               gsl_scattered_cuda_u64 seed, gsl_scattered_cuda_u64 first,
                                                size_t nq, double xlo, double xhi, double ylo,
                                                double yhi, double *d_xq, double *d_yq,
                                                void *stream);
 /* same generator on the host (bit-identical) */
-void gsl_scattered_cuda_generate_uniform_host(unsigned long long seed, unsigned long long first,
+void gsl_scattered_cuda_generate_uniform_host(gsl_scattered_cuda_u64 seed, gsl_scattered_cuda_u64 first,
                                               size_t nq, double xlo, double xhi, double ylo,
                                               double yhi, double xq[], double yq[]);
 
 /* out[0] = wrapping sum of leaf ids, out[1] = wrapping sum of the value bit patterns */
 int gsl_scattered_cuda_checksum_device(const gsl_scattered_cuda *w, int dev, const int *d_leaf,
-                                       const double *d_val, size_t n, unsigned long long out[2],
+                                       const double *d_val, size_t n, gsl_scattered_cuda_u64 out[2],
                                        void *stream);
 /* out[0] = number of differing leaf ids, out[1] = number of differing value bit patterns */
 int gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, const int *d_leaf_a,
                                       const int *d_leaf_b, const double *d_val_a,
                                       const double *d_val_b, size_t n, size_t n_val,
-                                      unsigned long long out[2], void *stream);
+                                      gsl_scattered_cuda_u64 out[2], void *stream);
 
 const char *gsl_scattered_cuda_version(void);
 
