@@ -56,3 +56,32 @@ def test_c_host_program_reproduces_the_reference_raster(tmp_path, golden):
         assert np.array_equal(out[1:].view(np.uint64), want.view(np.uint64))
     else:
         assert np.allclose(out[1:], want, rtol=1e-9, equal_nan=True)
+
+
+GLUE = os.path.join(ROOT, "oracle", "_ref", "glue_demo")
+
+
+def test_reference_side_glue_builds_against_the_real_reference(have_gpu):
+    """INTEGRATION.md section 2 as a real translation unit (examples/reference_glue/): compiled by
+    oracle/Makefile against the reference's own headers and objects.  Without a GPU the demo
+    builds the tree with the reference and then refuses to evaluate (no CPU path)."""
+    if not os.path.exists(GLUE):
+        pytest.skip("oracle/_ref/glue_demo not built (needs the reference sources at build time)")
+    if have_gpu:
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([GLUE, "200", "3", "16"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU evaluation path" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,n_grid", [(50, 1, 100), (2000, 12345, 256), (20000, 7, 512)])
+def test_true_drop_in_reference_tree_evaluated_on_the_gpu(n, seed, n_grid):
+    """One C process: simplex_tree_init of the UNMODIFIED reference builds the tree, the glue hands
+    it to gsl_scattered_cuda_init_from_tree, and a raster (sticking out of the hull) plus the data
+    nodes themselves are evaluated both by the reference's find_leaf + interp_point loop and by
+    the GPU library: leaf ids and value bits must be identical."""
+    if not os.path.exists(GLUE):
+        pytest.skip("oracle/_ref/glue_demo not built")
+    r = subprocess.run([GLUE, str(n), str(seed), str(n_grid)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "leaf_mismatches 0 value_bit_mismatches 0" in r.stdout
