@@ -729,7 +729,7 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
       if (r) w->reps.push_back(r);
       if (s) return s;
       apply_l2_fetch(w);
-      CU(slab_alloc(r, w->hdr.total_bytes, w->vmm));
+      CU(slab_alloc(r, w->hdr.total_bytes, w->vmm && devs.size() == 1)); /* peer copies: plain cudaMalloc */
       r->view = gsi_view_of(r->slab, &w->hdr);
       if (!w->exact_entry) r->view.entry = nullptr;
     }
@@ -797,7 +797,7 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       if (r) w->reps.push_back(r);
       if (s) return s;
       apply_l2_fetch(w);
-      CU(slab_alloc(r, bytes, w->vmm));
+      CU(slab_alloc(r, bytes, w->vmm && devs.size() == 1));
       r->view = gsi_view_of(r->slab, &w->hdr);
       if (!w->exact_entry) r->view.entry = nullptr;
       CU(cudaMemcpy(r->slab, src, bytes, cudaMemcpyDefault));
