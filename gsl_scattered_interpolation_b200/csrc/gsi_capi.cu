@@ -124,7 +124,7 @@ struct gsl_scattered_cuda
      fields on a triangulation whose fast-path structure exceeds the L2) */
   int reorder = 0;
   size_t reorder_window = (size_t) 1 << 27, reorder_min = (size_t) 1 << 22;
-  int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_shift = -1, tile_ranges = 4, tile_leaves = 1024;
+  int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_ranges = 4, tile_smem = 1;
   size_t reorder_max_fields = 2;
   int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
   int vmm = 1;         /* slab through cuMemCreate/cuMemMap with the recommended granularity (0: cudaMalloc) */
@@ -404,44 +404,13 @@ want_reorder(const gsl_scattered_cuda *w, size_t nq)
   return nq >= w->reorder_min && w->n_fields <= w->reorder_max_fields && w->hdr.n_leaves >= 32768;
 }
 
-/* tile geometry of the reorder pipeline: tiles of 2^shift x 2^shift seed-grid cells holding
- * about tile_leaves leaves each (one tile's leaf records + seed cells should fit an SM's L1),
- * Morton id with at most GSI_TILE_BITS_MAX bits per axis */
-void
-tile_geometry(const gsl_scattered_cuda *w, int *shift, int *bits)
-{
-  const double G = (double) std::max<uint32_t>(1, w->hdr.grid_g);
-  const double L = (double) std::max<uint64_t>(1, w->hdr.n_leaves);
-  int s = w->tile_shift;
-  if (s < 0)
-    {
-      const double cells_per_tile = std::max(1.0, (double) w->tile_leaves * G * G / L);
-      s = (int) std::lround(0.5 * std::log2(cells_per_tile));
-    }
-  s = std::max(0, std::min(s, 15));
-  for (;;)
-    {
-      const uint32_t per_axis = (w->hdr.grid_g + (1u << s) - 1) >> s;
-      int b = 0;
-      while ((1u << b) < per_axis) b++;
-      if (b <= GSI_TILE_BITS_MAX)
-        {
-          *shift = s;
-          *bits = b;
-          return;
-        }
-      s++;
-    }
-}
-
 int
 ensure_reorder(const gsl_scattered_cuda *w, replica *r, size_t window, bool want_z, bool want_leaf)
 {
   gsi_reorder_scratch &o = r->ro;
-  int shift, bits;
-  tile_geometry(w, &shift, &bits);
+  const int bits = (int) w->hdr.tile_bits;
   const int S = std::max(32, std::min(w->reorder_chunk, GSI_BIN_CHUNK_MAX)) & ~31;
-  const size_t nt = (size_t) 1 << (2 * bits);
+  const size_t nt = (size_t) 1 << bits;
   const size_t n_chunks = (window + (size_t) S - 1) / (size_t) S;
   const size_t off_entries = n_chunks * (nt + 2);
   const size_t F = w->n_fields;
@@ -470,8 +439,8 @@ ensure_reorder(const gsl_scattered_cuda *w, replica *r, size_t window, bool want
       r->ro_fields = F;
     }
   if (want_leaf && !o.lb) CU(cudaMalloc(&o.lb, o.cap * sizeof(int)));
-  o.tile_shift = shift;
-  o.tile_bits = bits;
+  o.tile_max_leaves = (int) w->hdr.tile_max_leaves;
+  o.tile_smem = w->tile_smem;
   o.ranges = std::max(1, w->tile_ranges);
   return 0;
 }
@@ -778,7 +747,9 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       || h.off_dag + h.n_dag * sizeof(gsi_rec) > bytes
       || h.off_leaf + h.n_leaves * (uint64_t) h.leaf_stride > bytes
       || h.off_seeds + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes
-      || h.off_entry >= bytes || h.off_entry + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes)
+      || h.off_entry >= bytes || h.off_entry + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes
+      || h.tile_bits < 1 || h.tile_bits > 12 || h.off_tiles >= bytes
+      || h.off_tiles + (((uint64_t) 1 << h.tile_bits) + 1) * sizeof(int32_t) > bytes)
     GSI_ERROR("slab sections out of range", GSL_SCATTERED_EINVAL);
   drop_replicas(w);
   w->built = false;
@@ -898,9 +869,9 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "reorder_min" && value >= 0) w->reorder_min = (size_t) value;
   else if (k == "reorder_chunk" && value >= 32 && value <= GSI_BIN_CHUNK_MAX) w->reorder_chunk = (int) value;
   else if (k == "reorder_max_fields" && value >= 0) w->reorder_max_fields = (size_t) value;
-  else if (k == "tile_shift" && value >= -1 && value <= 15) w->tile_shift = (int) value;
   else if (k == "tile_ranges" && value >= 1 && value <= 64) w->tile_ranges = (int) value;
-  else if (k == "tile_leaves" && value >= 1) w->tile_leaves = (int) value;
+  else if (k == "tile_leaves" && value >= 1) w->fprm.tile_leaves = (uint32_t) value;
+  else if (k == "tile_smem" && (value == 0 || value == 1)) w->tile_smem = (int) value;
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
   else if (k == "exact_entry" && (value == 0 || value == 1))
     {

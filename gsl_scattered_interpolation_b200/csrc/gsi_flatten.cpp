@@ -160,6 +160,11 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   h.off_z = off;     off = align256(off + std::max<size_t>(1, n) * n_fields * sizeof(double));
   h.off_seeds = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
   h.off_entry = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
+  /* Morton-prefix tiles of about tile_leaves leaves: P bits, 2 <= P <= 12 */
+  uint32_t P = 2;
+  while (P < 12 && (double) L / (double) (1u << P) > (double) std::max<uint32_t>(1, prm.tile_leaves) * 1.05) P++;
+  h.tile_bits = P;
+  h.off_tiles = off; off = align256(off + ((uint64_t) (1u << P) + 1) * sizeof(int32_t));
   h.total_bytes = off;
 
   image->assign((size_t) h.total_bytes, 0);
@@ -248,6 +253,24 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
       lf.t = tail;
       std::memcpy(leaf_base + k * leaf_stride, &lf, sizeof lf);
     }
+
+  /* --- tiles: first leaf slot of every Morton prefix ------------------------------------ */
+  {
+    int32_t *tiles = (int32_t *) (base + h.off_tiles);
+    const uint32_t nt = 1u << h.tile_bits, sh = 32 - h.tile_bits;
+    size_t k = 0;
+    uint32_t biggest = 0;
+    for (uint32_t tl = 0; tl < nt; tl++)
+      {
+        while (k < L && (keyed[k].first >> sh) < tl) k++;
+        tiles[tl] = (int32_t) k;
+        if (tl) biggest = std::max<uint32_t>(biggest, (uint32_t) (tiles[tl] - tiles[tl - 1]));
+      }
+    tiles[nt] = (int32_t) L;
+    biggest = std::max<uint32_t>(biggest, (uint32_t) (tiles[nt] - tiles[nt - 1]));
+    gsi_slab_header *hp = (gsi_slab_header *) base;
+    hp->tile_max_leaves = biggest;
+  }
 
   /* --- values -------------------------------------------------------------------------- */
   if (za)

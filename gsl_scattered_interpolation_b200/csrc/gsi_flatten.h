@@ -15,6 +15,7 @@ struct gsi_flatten_params
   double delta = 3.725290298461914e-09; /* 2^-28: absolute edge margin, standardised units */
   double tau_floor = 9.094947017729282e-13; /* 2^-40 */
   uint32_t leaf_stride = 96;    /* 96 = packed records, 128 = one 128-byte line per leaf */
+  uint32_t tile_leaves = 1000;  /* target leaves per Morton-prefix tile (reorder pipeline) */
 };
 
 /* za: n_fields x n_points, field-major (may be NULL: values left zero).

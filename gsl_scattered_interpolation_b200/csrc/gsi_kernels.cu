@@ -393,7 +393,8 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
  * Uniformly random queries make every leaf fetch an isolated L2/DRAM access.  The pipeline
  * gives the walk spatial coherence without a global sort and without scattered global writes:
  *   k_bin          one CTA per chunk of <= 8192 consecutive queries: counting sort by spatial
- *                  tile (Morton id of a block of seed-grid cells) entirely in shared memory,
+ *                  tile (Morton-key prefix of the query position: the leaf order's own key, so a
+ *                  tile's leaves are one contiguous slot range) entirely in shared memory,
  *                  then coalesced stores of the binned coordinates, the 16-bit in-chunk index
  *                  of every binned query and the chunk's run table (start of each tile's run);
  *   k_tile_locate  tile-major: the CTAs of tile t gather t's run from every chunk (32 chunks
@@ -407,42 +408,46 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
  * bit-identical; deferred queries go to the same list (original query index) and are replayed
  * after k_unpermute. */
 __device__ __forceinline__ unsigned
-spread8(unsigned x) /* abcdefgh -> 0a0b0c0d0e0f0g0h */
+spread16(unsigned x) /* the low 16 bits of x on the even bit positions */
 {
-  x &= 0xffu;
-  x = (x | (x << 4)) & 0x0f0fu;
-  x = (x | (x << 2)) & 0x3333u;
-  x = (x | (x << 1)) & 0x5555u;
+  x &= 0x0000ffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
   return x;
 }
 
 __device__ __forceinline__ unsigned
-compact8(unsigned x)
+compact16(unsigned x) /* inverse of spread16 */
 {
-  x &= 0x5555u;
-  x = (x | (x >> 1)) & 0x3333u;
-  x = (x | (x >> 2)) & 0x0f0fu;
-  x = (x | (x >> 4)) & 0x00ffu;
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0f0f0f0fu;
+  x = (x | (x >> 4)) & 0x00ff00ffu;
+  x = (x | (x >> 8)) & 0x0000ffffu;
   return x;
 }
 
-/* Morton id of the tile (2^shift x 2^shift seed-grid cells) of a query; the cell is the one of
- * gsi_cell_of, so non-finite coordinates land in tile 0 and are deferred by the walk */
+/* Tile of a query = the tile_bits-bit prefix of the 32-bit Morton key of its position in the data
+ * bounding box (16 bits per axis, y on the odd bits) -- the key gsi_flatten.cpp sorts the leaves'
+ * centroids by, so tile t's leaves are the slots [V.tiles[t], V.tiles[t+1]).  Non-finite and
+ * outside coordinates are clamped (they are deferred by the walk anyway). */
 __device__ __forceinline__ unsigned
-tile_of(const gsi_view &V, double qx, double qy, int shift)
+tile_of(const gsi_view &V, double qx, double qy)
 {
   const double u = (qx - V.xf.cx) * V.xf.sx, v = (qy - V.xf.cy) * V.xf.sy;
-  const double gmax = (double) (V.grid_g - 1);
-  const int ix = __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du, 0.0), gmax));
-  const int iy = __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv, 0.0), gmax));
-  return spread8((unsigned) ix >> shift) | (spread8((unsigned) iy >> shift) << 1);
+  const double k = 65536.0 / (double) V.grid_g; /* (u - u0) * inv_du is in grid cells */
+  const unsigned ix = (unsigned) __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du * k, 0.0), 65535.0));
+  const unsigned iy = (unsigned) __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv * k, 0.0), 65535.0));
+  return (spread16(ix) | (spread16(iy) << 1)) >> (32 - V.tile_bits);
 }
 
 /* One coordinate is staged at a time (96 KB of shared memory for 8192-query chunks) so that two
  * CTAs share an SM and one CTA's global loads overlap the other's scan / copy-out. */
 __global__ void __launch_bounds__(GSI_BIN_THREADS, 2)
 k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict__ yq, size_t nq, int S,
-       int shift, int nt, double *__restrict__ bx, double *__restrict__ by,
+       int nt, double *__restrict__ bx, double *__restrict__ by,
        unsigned short *__restrict__ bi, unsigned short *__restrict__ off)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -472,7 +477,7 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
           pk[k] = 0xffffffffu;
           if (i < n)
             {
-              const unsigned t = tile_of(V, __ldg(xq + q0 + i), __ldg(yq + q0 + i), shift);
+              const unsigned t = tile_of(V, __ldg(xq + q0 + i), __ldg(yq + q0 + i));
               pk[k] = t | (atomicAdd(hist + t, 1u) << 12);
             }
         }
@@ -656,13 +661,10 @@ template <bool STATS>
 __global__ void __launch_bounds__(GSI_TILE_THREADS, 2)
 k_tile_locate(const gsi_view V, const double *__restrict__ bx, const double *__restrict__ by,
               const unsigned short *__restrict__ bi, const unsigned short *__restrict__ off,
-              unsigned n_chunks, int S, int nt, int shift, int ranges, double *zb, int *lb, size_t ldb,
+              unsigned n_chunks, int S, int nt, int ranges, double *zb, int *lb, size_t ldb,
               unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters, int max_steps)
 {
   const unsigned t = blockIdx.x / (unsigned) ranges, r = blockIdx.x - t * (unsigned) ranges;
-  /* Morton ids whose cells all lie beyond the grid hold no query */
-  if ((compact8(t) << shift) >= (unsigned) V.grid_g || (compact8(t >> 1) << shift) >= (unsigned) V.grid_g)
-    return;
   constexpr unsigned WPC = GSI_TILE_THREADS / 32;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned n_blocks = (n_chunks + 31u) >> 5;
@@ -679,6 +681,172 @@ k_tile_locate(const gsi_view V, const double *__restrict__ bx, const double *__r
           const size_t pos = tile_item(live ? base + lane : total - 1, cb, S, o0, len, incl, &cbase);
           tile_direct_step<STATS>(V, bx, by, bi, live, pos, cbase, zb, lb, ldb, list, list_cap, ovf_mask,
                                   counters, max_steps, steps_acc);
+        }
+    }
+  if (STATS && steps_acc)
+    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
+}
+
+/* ---- tile kernel with the tile staged in shared memory ---------------------------------------------
+ * k_tile_locate gathers every leaf sector through L1, and a divergent L1 access costs the same
+ * L1 cycles whether it hits or not (0.77 sectors/clk/SM measured).  Here the CTA first copies its
+ * tile -- the contiguous slot range [V.tiles[t], V.tiles[t+1]) of 96-byte leaf records and the
+ * block of seed cells under the tile's rectangle -- into shared memory with coalesced loads, and
+ * the walk reads seeds, records and tails from there; only leaves outside the tile (walks that
+ * leave it, tiles larger than the staging area) and the query coordinates come from global
+ * memory.  Same per-query operations as every other fast-path kernel. */
+__device__ __forceinline__ void
+fetch_rec_smem(gsi_rec *r, const uint4 *p)
+{
+  const uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+  r->x0x = __hiloint2double((int) a.y, (int) a.x);
+  r->x0y = __hiloint2double((int) a.w, (int) a.z);
+  r->u00 = __hiloint2double((int) b.y, (int) b.x);
+  r->u01 = __hiloint2double((int) b.w, (int) b.z);
+  r->u11 = __hiloint2double((int) c.y, (int) c.x);
+  r->l10 = __hiloint2double((int) c.w, (int) c.z);
+  r->lnk[0] = (int32_t) d.x;
+  r->lnk[1] = (int32_t) d.y;
+  r->lnk[2] = (int32_t) d.z;
+  r->meta = d.w;
+}
+
+__device__ __forceinline__ void
+fetch_tail_smem(gsi_leaf_tail *t, const uint4 *p)
+{
+  const uint4 e = p[4], f = p[5];
+  t->s.node = (int32_t) e.x;
+  t->s.vflags = e.y;
+  t->s.z[0] = __hiloint2double((int) e.w, (int) e.z);
+  t->s.z[1] = __hiloint2double((int) f.y, (int) f.x);
+  t->s.z[2] = __hiloint2double((int) f.w, (int) f.z);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(GSI_TILE_THREADS, 2)
+k_tile_locate_smem(const gsi_view V, const double *__restrict__ bx, const double *__restrict__ by,
+                   const unsigned short *__restrict__ bi, const unsigned short *__restrict__ off,
+                   unsigned n_chunks, int S, int nt, int ranges, int leaf_cap, int seed_rows, int seed_pitch,
+                   double *zb, int *lb, size_t ldb, unsigned *list, unsigned list_cap, unsigned *ovf_mask,
+                   unsigned *counters, int max_steps)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4 *sleaf = reinterpret_cast<uint4 *>(smem_raw);
+  int *sseed = reinterpret_cast<int *>(sleaf + (size_t) leaf_cap * 6);
+  const unsigned FULL = 0xffffffffu;
+  const unsigned t = blockIdx.x / (unsigned) ranges, r = blockIdx.x - t * (unsigned) ranges;
+  constexpr unsigned WPC = GSI_TILE_THREADS / 32;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned n_blocks = (n_chunks + 31u) >> 5;
+  const size_t ntp = (size_t) nt + 2;
+
+  /* ---- stage the tile ---- */
+  const int slot0 = V.tiles[t];
+  const int n_staged = min(V.tiles[t + 1] - slot0, leaf_cap);
+  if (V.leaf_stride == (int) sizeof(gsi_leaf))
+    {
+      const uint4 *src = reinterpret_cast<const uint4 *>(V.leaf + (size_t) slot0 * sizeof(gsi_leaf));
+      for (int i = threadIdx.x; i < n_staged * 6; i += GSI_TILE_THREADS) sleaf[i] = __ldg(src + i);
+    }
+  else
+    for (int i = threadIdx.x; i < n_staged * 6; i += GSI_TILE_THREADS)
+      sleaf[i] = __ldg(reinterpret_cast<const uint4 *>(V.leaf + (size_t) (slot0 + i / 6) * (size_t) V.leaf_stride) + i % 6);
+  /* the tile's rectangle in 16-bit Morton coordinates -> block of seed cells */
+  const int by_bits = (V.tile_bits + 1) >> 1, bx_bits = V.tile_bits >> 1;
+  const unsigned key_hi = t << (32 - V.tile_bits);
+  const unsigned qx_lo = compact16(key_hi), qy_lo = compact16(key_hi >> 1);
+  const double cells_per_q = (double) V.grid_g / 65536.0;
+  const int cx0 = max(0, (int) floor((double) qx_lo * cells_per_q) - 1);
+  const int cy0 = max(0, (int) floor((double) qy_lo * cells_per_q) - 1);
+  const int ncx = min(seed_pitch, V.grid_g - cx0), ncy = min(seed_rows, V.grid_g - cy0);
+  (void) bx_bits;
+  (void) by_bits;
+  for (int i = threadIdx.x; i < ncy * seed_pitch; i += GSI_TILE_THREADS)
+    {
+      const int ry = i / seed_pitch, rx = i - ry * seed_pitch;
+      if (rx < ncx) sseed[i] = __ldg(V.seeds + (size_t) (cy0 + ry) * (size_t) V.grid_g + (size_t) (cx0 + rx));
+    }
+  __syncthreads();
+
+  const double gmax = (double) (V.grid_g - 1);
+  unsigned long long steps_acc = 0;
+  for (unsigned cb = r * WPC + warp; cb < n_blocks; cb += (unsigned) ranges * WPC)
+    {
+      unsigned o0, len, incl;
+      const unsigned total = tile_runs(off, ntp, t, cb, n_blocks, n_chunks, o0, len, incl);
+      for (unsigned base = 0; base < total; base += 32)
+        {
+          const bool live = base + lane < total;
+          size_t cbase;
+          const size_t pos = tile_item(live ? base + lane : total - 1, cb, S, o0, len, incl, &cbase);
+          int status = GSI_STEP_MOVE; /* = not a live query */
+          int slot = 0;
+          double c0 = 0, c1 = 0;
+          if (live)
+            {
+              const double qx = __ldcs(bx + pos), qy = __ldcs(by + pos);
+              status = GSI_STEP_DEFER;
+              if (isfinite(qx) && isfinite(qy))
+                {
+                  /* the cell of gsi_cell_of; its seed from the staged block when it is inside */
+                  const double u = (qx - V.xf.cx) * V.xf.sx, v = (qy - V.xf.cy) * V.xf.sy;
+                  const int ix = __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du, 0.0), gmax));
+                  const int iy = __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv, 0.0), gmax));
+                  const unsigned rx = (unsigned) (ix - cx0), ry = (unsigned) (iy - cy0);
+                  slot = (rx < (unsigned) ncx && ry < (unsigned) ncy)
+                             ? sseed[ry * seed_pitch + rx]
+                             : gsi_ld_seed(V.seeds + (size_t) iy * (size_t) V.grid_g + (size_t) ix);
+                  for (int step = 0; step < max_steps; step++)
+                    {
+                      gsi_rec rec;
+                      const int at = slot;
+                      const unsigned rel = (unsigned) (at - slot0);
+                      if (rel < (unsigned) n_staged)
+                        fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
+                      else
+                        gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
+                      const int st = gsi_walk_step(&V.xf, &rec, qx, qy, &slot, &c0, &c1);
+                      if (st != GSI_STEP_MOVE)
+                        {
+                          status = st;
+                          slot = at;
+                          if (STATS && st == GSI_STEP_ACCEPT) steps_acc += (unsigned) step + 1u;
+                          break;
+                        }
+                    }
+                }
+            }
+          __syncwarp();
+          if (status == GSI_STEP_ACCEPT)
+            {
+              gsi_leaf_tail tl;
+              const unsigned rel = (unsigned) (slot - slot0);
+              if (rel < (unsigned) n_staged)
+                fetch_tail_smem(&tl, sleaf + (size_t) rel * 6);
+              else
+                gsi_fetch_tail(&tl, gsi_leaf_at(&V, slot));
+              if (lb) lb[pos] = tl.g.node;
+              if (zb) gsi_blend_store(&V, &tl, c0, c1, zb, ldb, pos);
+            }
+          const bool defer = status == GSI_STEP_DEFER;
+          const unsigned dm = __ballot_sync(FULL, defer);
+          if (dm)
+            {
+              const int leader = __ffs(dm) - 1;
+              unsigned at0 = 0;
+              if (lane == (unsigned) leader) at0 = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+              at0 = __shfl_sync(FULL, at0, leader);
+              if (defer)
+                {
+                  const size_t q = cbase + bi[pos];
+                  const unsigned at = at0 + __popc(dm & lt_mask);
+                  if (at < list_cap)
+                    list[at] = (unsigned) q;
+                  else
+                    mark_overflow(ovf_mask, q, counters);
+                }
+            }
         }
     }
   if (STATS && steps_acc)
@@ -825,16 +993,26 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
                  size_t ld, const gsi_launch_cfg &cfg, unsigned list_cap, cudaStream_t st)
 {
   const gsi_reorder_scratch *R = cfg.reorder;
-  if (!R || nq > R->cap || R->chunk < 32 || R->chunk > GSI_BIN_CHUNK_MAX) return false;
-  const int S = R->chunk, nt = 1 << (2 * R->tile_bits);
+  if (!R || nq > R->cap || R->chunk < 32 || R->chunk > GSI_BIN_CHUNK_MAX || V.tile_bits < 1 || V.tile_bits > 12)
+    return false;
+  const int S = R->chunk, nt = 1 << V.tile_bits;
   const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
   const size_t smem_bin = (size_t) S * 10 + (size_t) nt * 4, smem_unp = (size_t) S * 12;
+  /* staging area of the tile kernel: the largest tile's records (capped) + the seed cells under a
+     tile's rectangle (x gets floor(P/2) bits of the prefix, y the rest), two cells of margin */
+  const int bx_bits = V.tile_bits >> 1, by_bits = (V.tile_bits + 1) >> 1;
+  const int seed_pitch = (V.grid_g >> bx_bits) + 4, seed_rows = (V.grid_g >> by_bits) + 4;
+  const size_t seed_bytes = (size_t) seed_pitch * seed_rows * 4;
+  int leaf_cap = R->tile_max_leaves < 1 ? 1 : R->tile_max_leaves;
+  const size_t budget = 110 * 1024; /* two CTAs per SM */
+  if (seed_bytes + 96 > budget) leaf_cap = 0;
+  else if ((size_t) leaf_cap * 96 + seed_bytes > budget) leaf_cap = (int) ((budget - seed_bytes) / 96);
+  const size_t smem_tile = (size_t) leaf_cap * 96 + seed_bytes;
   /* per device (the current one), so not cached in a process-wide flag */
   cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 10 + 4096 * 4);
   cudaFuncSetAttribute(k_unpermute, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 12);
   const int g_bin = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
-  k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(V, src.x, src.y, nq, S, R->tile_shift, nt, R->bx, R->by, R->bi,
-                                                  R->off);
+  k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(V, src.x, src.y, nq, S, nt, R->bx, R->by, R->bi, R->off);
   /* CTAs per tile: every warp of a CTA should get a few 32-chunk blocks, else one CTA per tile */
   const size_t n_blocks = (n_chunks + 31) / 32;
   int ranges = (int) (n_blocks / (4 * (GSI_TILE_THREADS / 32)));
@@ -842,17 +1020,30 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
   if (ranges < 1) ranges = 1;
   double *zb = val ? R->zb : nullptr;
   int *lb = leaf_out ? R->lb : nullptr;
-  if (cfg.stats)
+  if (R->tile_smem && leaf_cap > 0)
+    {
+      cudaFuncSetAttribute(k_tile_locate_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget);
+      cudaFuncSetAttribute(k_tile_locate_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget);
+      if (cfg.stats)
+        k_tile_locate_smem<true><<<nt * ranges, GSI_TILE_THREADS, smem_tile, st>>>(
+            V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, leaf_cap, seed_rows, seed_pitch, zb,
+            lb, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+      else
+        k_tile_locate_smem<false><<<nt * ranges, GSI_TILE_THREADS, smem_tile, st>>>(
+            V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, leaf_cap, seed_rows, seed_pitch, zb,
+            lb, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+    }
+  else if (cfg.stats)
     k_tile_locate<true><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
-        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, zb, lb, R->cap,
-        cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, zb, lb, R->cap, cfg.list, list_cap,
+        cfg.ovf_mask, cfg.counters, cfg.max_steps);
   else
     k_tile_locate<false><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
-        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, R->tile_shift, ranges, zb, lb, R->cap,
-        cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, zb, lb, R->cap, cfg.list, list_cap,
+        cfg.ovf_mask, cfg.counters, cfg.max_steps);
   const int g_unp = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
   k_unpermute<<<g_unp, GSI_UNPERMUTE_THREADS, smem_unp, st>>>(R->zb, R->lb, R->bi, nq, S, V.n_fields, R->cap, val, ld,
-                                                        leaf_out);
+                                                              leaf_out);
   return true;
 }
 

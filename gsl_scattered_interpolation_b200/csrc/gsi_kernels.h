@@ -14,7 +14,6 @@
 #define GSI_UNPERMUTE_THREADS 1024 /* k_unpermute */
 #define GSI_BIN_CHUNK_MAX 8192  /* queries per chunk (16-bit in-chunk indices, 160 KB of shared memory) */
 #define GSI_TILE_THREADS 512    /* k_tile_locate */
-#define GSI_TILE_BITS_MAX 6     /* Morton tile id: <= 6 bits per axis = 4096 tiles */
 
 /* device counters (unsigned[16]) */
 #define GSI_CNT_DEFERRED 0       /* u32: length of the deferred list of the current launch */
@@ -33,8 +32,8 @@
 
 /* Scratch of the reorder pipeline (k_bin -> k_tile_locate -> k_unpermute), one per replica.
  * Queries are processed in windows of `cap` queries; a window is cut into chunks of `chunk`
- * consecutive queries and every chunk is sorted by spatial tile (Morton id of a 2^shift x
- * 2^shift block of seed-grid cells) inside shared memory, so both the reorder and its inverse
+ * consecutive queries and every chunk is sorted by spatial tile (Morton-key prefix, the tiles of
+ * the slab's tile table) inside shared memory, so both the reorder and its inverse
  * are chunk-local permutations with coalesced global traffic. */
 struct gsi_reorder_scratch
 {
@@ -46,9 +45,9 @@ struct gsi_reorder_scratch
   int *lb = nullptr;
   size_t cap = 0;     /* queries per window */
   int chunk = 0;      /* queries per chunk */
-  int tile_shift = 0; /* tile edge = 2^tile_shift grid cells */
-  int tile_bits = 0;  /* bits per axis of the Morton tile id (nt = 4^tile_bits) */
-  int ranges = 4;     /* k_tile_locate CTAs per tile, each taking a share of the chunks */
+  int tile_max_leaves = 0; /* leaves of the largest tile (slab header): size of the staging area */
+  int tile_smem = 1;  /* 1 = k_tile_locate_smem (tile staged in shared memory), 0 = k_tile_locate (L1) */
+  int ranges = 4;     /* tile-kernel CTAs per tile, each taking a share of the chunks */
 };
 
 struct gsi_launch_cfg

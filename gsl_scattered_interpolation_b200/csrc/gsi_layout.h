@@ -17,6 +17,10 @@
  *   seeds    int32[G*G]         uniform grid over the data bounding box in standardised
  *                               coordinates: leaf slot containing the cell centre
  *                               (filled on the device by the exact-replay kernel)
+ *   tiles    int32[2^P + 1]     the leaves are sorted by the Morton key of their centroid, so the
+ *                               leaves whose key starts with the P-bit prefix t are the slot
+ *                               range [tiles[t], tiles[t+1]): a spatial tile whose records can be
+ *                               staged in shared memory with one contiguous copy (reorder pipeline)
  *   entry    int32[G*G]         per grid cell, the deepest history-DAG node that the reference's
  *                               descent provably passes through for EVERY point of the cell
  *                               (0 = root): where the exact replay of a query of that cell
@@ -33,7 +37,7 @@
 #include "gsi_core.h"
 
 #define GSI_SLAB_MAGIC 0x3142414c53495347ull /* "GSISLAB1" */
-#define GSI_SLAB_VERSION 3u
+#define GSI_SLAB_VERSION 4u
 
 /* One compacted leaf: 96 bytes = three 32-byte sectors, each fetched with one 256-bit load
  * (LDG.E.256 on sm_100a).  A walk step reads r (sectors 0-1); only the accepted leaf's tail
@@ -81,7 +85,11 @@ typedef struct
   double delta; /* absolute safety margin (standardised units) behind the per-leaf tau */
   uint64_t off_dag, off_leaf, off_z, off_seeds;
   uint64_t total_bytes;
-  uint64_t reserved[7]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
+  uint64_t reserved[4]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
+  uint32_t tile_bits;       /* tiles = the 2^tile_bits prefixes of the leaves' 32-bit Morton keys */
+  uint32_t tile_max_leaves; /* largest tile */
+  uint64_t off_tiles;       /* int32[2^tile_bits + 1]: first leaf slot of every tile */
+  uint64_t reserved2;
   uint64_t off_entry;
 } gsi_slab_header;
 
@@ -94,6 +102,8 @@ typedef struct
   const double *z;
   const int32_t *seeds;
   const int32_t *entry; /* NULL: exact replay always starts at the root */
+  const int32_t *tiles; /* first leaf slot per Morton-prefix tile, 2^tile_bits + 1 entries */
+  int32_t tile_bits;
   double u0, v0, inv_du, inv_dv;
   double delta;
   int32_t grid_g;
@@ -126,6 +136,8 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   v.z = (const double *) (b + h->off_z);
   v.seeds = (const int32_t *) (b + h->off_seeds);
   v.entry = (const int32_t *) (b + h->off_entry);
+  v.tiles = (const int32_t *) (b + h->off_tiles);
+  v.tile_bits = (int32_t) h->tile_bits;
   v.delta = h->delta;
   v.u0 = h->u0; v.v0 = h->v0; v.inv_du = h->inv_du; v.inv_dv = h->inv_dv;
   v.grid_g = (int32_t) h->grid_g;

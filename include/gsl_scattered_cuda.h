@@ -93,8 +93,9 @@ int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_
  * tile-major walk -> inverse permutation): "reorder" (0 = off, default; 1 = always; 2 = large
  * few-field batches on triangulations beyond the L2), "reorder_window" (queries per window,
  * default 2^27), "reorder_chunk" (queries per sorted chunk, <= 8192), "reorder_min",
- * "reorder_max_fields", "tile_shift" (tile edge = 2^shift grid cells, -1 = from "tile_leaves"),
- * "tile_leaves" (default 1024), "tile_ranges" (CTAs per tile, default 4).
+ * "reorder_max_fields", "tile_leaves" (target leaves per Morton-prefix tile, default 1000; fixed
+ * at init/upload), "tile_smem" (1 = stage the tile's leaf records and seed cells in shared
+ * memory, default; 0 = read them through L1), "tile_ranges" (CTAs per tile, default 4).
  * Calls on one workspace share per-replica scratch (deferred list, counters, reorder buffers):
  * issue them on one stream at a time per device. */
 int gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double value);

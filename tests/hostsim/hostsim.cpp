@@ -27,7 +27,8 @@ extern "C" {
 
 hostsim *
 hostsim_create(const double *xa, const double *ya, const double *za, size_t n, size_t n_fields,
-               int flags, const size_t *order, double cells_per_leaf, double delta, int exact_entry)
+               int flags, const size_t *order, double cells_per_leaf, double delta, int exact_entry,
+               int tile_leaves)
 {
   hostsim *h = new hostsim();
   gsi_host_tree tree;
@@ -46,6 +47,7 @@ hostsim_create(const double *xa, const double *ya, const double *za, size_t n, s
   gsi_flatten_params prm;
   if (cells_per_leaf > 0) prm.cells_per_leaf = cells_per_leaf;
   if (delta > 0) prm.delta = delta;
+  if (tile_leaves > 0) prm.tile_leaves = (uint32_t) tile_leaves;
   if (gsi_flatten(tree, xa, ya, za, n_fields, prm, &h->image, &err))
     {
       delete h;
@@ -80,6 +82,9 @@ hostsim_free(hostsim *h)
 
 size_t hostsim_n_leaves(const hostsim *h) { return (size_t) h->hdr.n_leaves; }
 size_t hostsim_grid_g(const hostsim *h) { return (size_t) h->hdr.grid_g; }
+const int32_t *hostsim_tiles(const hostsim *h) { return (const int32_t *) (h->image.data() + h->hdr.off_tiles); }
+int hostsim_tile_bits(const hostsim *h) { return (int) h->hdr.tile_bits; }
+int hostsim_tile_max_leaves(const hostsim *h) { return (int) h->hdr.tile_max_leaves; }
 const int32_t *hostsim_entry(const hostsim *h) { return (const int32_t *) (h->image.data() + h->hdr.off_entry); }
 /* depth of DAG node `node` below the root is not stored; report the node type instead */
 int hostsim_node_is_leaf(const hostsim *h, int node) { return (h->view.dag[node].meta & GSI_META_TYPE_MASK) == GSI_LEAF; }

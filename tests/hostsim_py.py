@@ -19,7 +19,13 @@ def lib():
         H = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libhostsim.so"))
         H.hostsim_create.restype = c_void_p
         H.hostsim_create.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_void_p,
-                                     c_double, c_double, c_int]
+                                     c_double, c_double, c_int, c_int]
+        H.hostsim_tiles.restype = c_void_p
+        H.hostsim_tiles.argtypes = [c_void_p]
+        H.hostsim_tile_bits.restype = c_int
+        H.hostsim_tile_bits.argtypes = [c_void_p]
+        H.hostsim_tile_max_leaves.restype = c_int
+        H.hostsim_tile_max_leaves.argtypes = [c_void_p]
         H.hostsim_entry.restype = c_void_p
         H.hostsim_entry.argtypes = [c_void_p]
         H.hostsim_node_is_leaf.restype = c_int
@@ -36,7 +42,8 @@ def lib():
 
 
 class HostSim:
-    def __init__(self, xa, ya, za, flags=0, order=None, cells_per_leaf=0.0, delta=0.0, exact_entry=1):
+    def __init__(self, xa, ya, za, flags=0, order=None, cells_per_leaf=0.0, delta=0.0, exact_entry=1,
+                 tile_leaves=0):
         self.H = lib()
         xa = np.ascontiguousarray(xa, dtype=np.float64)
         ya = np.ascontiguousarray(ya, dtype=np.float64)
@@ -44,7 +51,7 @@ class HostSim:
         self.F = za.shape[0]
         order = None if order is None else np.ascontiguousarray(order, dtype=np.uint64)
         self.h = self.H.hostsim_create(_p(xa), _p(ya), _p(za), xa.size, self.F, flags, _p(order),
-                                       cells_per_leaf, delta, exact_entry)
+                                       cells_per_leaf, delta, exact_entry, tile_leaves)
         if not self.h:
             raise RuntimeError("hostsim_create failed")
 
@@ -53,6 +60,12 @@ class HostSim:
         g = self.H.hostsim_grid_g(self.h)
         buf = (ctypes.c_int32 * (g * g)).from_address(self.H.hostsim_entry(self.h))
         return np.frombuffer(buf, dtype=np.int32).copy()
+
+    def tiles(self):
+        """(tile_bits, first leaf slot per Morton-prefix tile [2^bits + 1], largest tile)"""
+        bits = self.H.hostsim_tile_bits(self.h)
+        buf = (ctypes.c_int32 * ((1 << bits) + 1)).from_address(self.H.hostsim_tiles(self.h))
+        return bits, np.frombuffer(buf, dtype=np.int32).copy(), self.H.hostsim_tile_max_leaves(self.h)
 
     def node_is_leaf(self, node):
         return bool(self.H.hostsim_node_is_leaf(self.h, int(node)))

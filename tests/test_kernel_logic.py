@@ -179,3 +179,19 @@ def test_logic_entry_nodes_shortcut_is_transparent(golden, kind, cpl):
             assert any(a.node_is_leaf(e) for e in interior[:: max(1, interior.size // 2000)])
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("n,tile_leaves", [(1000, 1000), (1000, 7), (20000, 1000), (20000, 100)])
+def test_tile_table_partitions_the_leaf_order(n, tile_leaves):
+    """slab section `tiles`: Morton-prefix tiles are consecutive slot ranges covering every leaf"""
+    xa, ya = synth.uniform_nodes(n)
+    hs = HostSim(xa, ya, synth.values(n, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n),
+                 tile_leaves=tile_leaves)
+    bits, tiles, biggest = hs.tiles()
+    L = hs.H.hostsim_n_leaves(hs.h)
+    assert 2 <= bits <= 12 and tiles.size == (1 << bits) + 1
+    assert tiles[0] == 0 and tiles[-1] == L and np.all(np.diff(tiles) >= 0)
+    assert biggest == np.diff(tiles).max()
+    if bits < 12:
+        assert L / (1 << bits) <= 1.05 * tile_leaves
+    hs.close()
