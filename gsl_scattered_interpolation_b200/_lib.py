@@ -1,8 +1,8 @@
 """ctypes binding of libgsl_scattered_cuda.so (C ABI in include/gsl_scattered_cuda.h).
 
-The library is built in-tree (``gsl_scattered_interpolation_b200/lib/``) by
-``gsl_scattered_interpolation_b200.build.build_library`` / ``__graft_entry__.build``.  There
-is deliberately no fallback: if the shared library is missing, importing the binding raises.
+The library is built in-tree (``gsl_scattered_interpolation_b200/lib/``) by ``make`` in
+``csrc/`` (what ``__graft_entry__.build()`` runs).  There is deliberately no fallback: if the
+shared library is missing, loading the binding raises.
 """
 import ctypes
 import os
@@ -27,7 +27,7 @@ class Info(ctypes.Structure):
         ("upload_seconds", c_double), ("n_deferred", c_ulonglong), ("n_outside", c_ulonglong),
         ("n_steps", c_ulonglong), ("n_kernel_launches", c_ulonglong),
         ("locate_seconds", c_double), ("exact_seconds", c_double),
-        ("n_reordered", c_ulonglong),
+        ("n_reordered", c_ulonglong), ("n_contexts", c_size_t),
     ]
 
 

@@ -63,6 +63,44 @@ report(const char *reason, const char *file, int line, int code)
     }                                                                                          \
   while (0)
 
+/* No C++ exception may cross the C ABI: every extern "C" body that can allocate (std::vector,
+ * std::string, std::thread) runs between these two macros and turns bad_alloc into
+ * GSL_SCATTERED_ENOMEM and anything else into GSL_SCATTERED_EFAILED, reported through the hook. */
+#define GSI_GUARD_BEGIN                                                                        \
+  try                                                                                          \
+    {
+#define GSI_GUARD_END                                                                          \
+    }                                                                                          \
+  catch (const std::bad_alloc &)                                                               \
+    {                                                                                          \
+      GSI_ERROR("out of host memory", GSL_SCATTERED_ENOMEM);                                   \
+    }                                                                                          \
+  catch (...)                                                                                  \
+    {                                                                                          \
+      GSI_ERROR("internal error (C++ exception)", GSL_SCATTERED_EFAILED);                      \
+    }
+
+/* The library switches the current CUDA device to the replica it works on; the caller's current
+ * device is restored when the entry point returns. */
+struct device_guard
+{
+  int prev = -1;
+  device_guard()
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess)
+      {
+        cudaGetLastError();
+        prev = -1;
+      }
+  }
+  ~device_guard()
+  {
+    if (prev >= 0 && cudaSetDevice(prev) != cudaSuccess) cudaGetLastError();
+  }
+  device_guard(const device_guard &) = delete;
+  device_guard &operator=(const device_guard &) = delete;
+};
+
 double
 now_s()
 {
@@ -77,6 +115,44 @@ struct stage_buf
   cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
 };
 
+/* pinned host staging for callers that hold pageable (malloc'd) arrays, as the reference's
+ * gsl_matrix / gsl_vector do */
+struct host_stage
+{
+  double *x = nullptr, *y = nullptr, *z = nullptr;
+  int *leaf = nullptr;
+  cudaEvent_t ev_out = nullptr;
+};
+
+/* Everything ONE evaluation call in flight needs besides the (read-only) slab: streams, deferred
+ * list, counters, staging buffers, reorder scratch.  Contexts are pooled per replica, so eval*
+ * is re-entrant across host threads: concurrent calls on one workspace get
+ * different contexts and never share mutable device state. */
+struct eval_ctx
+{
+  cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
+  unsigned *list = nullptr;
+  size_t list_cap = 0;
+  unsigned *ovf_mask = nullptr; /* overflow bitmask, one bit per query of a launch */
+  size_t ovf_words = 0;
+  unsigned *counters = nullptr;
+  unsigned long long *scratch2 = nullptr; /* 2 x u64 for checksum / compare */
+  stage_buf st[2];
+  size_t st_cap = 0, st_fields = 0;
+  host_stage hs[2];
+  size_t hs_cap = 0, hs_fields = 0;
+  gsi_reorder_scratch ro; /* reorder pipeline scratch (lazily sized) */
+  size_t ro_fields = 0, ro_runs_entries = 0;
+  /* profiling (param "profile"): timed event pairs around every kernel launch */
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_locate, prof_exact;
+  double locate_seconds = 0, exact_seconds = 0;
+  unsigned long long n_launches = 0, n_reordered = 0;
+  /* recorded on the stream that used the context last: the next user's stream waits for it, so a
+     context can be handed on while an asynchronous call on a caller's stream is still running */
+  cudaEvent_t ev_done = nullptr;
+  bool busy = false;
+};
+
 struct replica
 {
   int dev = 0;
@@ -88,22 +164,8 @@ struct replica
   unsigned long long slab_handle = 0;
   size_t slab_mapped = 0;
   gsi_view view;
-  cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
-  unsigned *list = nullptr;
-  size_t list_cap = 0;
-  unsigned *ovf_mask = nullptr; /* overflow bitmask, one bit per query of a launch */
-  size_t ovf_words = 0;
-  unsigned *counters = nullptr;
-  unsigned long long *scratch2 = nullptr; /* 2 x u64 for checksum / compare */
-  stage_buf st[2];
-  size_t st_cap = 0, st_fields = 0;
-  gsi_reorder_scratch ro; /* reorder pipeline scratch (lazily sized) */
-  size_t ro_fields = 0, ro_off_entries = 0;
-  /* profiling (param "profile"): timed event pairs around every kernel launch */
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_locate, prof_exact;
-  double locate_seconds = 0, exact_seconds = 0;
-  unsigned long long n_launches = 0, n_reordered = 0;
-  std::mutex mu;
+  std::mutex mu; /* guards the context pool, nothing else */
+  std::vector<eval_ctx *> ctxs;
 };
 
 } // namespace
@@ -118,13 +180,14 @@ struct gsl_scattered_cuda
   gsi_flatten_params fprm;
   int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
   int kernel = GSI_KERNEL_AUTO, walk_ctas_per_sm = 4;
-  int l2_fetch = 32; /* cudaLimitMaxL2FetchGranularity: random 32-byte sector gathers */
-  /* reorder pipeline (gsi_kernels.cu): 0 = off (default: measured slower than the direct walk on
-     B200), 1 = always for query arrays, 2 = auto (large batches of few
-     fields on a triangulation whose fast-path structure exceeds the L2) */
-  int reorder = 0;
-  size_t reorder_window = (size_t) 1 << 27, reorder_min = (size_t) 1 << 22;
-  int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_ranges = 4, tile_smem = 1;
+  int l2_fetch = 0; /* cudaLimitMaxL2FetchGranularity, device-wide: 0 = leave the host application's setting
+                       alone (measured without effect on B200: an L2 miss fills the whole 128-byte line) */
+  /* reorder pipeline (gsi_kernels.cu): 0 = off, 1 = always for query arrays, 2 = auto (default):
+     large batches of few fields on a triangulation whose fast-path structure exceeds the L2 */
+  int reorder = 2;
+  size_t reorder_window = (size_t) 1 << 27, reorder_min = (size_t) 1 << 24;
+  size_t reorder_min_leaves = 600000; /* ~58 MB of leaf records: about half the L2 */
+  int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_ranges = 0, tile_threads = GSI_TILE_THREADS;
   size_t reorder_max_fields = 2;
   int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
   int vmm = 1;         /* slab through cuMemCreate/cuMemMap with the recommended granularity (0: cudaMalloc) */
@@ -132,6 +195,8 @@ struct gsl_scattered_cuda
   size_t chunk = (size_t) 0xfffffff0u;
   double list_fraction = 1.0 / 8;
   size_t host_chunk = (size_t) 1 << 22;
+  int copy_threads = 4; /* host threads moving pageable caller arrays to / from the pinned staging */
+  size_t pageable_min = (size_t) 1 << 18; /* smaller pageable batches go straight through cudaMemcpyAsync */
   std::vector<int> devs;
   std::vector<replica *> reps;
   gsi_slab_header hdr;
@@ -254,35 +319,52 @@ slab_alloc(replica *r, size_t bytes, int use_vmm)
 }
 
 void
-free_reorder(replica *r)
+free_reorder(eval_ctx *c)
 {
-  gsi_reorder_scratch &o = r->ro;
+  gsi_reorder_scratch &o = c->ro;
   if (o.bx) cudaFree(o.bx);
   if (o.by) cudaFree(o.by);
   if (o.bi) cudaFree(o.bi);
-  if (o.off) cudaFree(o.off);
+  if (o.runs) cudaFree(o.runs);
+  if (o.work) cudaFree(o.work);
   if (o.zb) cudaFree(o.zb);
   if (o.lb) cudaFree(o.lb);
   o = gsi_reorder_scratch();
-  r->ro_fields = r->ro_off_entries = 0;
+  c->ro_fields = c->ro_runs_entries = 0;
 }
 
 void
-free_replica(replica *r)
+free_host_stage(eval_ctx *c)
 {
-  if (!r) return;
-  cudaSetDevice(r->dev);
-  for (auto &p : r->prof_locate) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  for (auto &p : r->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  slab_free(r);
-  if (r->list) cudaFree(r->list);
-  if (r->ovf_mask) cudaFree(r->ovf_mask);
-  if (r->counters) cudaFree(r->counters);
-  if (r->scratch2) cudaFree(r->scratch2);
-  free_reorder(r);
   for (int b = 0; b < 2; b++)
     {
-      stage_buf &s = r->st[b];
+      host_stage &h = c->hs[b];
+      if (h.x) cudaFreeHost(h.x);
+      if (h.y) cudaFreeHost(h.y);
+      if (h.z) cudaFreeHost(h.z);
+      if (h.leaf) cudaFreeHost(h.leaf);
+      h.x = h.y = h.z = nullptr;
+      h.leaf = nullptr;
+    }
+  c->hs_cap = c->hs_fields = 0;
+}
+
+/* the current device must be the context's */
+void
+free_ctx(eval_ctx *c)
+{
+  if (!c) return;
+  for (auto &p : c->prof_locate) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto &p : c->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  if (c->list) cudaFree(c->list);
+  if (c->ovf_mask) cudaFree(c->ovf_mask);
+  if (c->counters) cudaFree(c->counters);
+  if (c->scratch2) cudaFree(c->scratch2);
+  free_reorder(c);
+  free_host_stage(c);
+  for (int b = 0; b < 2; b++)
+    {
+      stage_buf &s = c->st[b];
       if (s.x) cudaFree(s.x);
       if (s.y) cudaFree(s.y);
       if (s.z) cudaFree(s.z);
@@ -290,10 +372,25 @@ free_replica(replica *r)
       if (s.ev_in) cudaEventDestroy(s.ev_in);
       if (s.ev_k) cudaEventDestroy(s.ev_k);
       if (s.ev_out) cudaEventDestroy(s.ev_out);
+      if (c->hs[b].ev_out) cudaEventDestroy(c->hs[b].ev_out);
     }
-  if (r->s_k) cudaStreamDestroy(r->s_k);
-  if (r->s_in) cudaStreamDestroy(r->s_in);
-  if (r->s_out) cudaStreamDestroy(r->s_out);
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
+  if (c->s_k) cudaStreamDestroy(c->s_k);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  delete c;
+}
+
+void
+free_replica(replica *r)
+{
+  if (!r) return;
+  cudaSetDevice(r->dev);
+  cudaDeviceSynchronize();
+  for (eval_ctx *c : r->ctxs) free_ctx(c);
+  r->ctxs.clear();
+  slab_free(r);
+  cudaGetLastError();
   delete r;
 }
 
@@ -306,6 +403,89 @@ drop_replicas(gsl_scattered_cuda *w)
 }
 
 int
+make_ctx(eval_ctx **out)
+{
+  eval_ctx *c = new (std::nothrow) eval_ctx();
+  if (!c) GSI_ERROR("out of memory", GSL_SCATTERED_ENOMEM);
+  *out = c;
+  CU(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  CU(cudaMalloc(&c->counters, GSI_CNT_WORDS * sizeof(unsigned)));
+  CU(cudaMemset(c->counters, 0, GSI_CNT_WORDS * sizeof(unsigned)));
+  CU(cudaMalloc(&c->scratch2, 2 * sizeof(unsigned long long)));
+  CU(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  for (int b = 0; b < 2; b++)
+    {
+      CU(cudaEventCreateWithFlags(&c->st[b].ev_in, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->st[b].ev_k, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->st[b].ev_out, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->hs[b].ev_out, cudaEventDisableTiming));
+    }
+  return 0;
+}
+
+/* Take a context of replica r for one evaluation call (current device = r->dev).  `user` is the
+ * caller's stream or NULL; *st receives the stream the call launches on, already ordered after
+ * whatever used the context before. */
+int
+acquire_ctx(replica *r, cudaStream_t user, eval_ctx **out, cudaStream_t *st)
+{
+  eval_ctx *c = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(r->mu);
+    for (eval_ctx *k : r->ctxs)
+      if (!k->busy)
+        {
+          c = k;
+          c->busy = true;
+          break;
+        }
+  }
+  if (!c)
+    {
+      const int s = make_ctx(&c);
+      if (s)
+        {
+          free_ctx(c);
+          return s;
+        }
+      c->busy = true;
+      std::lock_guard<std::mutex> lock(r->mu);
+      r->ctxs.push_back(c);
+    }
+  *out = c;
+  *st = user ? user : c->s_k;
+  CU(cudaStreamWaitEvent(*st, c->ev_done, 0));
+  return 0;
+}
+
+void
+release_ctx(replica *r, eval_ctx *c, cudaStream_t st)
+{
+  if (!c) return;
+  if (cudaEventRecord(c->ev_done, st) != cudaSuccess) cudaGetLastError();
+  std::lock_guard<std::mutex> lock(r->mu);
+  c->busy = false;
+}
+
+/* RAII: a context for the duration of one entry point */
+struct ctx_lease
+{
+  replica *r = nullptr;
+  eval_ctx *c = nullptr;
+  cudaStream_t st = nullptr;
+  int status = 0;
+  ctx_lease(replica *rep, cudaStream_t user) : r(rep) { status = acquire_ctx(r, user, &c, &st); }
+  ~ctx_lease()
+  {
+    if (status == 0) release_ctx(r, c, st);
+  }
+  ctx_lease(const ctx_lease &) = delete;
+  ctx_lease &operator=(const ctx_lease &) = delete;
+};
+
+int
 make_replica(int dev, replica **out)
 {
   replica *r = new (std::nothrow) replica();
@@ -316,24 +496,11 @@ make_replica(int dev, replica **out)
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, dev));
   r->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&r->s_k, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&r->s_in, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&r->s_out, cudaStreamNonBlocking));
-  CU(cudaMalloc(&r->counters, GSI_CNT_WORDS * sizeof(unsigned)));
-  CU(cudaMemset(r->counters, 0, GSI_CNT_WORDS * sizeof(unsigned)));
-  CU(cudaMalloc(&r->scratch2, 2 * sizeof(unsigned long long)));
-  for (int b = 0; b < 2; b++)
-    {
-      CU(cudaEventCreateWithFlags(&r->st[b].ev_in, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&r->st[b].ev_k, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&r->st[b].ev_out, cudaEventDisableTiming));
-    }
   return 0;
 }
 
-/* The eval path gathers isolated 32-byte sectors from a structure that exceeds the L2 at
- * 10^6 nodes; the default 64-byte L2 fetch granularity would double the DRAM traffic of every
- * miss.  Device-wide hint (cudaLimitMaxL2FetchGranularity); 0 = leave the driver default. */
+/* Optional device-wide hint (cudaLimitMaxL2FetchGranularity), param "l2_fetch"; off by default:
+ * the library does not touch device-wide state of its host application unless asked. */
 void
 apply_l2_fetch(const gsl_scattered_cuda *w)
 {
@@ -353,95 +520,99 @@ find_replica(const gsl_scattered_cuda *w, int dev)
 }
 
 int
-ensure_list(replica *r, size_t cap, size_t per_launch)
+ensure_list(eval_ctx *c, size_t cap, size_t per_launch)
 {
-  if (r->list_cap < cap)
+  if (c->list_cap < cap)
     {
-      if (r->list) cudaFree(r->list);
-      r->list = nullptr;
-      r->list_cap = 0;
-      CU(cudaMalloc(&r->list, cap * sizeof(unsigned)));
-      r->list_cap = cap;
+      if (c->list) cudaFree(c->list);
+      c->list = nullptr;
+      c->list_cap = 0;
+      CU(cudaMalloc(&c->list, cap * sizeof(unsigned)));
+      c->list_cap = cap;
     }
   const size_t words = (per_launch + 31) / 32;
-  if (r->ovf_words < words)
+  if (c->ovf_words < words)
     {
-      if (r->ovf_mask) cudaFree(r->ovf_mask);
-      r->ovf_mask = nullptr;
-      r->ovf_words = 0;
-      CU(cudaMalloc(&r->ovf_mask, words * sizeof(unsigned)));
-      CU(cudaMemset(r->ovf_mask, 0, words * sizeof(unsigned))); /* kernels leave it zero */
-      r->ovf_words = words;
+      if (c->ovf_mask) cudaFree(c->ovf_mask);
+      c->ovf_mask = nullptr;
+      c->ovf_words = 0;
+      CU(cudaMalloc(&c->ovf_mask, words * sizeof(unsigned)));
+      CU(cudaMemset(c->ovf_mask, 0, words * sizeof(unsigned))); /* kernels leave it zero */
+      c->ovf_words = words;
     }
   return 0;
 }
 
 gsi_launch_cfg
-cfg_of(const gsl_scattered_cuda *w, const replica *r)
+cfg_of(const gsl_scattered_cuda *w, const replica *r, const eval_ctx *c)
 {
-  gsi_launch_cfg c;
-  c.mode = w->mode;
-  c.stats = w->stats;
-  c.max_steps = w->max_steps;
-  c.sm_count = r->sm_count;
-  c.locate_ctas_per_sm = w->ctas_per_sm;
-  c.kernel = w->kernel;
-  c.walk_ctas_per_sm = w->walk_ctas_per_sm;
-  c.walk_chunk = w->walk_chunk;
-  c.list = r->list;
-  c.list_capacity = r->list_cap;
-  c.ovf_mask = r->ovf_mask;
-  c.counters = r->counters;
-  return c;
+  gsi_launch_cfg g;
+  g.mode = w->mode;
+  g.stats = w->stats;
+  g.max_steps = w->max_steps;
+  g.sm_count = r->sm_count;
+  g.locate_ctas_per_sm = w->ctas_per_sm;
+  g.kernel = w->kernel;
+  g.walk_ctas_per_sm = w->walk_ctas_per_sm;
+  g.walk_chunk = w->walk_chunk;
+  g.list = c->list;
+  g.list_capacity = c->list_cap;
+  g.ovf_mask = c->ovf_mask;
+  g.counters = c->counters;
+  return g;
 }
 
-/* Does a batch of nq incoherent queries go through the reorder pipeline? */
+/* Does a batch of nq incoherent queries go through the reorder pipeline?  Auto (2): the batch is
+ * large enough to amortise three streaming passes and the leaf records do not fit the L2, so the
+ * direct walk would pay an HBM line fill per visited leaf. */
 bool
 want_reorder(const gsl_scattered_cuda *w, size_t nq)
 {
   if (w->mode != GSI_MODE_FAST || w->reorder == 0 || nq == 0) return false;
+  if (w->hdr.tile_bits < 1 || w->hdr.tile_bits > 12) return false;
   if (w->reorder == 1) return true;
-  return nq >= w->reorder_min && w->n_fields <= w->reorder_max_fields && w->hdr.n_leaves >= 32768;
+  return nq >= w->reorder_min && w->n_fields <= w->reorder_max_fields && w->hdr.n_leaves >= w->reorder_min_leaves;
 }
 
 int
-ensure_reorder(const gsl_scattered_cuda *w, replica *r, size_t window, bool want_z, bool want_leaf)
+ensure_reorder(const gsl_scattered_cuda *w, eval_ctx *c, size_t window, bool want_z, bool want_leaf)
 {
-  gsi_reorder_scratch &o = r->ro;
+  gsi_reorder_scratch &o = c->ro;
   const int bits = (int) w->hdr.tile_bits;
   const int S = std::max(32, std::min(w->reorder_chunk, GSI_BIN_CHUNK_MAX)) & ~31;
   const size_t nt = (size_t) 1 << bits;
   const size_t n_chunks = (window + (size_t) S - 1) / (size_t) S;
-  const size_t off_entries = n_chunks * (nt + 2);
+  const size_t runs_entries = n_chunks * nt;
   const size_t F = w->n_fields;
   if (o.cap < window || o.chunk != S)
     {
-      free_reorder(r);
+      free_reorder(c);
       CU(cudaMalloc(&o.bx, window * sizeof(double)));
       CU(cudaMalloc(&o.by, window * sizeof(double)));
       CU(cudaMalloc(&o.bi, window * sizeof(unsigned short)));
+      CU(cudaMalloc(&o.work, 64));
       o.cap = window;
       o.chunk = S;
     }
-  if (r->ro_off_entries < off_entries)
+  if (c->ro_runs_entries < runs_entries)
     {
-      if (o.off) cudaFree(o.off);
-      o.off = nullptr;
-      r->ro_off_entries = 0;
-      CU(cudaMalloc(&o.off, off_entries * sizeof(unsigned short)));
-      r->ro_off_entries = off_entries;
+      if (o.runs) cudaFree(o.runs);
+      o.runs = nullptr;
+      c->ro_runs_entries = 0;
+      CU(cudaMalloc(&o.runs, runs_entries * sizeof(unsigned)));
+      c->ro_runs_entries = runs_entries;
     }
-  if (want_z && (!o.zb || r->ro_fields < F))
+  if (want_z && (!o.zb || c->ro_fields < F))
     {
       if (o.zb) cudaFree(o.zb);
       o.zb = nullptr;
       CU(cudaMalloc(&o.zb, o.cap * F * sizeof(double)));
-      r->ro_fields = F;
+      c->ro_fields = F;
     }
   if (want_leaf && !o.lb) CU(cudaMalloc(&o.lb, o.cap * sizeof(int)));
   o.tile_max_leaves = (int) w->hdr.tile_max_leaves;
-  o.tile_smem = w->tile_smem;
-  o.ranges = std::max(1, w->tile_ranges);
+  o.ranges = w->tile_ranges;
+  o.tile_threads = w->tile_threads;
   return 0;
 }
 
@@ -454,36 +625,33 @@ struct raster_spec
 };
 
 int
-prepare_launch(const gsl_scattered_cuda *w, replica *r, size_t per_launch, cudaEvent_t ev[4],
-               gsi_launch_cfg *cfg)
+prepare_launch(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, cudaEvent_t ev[4], gsi_launch_cfg *cfg)
 {
-  *cfg = cfg_of(w, r);
+  *cfg = cfg_of(w, r, c);
   if (w->profile)
     {
       for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ev[i]));
       if (w->mode == GSI_MODE_FAST)
         {
           cfg->ev_locate0 = ev[0]; cfg->ev_locate1 = ev[1];
-          r->prof_locate.emplace_back(ev[0], ev[1]);
+          c->prof_locate.emplace_back(ev[0], ev[1]);
         }
       else
         {
           cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
         }
       cfg->ev_exact0 = ev[2]; cfg->ev_exact1 = ev[3];
-      r->prof_exact.emplace_back(ev[2], ev[3]);
+      c->prof_exact.emplace_back(ev[2], ev[3]);
     }
-  r->n_launches += (w->mode == GSI_MODE_FAST) ? 4 : 1;
-  (void) per_launch;
+  c->n_launches += (w->mode == GSI_MODE_FAST) ? 4 : 1;
   return 0;
 }
 
 /* chunked launch of the locate+blend kernels on device data: either query arrays (ras == NULL)
  * or a block of raster columns.  d_z / d_leaf point at the first query / pixel of the block. */
 int
-eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const double *d_y,
-               const raster_spec *ras, size_t nq, double *d_z, size_t ld, int *d_leaf,
-               cudaStream_t st)
+eval_on_device(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, const double *d_x, const double *d_y,
+               const raster_spec *ras, size_t nq, double *d_z, size_t ld, int *d_leaf, cudaStream_t st)
 {
   if (nq == 0) return 0;
   size_t chunk = std::max<size_t>(1, std::min(w->chunk, (size_t) 0xfffffff0u));
@@ -491,7 +659,7 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
   if (reorder)
     {
       chunk = std::min(chunk, std::max<size_t>(w->reorder_window, 32));
-      const int s = ensure_reorder(w, r, std::min(chunk, nq), d_z != nullptr, d_leaf != nullptr);
+      const int s = ensure_reorder(w, c, std::min(chunk, nq), d_z != nullptr, d_leaf != nullptr);
       if (s) return s;
     }
   size_t cols_per_chunk = 0;
@@ -507,7 +675,7 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
       const size_t per_launch = std::min(chunk, nq);
       const size_t want = std::max<size_t>(std::min<size_t>(per_launch, 65536),
                                            (size_t) (w->list_fraction * (double) per_launch));
-      const int s = ensure_list(r, want, per_launch);
+      const int s = ensure_list(c, want, per_launch);
       if (s) return s;
     }
   for (size_t off = 0; off < nq; off += chunk)
@@ -515,13 +683,13 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
       const size_t n = std::min(chunk, nq - off);
       gsi_launch_cfg cfg;
       cudaEvent_t ev[4];
-      const int s = prepare_launch(w, r, n, ev, &cfg);
+      const int s = prepare_launch(w, r, c, ev, &cfg);
       if (s) return s;
       if (reorder)
         {
-          cfg.reorder = &r->ro;
-          r->n_reordered += n;
-          r->n_launches += 2; /* k_bin + k_tile_locate + k_unpermute instead of one locate kernel */
+          cfg.reorder = &c->ro;
+          c->n_reordered += n;
+          c->n_launches += 2; /* k_bin + k_tile_walk + k_unpermute instead of one locate kernel */
         }
       cudaError_t e;
       if (ras)
@@ -538,20 +706,19 @@ eval_on_device(const gsl_scattered_cuda *w, replica *r, const double *d_x, const
 }
 
 int
-read_counters(replica *r, unsigned out[GSI_CNT_WORDS])
+read_counters(eval_ctx *c, unsigned out[GSI_CNT_WORDS])
 {
-  CU(cudaSetDevice(r->dev));
-  CU(cudaMemcpy(out, r->counters, GSI_CNT_WORDS * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, c->counters, GSI_CNT_WORDS * sizeof(unsigned), cudaMemcpyDeviceToHost));
   return 0;
 }
 
 int
-ensure_stage(replica *r, size_t cap, size_t fields)
+ensure_stage(eval_ctx *c, size_t cap, size_t fields)
 {
-  if (r->st_cap >= cap && r->st_fields >= fields) return 0;
+  if (c->st_cap >= cap && c->st_fields >= fields) return 0;
   for (int b = 0; b < 2; b++)
     {
-      stage_buf &s = r->st[b];
+      stage_buf &s = c->st[b];
       if (s.x) cudaFree(s.x);
       if (s.y) cudaFree(s.y);
       if (s.z) cudaFree(s.z);
@@ -559,52 +726,136 @@ ensure_stage(replica *r, size_t cap, size_t fields)
       s.x = s.y = s.z = nullptr;
       s.leaf = nullptr;
     }
-  r->st_cap = r->st_fields = 0;
+  c->st_cap = c->st_fields = 0;
   for (int b = 0; b < 2; b++)
     {
-      stage_buf &s = r->st[b];
+      stage_buf &s = c->st[b];
       CU(cudaMalloc(&s.x, cap * sizeof(double)));
       CU(cudaMalloc(&s.y, cap * sizeof(double)));
       CU(cudaMalloc(&s.z, cap * fields * sizeof(double)));
       CU(cudaMalloc(&s.leaf, cap * sizeof(int)));
     }
-  r->st_cap = cap;
-  r->st_fields = fields;
+  c->st_cap = cap;
+  c->st_fields = fields;
   return 0;
 }
 
+int
+ensure_host_stage(eval_ctx *c, size_t cap, size_t fields)
+{
+  if (c->hs_cap >= cap && c->hs_fields >= fields) return 0;
+  free_host_stage(c);
+  for (int b = 0; b < 2; b++)
+    {
+      host_stage &h = c->hs[b];
+      CU(cudaHostAlloc((void **) &h.x, cap * sizeof(double), cudaHostAllocDefault));
+      CU(cudaHostAlloc((void **) &h.y, cap * sizeof(double), cudaHostAllocDefault));
+      CU(cudaHostAlloc((void **) &h.z, cap * fields * sizeof(double), cudaHostAllocDefault));
+      CU(cudaHostAlloc((void **) &h.leaf, cap * sizeof(int), cudaHostAllocDefault));
+    }
+  c->hs_cap = cap;
+  c->hs_fields = fields;
+  return 0;
+}
+
+/* is p ordinary pageable host memory (not pinned / registered / managed)? */
+bool
+is_pageable(const void *p)
+{
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return true;
+    }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+/* several host threads share one large copy (a single core moves ~10 GB/s, the PCIe link 50) */
+void
+parallel_copy(int threads, const std::vector<std::pair<void *, const void *>> &jobs, const std::vector<size_t> &bytes)
+{
+  size_t total = 0;
+  for (size_t b : bytes) total += b;
+  if (threads <= 1 || total < ((size_t) 1 << 20))
+    {
+      for (size_t j = 0; j < jobs.size(); j++) std::memcpy(jobs[j].first, jobs[j].second, bytes[j]);
+      return;
+    }
+  auto part = [&](int t) {
+    for (size_t j = 0; j < jobs.size(); j++)
+      {
+        const size_t lo = bytes[j] * (size_t) t / (size_t) threads, hi = bytes[j] * (size_t) (t + 1) / (size_t) threads;
+        std::memcpy((char *) jobs[j].first + lo, (const char *) jobs[j].second + lo, hi - lo);
+      }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < threads; t++) th.emplace_back(part, t);
+  part(0);
+  for (auto &t : th) t.join();
+}
+
 /* host-buffer pipeline on one replica: H2D (s_in) | kernels (s_k) | D2H (s_out), two chunk
- * buffers in flight.  With pinned user buffers (gsl_scattered_cuda_host_alloc) all three
- * stages overlap; pageable buffers work but the copies serialise on the host. */
+ * buffers in flight.  Pinned caller buffers (gsl_scattered_cuda_host_alloc, cudaHostRegister) are
+ * used in place.  Pageable ones (plain malloc, as the reference's gsl_matrix / gsl_vector hold)
+ * would make every cudaMemcpyAsync synchronous and staged by the driver through one small bounce
+ * buffer; they are moved through the context's own pinned staging by a few host threads instead,
+ * copy-in of chunk k+1 and copy-out of chunk k-1 overlapping the GPU work on chunk k. */
 int
 eval_host_slice(const gsl_scattered_cuda *w, replica *r, const double *xq, const double *yq,
                 const raster_spec *ras, size_t nq, double *zq, size_t ld, int *leaf,
                 unsigned *outside_before_after)
 {
-  std::lock_guard<std::mutex> lock(r->mu);
   CU(cudaSetDevice(r->dev));
+  ctx_lease lease(r, nullptr);
+  if (lease.status) return lease.status;
+  eval_ctx *c = lease.c;
   const size_t F = w->n_fields;
   size_t C = std::max<size_t>(1, std::min(w->host_chunk, nq));
   if (ras) C = std::max<size_t>(1, w->host_chunk / ras->ny) * ras->ny; /* whole columns */
   if (C > nq) C = nq;
-  int s = ensure_stage(r, C, F);
+  int s = ensure_stage(c, C, F);
   if (s) return s;
+  const bool staged = nq >= w->pageable_min
+                      && ((!ras && (is_pageable(xq) || is_pageable(yq))) || is_pageable(zq) || is_pageable(leaf));
+  if (staged && (s = ensure_host_stage(c, C, F))) return s;
   unsigned c0[GSI_CNT_WORDS], c1[GSI_CNT_WORDS];
-  if ((s = read_counters(r, c0))) return s;
+  CU(cudaStreamSynchronize(c->s_k));
+  if ((s = read_counters(c, c0))) return s;
+  auto copy_out = [&](size_t k) { /* staged mode: pinned staging -> caller arrays of chunk k */
+    const size_t off = k * C, n = std::min(C, nq - off);
+    host_stage &h = c->hs[k & 1];
+    std::vector<std::pair<void *, const void *>> jobs;
+    std::vector<size_t> bytes;
+    if (leaf) { jobs.emplace_back(leaf + off, h.leaf); bytes.push_back(n * sizeof(int)); }
+    if (zq)
+      for (size_t f = 0; f < F; f++) { jobs.emplace_back(zq + f * ld + off, h.z + f * C); bytes.push_back(n * sizeof(double)); }
+    parallel_copy(w->copy_threads, jobs, bytes);
+  };
   size_t k = 0;
   for (size_t off = 0; off < nq; off += C, k++)
     {
       const size_t n = std::min(C, nq - off);
-      stage_buf &b = r->st[k & 1];
+      stage_buf &b = c->st[k & 1];
+      host_stage &h = c->hs[k & 1];
       if (!ras)
         {
-          if (k >= 2) CU(cudaStreamWaitEvent(r->s_in, b.ev_k, 0));
-          CU(cudaMemcpyAsync(b.x, xq + off, n * sizeof(double), cudaMemcpyHostToDevice, r->s_in));
-          CU(cudaMemcpyAsync(b.y, yq + off, n * sizeof(double), cudaMemcpyHostToDevice, r->s_in));
-          CU(cudaEventRecord(b.ev_in, r->s_in));
-          CU(cudaStreamWaitEvent(r->s_k, b.ev_in, 0));
+          const double *sx = xq + off, *sy = yq + off;
+          if (staged)
+            {
+              /* h was drained by copy_out(k - 2) in the previous iteration */
+              parallel_copy(w->copy_threads, {{h.x, sx}, {h.y, sy}}, {n * sizeof(double), n * sizeof(double)});
+              sx = h.x;
+              sy = h.y;
+            }
+          if (k >= 2) CU(cudaStreamWaitEvent(c->s_in, b.ev_k, 0));
+          CU(cudaMemcpyAsync(b.x, sx, n * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+          CU(cudaMemcpyAsync(b.y, sy, n * sizeof(double), cudaMemcpyHostToDevice, c->s_in));
+          CU(cudaEventRecord(b.ev_in, c->s_in));
+          CU(cudaStreamWaitEvent(c->s_k, b.ev_in, 0));
         }
-      if (k >= 2) CU(cudaStreamWaitEvent(r->s_k, b.ev_out, 0));
+      if (k >= 2) CU(cudaStreamWaitEvent(c->s_k, b.ev_out, 0));
       raster_spec rs;
       if (ras)
         {
@@ -612,22 +863,38 @@ eval_host_slice(const gsl_scattered_cuda *w, replica *r, const double *xq, const
           rs.i_first += off / ras->ny;
           rs.n_cols = n / ras->ny;
         }
-      s = eval_on_device(w, r, b.x, b.y, ras ? &rs : nullptr, n, zq ? b.z : nullptr, C,
-                         leaf ? b.leaf : nullptr, r->s_k);
+      s = eval_on_device(w, r, c, b.x, b.y, ras ? &rs : nullptr, n, zq ? b.z : nullptr, C,
+                         leaf ? b.leaf : nullptr, c->s_k);
       if (s) return s;
-      CU(cudaEventRecord(b.ev_k, r->s_k));
-      CU(cudaStreamWaitEvent(r->s_out, b.ev_k, 0));
-      if (leaf)
-        CU(cudaMemcpyAsync(leaf + off, b.leaf, n * sizeof(int), cudaMemcpyDeviceToHost, r->s_out));
-      if (zq)
-        for (size_t f = 0; f < F; f++)
-          CU(cudaMemcpyAsync(zq + f * ld + off, b.z + f * C, n * sizeof(double),
-                             cudaMemcpyDeviceToHost, r->s_out));
-      CU(cudaEventRecord(b.ev_out, r->s_out));
+      CU(cudaEventRecord(b.ev_k, c->s_k));
+      CU(cudaStreamWaitEvent(c->s_out, b.ev_k, 0));
+      if (staged)
+        {
+          if (leaf) CU(cudaMemcpyAsync(h.leaf, b.leaf, n * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
+          if (zq) CU(cudaMemcpyAsync(h.z, b.z, ((F - 1) * C + n) * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+          CU(cudaEventRecord(b.ev_out, c->s_out));
+          CU(cudaEventRecord(h.ev_out, c->s_out));
+          if (k >= 1)
+            {
+              CU(cudaEventSynchronize(c->hs[(k - 1) & 1].ev_out));
+              copy_out(k - 1);
+            }
+        }
+      else
+        {
+          if (leaf)
+            CU(cudaMemcpyAsync(leaf + off, b.leaf, n * sizeof(int), cudaMemcpyDeviceToHost, c->s_out));
+          if (zq)
+            for (size_t f = 0; f < F; f++)
+              CU(cudaMemcpyAsync(zq + f * ld + off, b.z + f * C, n * sizeof(double),
+                                 cudaMemcpyDeviceToHost, c->s_out));
+          CU(cudaEventRecord(b.ev_out, c->s_out));
+        }
     }
-  CU(cudaStreamSynchronize(r->s_out));
-  CU(cudaStreamSynchronize(r->s_k));
-  if ((s = read_counters(r, c1))) return s;
+  CU(cudaStreamSynchronize(c->s_out));
+  CU(cudaStreamSynchronize(c->s_k));
+  if (staged && k >= 1) copy_out(k - 1);
+  if ((s = read_counters(c, c1))) return s;
   *outside_before_after = c1[GSI_CNT_OUTSIDE] - c0[GSI_CNT_OUTSIDE];
   return 0;
 }
@@ -639,32 +906,45 @@ eval_host(const gsl_scattered_cuda *w, const double *xq, const double *yq, const
   if (!w || !w->uploaded || w->reps.empty())
     GSI_ERROR("workspace not initialised on a GPU", GSL_SCATTERED_EFAILED);
   if (nq == 0) return GSL_SCATTERED_SUCCESS;
+  device_guard restore;
   const size_t R = w->reps.size();
   std::vector<int> status(R, 0);
   std::vector<unsigned> outside(R, 0);
   auto run = [&](size_t i) {
-    size_t q0 = nq * i / R, q1 = nq * (i + 1) / R;
-    raster_spec rs;
-    if (ras)
+    try
       {
-        /* split a raster by whole columns */
-        const size_t c0 = ras->n_cols * i / R, c1 = ras->n_cols * (i + 1) / R;
-        rs = *ras;
-        rs.i_first += c0;
-        rs.n_cols = c1 - c0;
-        q0 = c0 * ras->ny;
-        q1 = c1 * ras->ny;
+        size_t q0 = nq * i / R, q1 = nq * (i + 1) / R;
+        raster_spec rs;
+        if (ras)
+          {
+            /* split a raster by whole columns */
+            const size_t c0 = ras->n_cols * i / R, c1 = ras->n_cols * (i + 1) / R;
+            rs = *ras;
+            rs.i_first += c0;
+            rs.n_cols = c1 - c0;
+            q0 = c0 * ras->ny;
+            q1 = c1 * ras->ny;
+          }
+        status[i] = eval_host_slice(w, w->reps[i], ras ? nullptr : xq + q0, ras ? nullptr : yq + q0,
+                                    ras ? &rs : nullptr, q1 - q0, zq ? zq + q0 : nullptr, nq,
+                                    leaf ? leaf + q0 : nullptr, &outside[i]);
       }
-    status[i] = eval_host_slice(w, w->reps[i], ras ? nullptr : xq + q0, ras ? nullptr : yq + q0,
-                                ras ? &rs : nullptr, q1 - q0, zq ? zq + q0 : nullptr, nq,
-                                leaf ? leaf + q0 : nullptr, &outside[i]);
+    catch (const std::bad_alloc &)
+      {
+        status[i] = report("out of host memory", __FILE__, __LINE__, GSL_SCATTERED_ENOMEM);
+      }
+    catch (...)
+      {
+        status[i] = report("internal error (C++ exception)", __FILE__, __LINE__, GSL_SCATTERED_EFAILED);
+      }
   };
   if (R == 1)
     run(0);
   else
     {
       std::vector<std::thread> th;
-      for (size_t i = 0; i < R; i++) th.emplace_back(run, i);
+      for (size_t i = 1; i < R; i++) th.emplace_back(run, i);
+      run(0);
       for (auto &t : th) t.join();
     }
   unsigned long long out_total = 0;
@@ -685,10 +965,11 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     GSI_ERROR("no CUDA device available: libgsl_scattered_cuda has no CPU evaluation path",
               GSL_SCATTERED_EFAILED);
+  device_guard restore;
   drop_replicas(w);
   std::memcpy(&w->hdr, image.data(), sizeof w->hdr);
   std::vector<int> devs = w->devs;
-  if (devs.empty()) devs.push_back(0);
+  if (devs.empty()) devs.push_back(restore.prev >= 0 ? restore.prev : 0);
   for (int d : devs)
     if (d < 0 || d >= ndev) GSI_ERROR("device id out of range", GSL_SCATTERED_EINVAL);
   for (int d : devs)
@@ -704,17 +985,20 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
     }
   replica *r0 = w->reps[0];
   CU(cudaSetDevice(r0->dev));
-  CU(cudaMemcpyAsync(r0->slab, image.data(), image.size(), cudaMemcpyHostToDevice, r0->s_k));
-  CU(gsi_launch_entry_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_entry), r0->sm_count, r0->s_k));
-  CU(gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->sm_count,
-                           r0->s_k));
-  CU(cudaStreamSynchronize(r0->s_k));
-  for (size_t i = 1; i < w->reps.size(); i++)
+  cudaStream_t st = nullptr;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaError_t e = cudaMemcpyAsync(r0->slab, image.data(), image.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = gsi_launch_entry_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_entry), r0->sm_count, st);
+  if (e == cudaSuccess) e = gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->sm_count, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  for (size_t i = 1; e == cudaSuccess && i < w->reps.size(); i++)
     {
       replica *r = w->reps[i];
-      CU(cudaMemcpyPeerAsync(r->slab, r->dev, r0->slab, r0->dev, w->hdr.total_bytes, r0->s_k));
+      e = cudaMemcpyPeerAsync(r->slab, r->dev, r0->slab, r0->dev, w->hdr.total_bytes, st);
     }
-  CU(cudaStreamSynchronize(r0->s_k));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  CU(e);
   w->uploaded = true;
   return 0;
 }
@@ -735,6 +1019,15 @@ slab_checksum(const char *image, size_t bytes)
   return hsh;
 }
 
+/* a + b*c without wrapping: false on overflow */
+bool
+extent_ok(uint64_t off, uint64_t count, uint64_t elem, uint64_t total)
+{
+  if (off > total) return false;
+  if (elem && count > (total - off) / elem) return false;
+  return true;
+}
+
 /* take over a complete slab image (device or host memory; the seed grid is part of it) */
 int
 adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, size_t bytes)
@@ -742,25 +1035,23 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
   if (h.magic != GSI_SLAB_MAGIC || h.version != GSI_SLAB_VERSION || h.total_bytes != bytes)
     GSI_ERROR("slab header mismatch", GSL_SCATTERED_EINVAL);
   if (h.n_fields != w->n_fields) GSI_ERROR("n_fields differs from alloc", GSL_SCATTERED_EBADLEN);
-  if (h.off_dag >= bytes || h.off_leaf >= bytes || h.off_z >= bytes || h.off_seeds >= bytes
-      || h.n_dag == 0 || h.grid_g == 0
-      || h.off_dag + h.n_dag * sizeof(gsi_rec) > bytes
-      || h.off_leaf + h.n_leaves * (uint64_t) h.leaf_stride > bytes
-      || h.off_seeds + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes
-      || h.off_entry >= bytes || h.off_entry + (uint64_t) h.grid_g * h.grid_g * sizeof(int32_t) > bytes
-      || h.tile_bits < 1 || h.tile_bits > 12 || h.off_tiles >= bytes
-      || h.off_tiles + (((uint64_t) 1 << h.tile_bits) + 1) * sizeof(int32_t) > bytes)
+  const uint64_t cells = (uint64_t) h.grid_g * h.grid_g;
+  if (h.n_dag == 0 || h.grid_g == 0 || h.grid_g > 32768 || h.n_dag > 0x7fffffffull || h.n_leaves > 0x7fffffffull
+      || h.n_leaves > h.n_dag || (h.leaf_stride != 96 && h.leaf_stride != 128) || h.tile_bits < 1 || h.tile_bits > 12
+      || !extent_ok(h.off_dag, h.n_dag, sizeof(gsi_rec), bytes)
+      || !extent_ok(h.off_leaf, h.n_leaves, h.leaf_stride, bytes)
+      || !extent_ok(h.off_z, std::max<uint64_t>(1, h.n_points), (uint64_t) h.n_fields * sizeof(double), bytes)
+      || !extent_ok(h.off_seeds, cells, sizeof(int32_t), bytes) || !extent_ok(h.off_entry, cells, sizeof(int32_t), bytes)
+      || !extent_ok(h.off_tiles, ((uint64_t) 1 << h.tile_bits) + 1, sizeof(int32_t), bytes)
+      || (h.off_dag | h.off_leaf | h.off_z | h.off_seeds | h.off_entry | h.off_tiles) % 32 != 0
+      || !(h.inv_du > 0) || !(h.inv_dv > 0) || !(h.delta > 0))
     GSI_ERROR("slab sections out of range", GSL_SCATTERED_EINVAL);
+  device_guard restore;
   drop_replicas(w);
   w->built = false;
   w->hdr = h;
   std::vector<int> devs = w->devs;
-  if (devs.empty())
-    {
-      int cur = 0;
-      CU(cudaGetDevice(&cur));
-      devs.push_back(cur);
-    }
+  if (devs.empty()) devs.push_back(restore.prev >= 0 ? restore.prev : 0);
   for (int d : devs)
     {
       replica *r = nullptr;
@@ -772,6 +1063,20 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       r->view = gsi_view_of(r->slab, &w->hdr);
       if (!w->exact_entry) r->view.entry = nullptr;
       CU(cudaMemcpy(r->slab, src, bytes, cudaMemcpyDefault));
+      /* links, neighbour slots, seeds, entry nodes and tile boundaries must stay inside their
+         sections: one pass on the device before any evaluation kernel trusts them */
+      unsigned long long *bad = nullptr;
+      CU(cudaMalloc(&bad, sizeof *bad));
+      cudaError_t e = gsi_launch_validate_slab(r->view, bad, r->sm_count, nullptr);
+      unsigned long long n_bad = 0;
+      if (e == cudaSuccess) e = cudaMemcpy(&n_bad, bad, sizeof n_bad, cudaMemcpyDeviceToHost);
+      cudaFree(bad);
+      CU(e);
+      if (n_bad)
+        {
+          drop_replicas(w);
+          GSI_ERROR("slab image holds out-of-range links", GSL_SCATTERED_EINVAL);
+        }
     }
   w->uploaded = true;
   return GSL_SCATTERED_SUCCESS;
@@ -786,7 +1091,7 @@ extern "C" {
 const char *
 gsl_scattered_cuda_version(void)
 {
-  return "gsl_scattered_cuda 0.1 (sm_100a)";
+  return "gsl_scattered_cuda 0.2 (sm_100a)";
 }
 
 gsl_scattered_cuda_error_handler_t *
@@ -814,8 +1119,15 @@ gsl_scattered_cuda_alloc(size_t n_nodes, size_t n_fields)
 {
   if (n_fields == 0) GSI_ERROR_NULL("n_fields must be positive", GSL_SCATTERED_EINVAL);
   if (n_nodes > (size_t) 200000000) GSI_ERROR_NULL("n_nodes too large", GSL_SCATTERED_EINVAL);
-  gsl_scattered_cuda *w = new (std::nothrow) gsl_scattered_cuda();
-  if (!w) GSI_ERROR_NULL("failed to allocate workspace", GSL_SCATTERED_ENOMEM);
+  gsl_scattered_cuda *w = nullptr;
+  try
+    {
+      w = new gsl_scattered_cuda();
+    }
+  catch (...)
+    {
+      GSI_ERROR_NULL("failed to allocate workspace", GSL_SCATTERED_ENOMEM);
+    }
   w->n_cap = n_nodes;
   w->n_fields = n_fields;
   std::memset(&w->hdr, 0, sizeof w->hdr);
@@ -826,7 +1138,10 @@ void
 gsl_scattered_cuda_free(gsl_scattered_cuda *w)
 {
   if (!w) return;
-  drop_replicas(w);
+  {
+    device_guard restore;
+    drop_replicas(w);
+  }
   delete w;
 }
 
@@ -835,18 +1150,21 @@ gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_t nd
 {
   if (!w || (ndev && !dev)) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
   if (w->uploaded) GSI_ERROR("set_devices must precede init/upload", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
   std::vector<int> d(dev, dev + ndev);
   for (size_t i = 0; i < d.size(); i++)
     for (size_t j = i + 1; j < d.size(); j++)
       if (d[i] == d[j]) GSI_ERROR("duplicate device id", GSL_SCATTERED_EINVAL);
   w->devs = d;
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
 gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double value)
 {
   if (!w || !name) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
   const std::string k(name);
   if (k == "cells_per_leaf" && value > 0) w->fprm.cells_per_leaf = value;
   else if (k == "grid_g" && value >= 0 && value <= 32768) w->fprm.grid_g = (uint32_t) value;
@@ -867,12 +1185,15 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "reorder" && (value == 0 || value == 1 || value == 2)) w->reorder = (int) value;
   else if (k == "reorder_window" && value >= 32) w->reorder_window = (size_t) value;
   else if (k == "reorder_min" && value >= 0) w->reorder_min = (size_t) value;
+  else if (k == "reorder_min_leaves" && value >= 0) w->reorder_min_leaves = (size_t) value;
   else if (k == "reorder_chunk" && value >= 32 && value <= GSI_BIN_CHUNK_MAX) w->reorder_chunk = (int) value;
   else if (k == "reorder_max_fields" && value >= 0) w->reorder_max_fields = (size_t) value;
-  else if (k == "tile_ranges" && value >= 1 && value <= 64) w->tile_ranges = (int) value;
+  else if (k == "tile_ranges" && value >= 0 && value <= 64) w->tile_ranges = (int) value;
+  else if (k == "tile_threads" && value >= 32 && value <= GSI_TILE_THREADS) w->tile_threads = (int) value;
   else if (k == "tile_leaves" && value >= 1) w->fprm.tile_leaves = (uint32_t) value;
-  else if (k == "tile_smem" && (value == 0 || value == 1)) w->tile_smem = (int) value;
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
+  else if (k == "copy_threads" && value >= 1 && value <= 64) w->copy_threads = (int) value;
+  else if (k == "pageable_min" && value >= 0) w->pageable_min = (size_t) value;
   else if (k == "exact_entry" && (value == 0 || value == 1))
     {
       w->exact_entry = (int) value;
@@ -881,16 +1202,19 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
     }
   else GSI_ERROR("unknown parameter or value out of range", GSL_SCATTERED_EINVAL);
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
 gsl_scattered_cuda_shuffle_mt19937(unsigned long seed, size_t n, size_t order[])
 {
   if (n && !order) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
   std::vector<int64_t> o(n);
   gsi_shuffle_mt19937(seed, n, o.data());
   for (size_t i = 0; i < n; i++) order[i] = (size_t) o[i];
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
@@ -901,7 +1225,11 @@ gsl_scattered_cuda_build(gsl_scattered_cuda *w, const double xa[], const double 
   if (n_nodes && (!xa || !ya)) GSI_ERROR("null coordinate array", GSL_SCATTERED_EINVAL);
   /* simplex_tree_init returns GSL_FAILURE when the tree has no room, linear_simplex.c:274-278 */
   if (n_nodes > w->n_cap) GSI_ERROR("more nodes than the workspace was allocated for", GSL_SCATTERED_EBADLEN);
-  drop_replicas(w);
+  GSI_GUARD_BEGIN
+  {
+    device_guard restore;
+    drop_replicas(w);
+  }
   w->built = false;
   w->xa.assign(xa, xa + n_nodes);
   w->ya.assign(ya, ya + n_nodes);
@@ -917,6 +1245,7 @@ gsl_scattered_cuda_build(gsl_scattered_cuda *w, const double xa[], const double 
   if (s) GSI_ERROR(err.empty() ? "triangulation build failed" : err.c_str(), s);
   w->built = true;
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
@@ -929,6 +1258,7 @@ gsl_scattered_cuda_upload(gsl_scattered_cuda *w, const double za[], size_t n_fie
   if (gsl_scattered_cuda_device_count() <= 0)
     GSI_ERROR("no CUDA device available: libgsl_scattered_cuda has no CPU evaluation path",
               GSL_SCATTERED_EFAILED);
+  GSI_GUARD_BEGIN
   double t0 = now_s();
   std::vector<char> image;
   std::string err;
@@ -939,6 +1269,7 @@ gsl_scattered_cuda_upload(gsl_scattered_cuda *w, const double za[], size_t n_fie
   s = install_image(w, image);
   w->upload_seconds = now_s() - t0;
   return s;
+  GSI_GUARD_END
 }
 
 int
@@ -964,16 +1295,12 @@ gsl_scattered_cuda_init_from_tree(gsl_scattered_cuda *w, size_t n_simplexes, con
     GSI_ERROR("null data/shuffle or bad stride", GSL_SCATTERED_EINVAL);
   if (n_nodes > w->n_cap) GSI_ERROR("more nodes than the workspace was allocated for", GSL_SCATTERED_EBADLEN);
   if (n_fields != w->n_fields) GSI_ERROR("n_fields differs from alloc", GSL_SCATTERED_EBADLEN);
-  drop_replicas(w);
-  gsi_host_tree &t = w->tree;
-  t.n_points = n_nodes;
-  t.pts.assign(pts3, pts3 + 3 * n_simplexes);
-  t.lnk.assign(lnk3, lnk3 + 3 * n_simplexes);
-  t.type.resize(n_simplexes);
+  if (n_simplexes > (size_t) 0x7fffffff) GSI_ERROR("too many simplexes", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
+  /* validate everything before touching the workspace: a failed call leaves it as it was */
   for (size_t i = 0; i < n_simplexes; i++)
     {
       if (type[i] < 0 || type[i] > 3) GSI_ERROR("bad node type", GSL_SCATTERED_EINVAL);
-      t.type[i] = (uint8_t) type[i];
       for (int k = 0; k < 3; k++)
         {
           const int p = pts3[3 * i + k], l = lnk3[3 * i + k];
@@ -981,12 +1308,30 @@ gsl_scattered_cuda_init_from_tree(gsl_scattered_cuda *w, size_t n_simplexes, con
           if (l < 0 || (size_t) l >= n_simplexes) GSI_ERROR("link out of range", GSL_SCATTERED_EINVAL);
         }
     }
+  {
+    std::vector<bool> seen(n_nodes, false);
+    for (size_t i = 0; i < n_nodes; i++)
+      {
+        if (shuffle[i] >= n_nodes || seen[shuffle[i]]) GSI_ERROR("shuffle is not a permutation", GSL_SCATTERED_EINVAL);
+        seen[shuffle[i]] = true;
+      }
+  }
+  {
+    device_guard restore;
+    drop_replicas(w);
+  }
+  w->built = false;
+  gsi_host_tree &t = w->tree;
+  t.n_points = n_nodes;
+  t.pts.assign(pts3, pts3 + 3 * n_simplexes);
+  t.lnk.assign(lnk3, lnk3 + 3 * n_simplexes);
+  t.type.resize(n_simplexes);
+  for (size_t i = 0; i < n_simplexes; i++) t.type[i] = (uint8_t) type[i];
   t.shuffle.resize(n_nodes);
   w->xa.resize(n_nodes);
   w->ya.resize(n_nodes);
   for (size_t i = 0; i < n_nodes; i++)
     {
-      if (shuffle[i] >= n_nodes) GSI_ERROR("shuffle is not a permutation", GSL_SCATTERED_EINVAL);
       t.shuffle[i] = (int64_t) shuffle[i];
       w->xa[i] = data[i * data_tda];
       w->ya[i] = data[i * data_tda + 1];
@@ -997,6 +1342,7 @@ gsl_scattered_cuda_init_from_tree(gsl_scattered_cuda *w, size_t n_simplexes, con
   t.build_seconds = 0;
   w->built = true;
   return gsl_scattered_cuda_upload(w, za, n_fields);
+  GSI_GUARD_END
 }
 
 int
@@ -1004,17 +1350,27 @@ gsl_scattered_cuda_eval_e(const gsl_scattered_cuda *w, const double xq[], const 
                           size_t nq, double zq[], int leaf[])
 {
   if (nq && (!xq || !yq)) GSI_ERROR("null query array", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
   return eval_host(w, xq, yq, nullptr, nq, zq, leaf);
+  GSI_GUARD_END
 }
 
 double
 gsl_scattered_cuda_eval(const gsl_scattered_cuda *w, double x, double y)
 {
-  std::vector<double> z(w ? w->n_fields : 1, std::numeric_limits<double>::quiet_NaN());
-  const int s = eval_host(w, &x, &y, nullptr, 1, z.data(), nullptr);
-  if (s != GSL_SCATTERED_SUCCESS && s != GSL_SCATTERED_EDOM)
-    return std::numeric_limits<double>::quiet_NaN();
-  return z[0];
+  try
+    {
+      std::vector<double> z(w ? w->n_fields : 1, std::numeric_limits<double>::quiet_NaN());
+      const int s = eval_host(w, &x, &y, nullptr, 1, z.data(), nullptr);
+      if (s != GSL_SCATTERED_SUCCESS && s != GSL_SCATTERED_EDOM)
+        return std::numeric_limits<double>::quiet_NaN();
+      return z[0];
+    }
+  catch (...)
+    {
+      report("internal error (C++ exception)", __FILE__, __LINE__, GSL_SCATTERED_EFAILED);
+      return std::numeric_limits<double>::quiet_NaN();
+    }
 }
 
 int
@@ -1023,8 +1379,11 @@ gsl_scattered_cuda_eval_raster_e(const gsl_scattered_cuda *w, double x0, double 
 {
   if (nx && ny && nx > std::numeric_limits<size_t>::max() / ny)
     GSI_ERROR("raster too large", GSL_SCATTERED_EINVAL);
+  if (nx == 0 || ny == 0) return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_BEGIN
   raster_spec rs{x0, dx, y0, dy, ny, 0, nx};
   return eval_host(w, nullptr, nullptr, &rs, nx * ny, zq, leaf);
+  GSI_GUARD_END
 }
 
 int
@@ -1037,22 +1396,31 @@ gsl_scattered_cuda_eval_device_e(const gsl_scattered_cuda *w, int dev, const dou
   if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
   if (nq && (!d_xq || !d_yq)) GSI_ERROR("null query array", GSL_SCATTERED_EINVAL);
   if (d_zq && ld < nq) GSI_ERROR("ld < nq", GSL_SCATTERED_EBADLEN);
-  std::lock_guard<std::mutex> lock(r->mu);
+  if (nq == 0) return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_BEGIN
+  device_guard restore;
   CU(cudaSetDevice(dev));
-  cudaStream_t st = stream ? (cudaStream_t) stream : r->s_k;
+  ctx_lease lease(r, (cudaStream_t) stream);
+  if (lease.status) return lease.status;
+  eval_ctx *c = lease.c;
   unsigned c0[GSI_CNT_WORDS], c1[GSI_CNT_WORDS];
   int s;
-  if (!stream && (s = read_counters(r, c0))) return s;
-  s = eval_on_device(w, r, d_xq, d_yq, nullptr, nq, d_zq, ld, d_leaf, st);
+  if (!stream)
+    {
+      CU(cudaStreamSynchronize(lease.st));
+      if ((s = read_counters(c, c0))) return s;
+    }
+  s = eval_on_device(w, r, c, d_xq, d_yq, nullptr, nq, d_zq, ld, d_leaf, lease.st);
   if (s) return s;
   if (!stream)
     {
-      CU(cudaStreamSynchronize(st));
-      if ((s = read_counters(r, c1))) return s;
+      CU(cudaStreamSynchronize(lease.st));
+      if ((s = read_counters(c, c1))) return s;
       if (c1[GSI_CNT_OUTSIDE] != c0[GSI_CNT_OUTSIDE])
         GSI_ERROR("query point outside the domain (cage)", GSL_SCATTERED_EDOM);
     }
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
@@ -1063,29 +1431,41 @@ gsl_scattered_cuda_eval_raster_device_e(const gsl_scattered_cuda *w, int dev, do
   if (!w || !w->uploaded) GSI_ERROR("workspace not initialised on a GPU", GSL_SCATTERED_EFAILED);
   replica *r = find_replica(w, dev);
   if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
-  std::lock_guard<std::mutex> lock(r->mu);
+  if (nx && ny && nx > std::numeric_limits<size_t>::max() / ny)
+    GSI_ERROR("raster too large", GSL_SCATTERED_EINVAL);
+  if (nx == 0 || ny == 0) return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_BEGIN
+  device_guard restore;
   CU(cudaSetDevice(dev));
-  cudaStream_t st = stream ? (cudaStream_t) stream : r->s_k;
+  ctx_lease lease(r, (cudaStream_t) stream);
+  if (lease.status) return lease.status;
+  eval_ctx *c = lease.c;
   raster_spec rs{x0, dx, y0, dy, ny, 0, nx};
   unsigned c0[GSI_CNT_WORDS], c1[GSI_CNT_WORDS];
   int s;
-  if (!stream && (s = read_counters(r, c0))) return s;
-  s = eval_on_device(w, r, nullptr, nullptr, &rs, nx * ny, d_zq, nx * ny, d_leaf, st);
+  if (!stream)
+    {
+      CU(cudaStreamSynchronize(lease.st));
+      if ((s = read_counters(c, c0))) return s;
+    }
+  s = eval_on_device(w, r, c, nullptr, nullptr, &rs, nx * ny, d_zq, nx * ny, d_leaf, lease.st);
   if (s) return s;
   if (!stream)
     {
-      CU(cudaStreamSynchronize(st));
-      if ((s = read_counters(r, c1))) return s;
+      CU(cudaStreamSynchronize(lease.st));
+      if ((s = read_counters(c, c1))) return s;
       if (c1[GSI_CNT_OUTSIDE] != c0[GSI_CNT_OUTSIDE])
         GSI_ERROR("query point outside the domain (cage)", GSL_SCATTERED_EDOM);
     }
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
 gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info *info)
 {
   if (!w || !info) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
   std::memset(info, 0, sizeof *info);
   info->n_nodes = w->built ? w->tree.n_points : (size_t) w->hdr.n_points;
   info->n_fields = w->n_fields;
@@ -1097,63 +1477,75 @@ gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info
   info->build_seconds = w->tree.build_seconds;
   info->flatten_seconds = w->flatten_seconds;
   info->upload_seconds = w->upload_seconds;
+  device_guard restore;
   for (replica *r : w->reps)
     {
-      unsigned c[GSI_CNT_WORDS];
-      std::lock_guard<std::mutex> lock(r->mu);
       CU(cudaSetDevice(r->dev));
-      CU(cudaStreamSynchronize(r->s_k));
-      const int s = read_counters(r, c);
-      if (s) return s;
-      unsigned long long u;
-      std::memcpy(&u, c + GSI_CNT_DEFERRED_TOTAL, 8);
-      info->n_deferred += u;
-      std::memcpy(&u, c + GSI_CNT_STEPS, 8);
-      info->n_steps += u;
-      info->n_outside += c[GSI_CNT_OUTSIDE];
-      /* fold finished profiling events into the running totals */
-      for (auto &p : r->prof_locate)
+      CU(cudaDeviceSynchronize()); /* every context's counters and profiling events are final */
+      std::lock_guard<std::mutex> lock(r->mu);
+      info->n_contexts += r->ctxs.size();
+      for (eval_ctx *c : r->ctxs)
         {
-          float ms = 0;
-          if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) r->locate_seconds += 1e-3 * ms;
-          cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+          unsigned cn[GSI_CNT_WORDS];
+          const int s = read_counters(c, cn);
+          if (s) return s;
+          unsigned long long u;
+          std::memcpy(&u, cn + GSI_CNT_DEFERRED_TOTAL, 8);
+          info->n_deferred += u;
+          std::memcpy(&u, cn + GSI_CNT_STEPS, 8);
+          info->n_steps += u;
+          info->n_outside += cn[GSI_CNT_OUTSIDE];
+          /* fold finished profiling events into the running totals */
+          for (auto &p : c->prof_locate)
+            {
+              float ms = 0;
+              if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) c->locate_seconds += 1e-3 * ms;
+              cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+            }
+          for (auto &p : c->prof_exact)
+            {
+              float ms = 0;
+              if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) c->exact_seconds += 1e-3 * ms;
+              cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+            }
+          c->prof_locate.clear();
+          c->prof_exact.clear();
+          cudaGetLastError();
+          info->locate_seconds += c->locate_seconds;
+          info->exact_seconds += c->exact_seconds;
+          info->n_kernel_launches += c->n_launches;
+          info->n_reordered += c->n_reordered;
         }
-      for (auto &p : r->prof_exact)
-        {
-          float ms = 0;
-          if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) r->exact_seconds += 1e-3 * ms;
-          cudaEventDestroy(p.first); cudaEventDestroy(p.second);
-        }
-      r->prof_locate.clear();
-      r->prof_exact.clear();
-      cudaGetLastError();
-      info->locate_seconds += r->locate_seconds;
-      info->exact_seconds += r->exact_seconds;
-      info->n_kernel_launches += r->n_launches;
-      info->n_reordered += r->n_reordered;
     }
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
 gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w)
 {
   if (!w) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
+  device_guard restore;
   for (replica *r : w->reps)
     {
-      std::lock_guard<std::mutex> lock(r->mu);
       CU(cudaSetDevice(r->dev));
-      CU(cudaMemsetAsync(r->counters, 0, GSI_CNT_WORDS * sizeof(unsigned), r->s_k));
-      CU(cudaStreamSynchronize(r->s_k));
-      for (auto &p : r->prof_locate) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-      for (auto &p : r->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-      r->prof_locate.clear();
-      r->prof_exact.clear();
-      r->locate_seconds = r->exact_seconds = 0;
-      r->n_launches = 0;
-      r->n_reordered = 0;
+      CU(cudaDeviceSynchronize());
+      std::lock_guard<std::mutex> lock(r->mu);
+      for (eval_ctx *c : r->ctxs)
+        {
+          CU(cudaMemset(c->counters, 0, GSI_CNT_WORDS * sizeof(unsigned)));
+          for (auto &p : c->prof_locate) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+          for (auto &p : c->prof_exact) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+          c->prof_locate.clear();
+          c->prof_exact.clear();
+          c->locate_seconds = c->exact_seconds = 0;
+          c->n_launches = 0;
+          c->n_reordered = 0;
+        }
     }
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
@@ -1189,10 +1581,11 @@ gsl_scattered_cuda_slab_export_device(const gsl_scattered_cuda *w, int dev, void
   if (!w || !w->uploaded || !d_dst) GSI_ERROR("nothing to export", GSL_SCATTERED_EINVAL);
   replica *r = find_replica(w, dev);
   if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
+  device_guard restore;
   CU(cudaSetDevice(dev));
-  cudaStream_t st = stream ? (cudaStream_t) stream : r->s_k;
-  CU(cudaMemcpyAsync(d_dst, r->slab, w->hdr.total_bytes, cudaMemcpyDeviceToDevice, st));
-  if (!stream) CU(cudaStreamSynchronize(st));
+  /* the slab is immutable after init: any stream may read it */
+  CU(cudaMemcpyAsync(d_dst, r->slab, w->hdr.total_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t) stream));
+  if (!stream) CU(cudaStreamSynchronize(nullptr));
   return GSL_SCATTERED_SUCCESS;
 }
 
@@ -1202,9 +1595,11 @@ gsl_scattered_cuda_init_from_slab_device(gsl_scattered_cuda *w, const void *d_sr
   if (!w || !d_src || bytes < sizeof(gsi_slab_header)) GSI_ERROR("bad slab", GSL_SCATTERED_EINVAL);
   if (gsl_scattered_cuda_device_count() <= 0)
     GSI_ERROR("no CUDA device available", GSL_SCATTERED_EFAILED);
+  GSI_GUARD_BEGIN
   gsi_slab_header h;
   CU(cudaMemcpy(&h, d_src, sizeof h, cudaMemcpyDefault));
   return adopt_slab(w, h, d_src, bytes);
+  GSI_GUARD_END
 }
 
 int
@@ -1212,20 +1607,12 @@ gsl_scattered_cuda_fwrite(FILE *stream, const gsl_scattered_cuda *w)
 {
   if (!stream || !w) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
   if (!w->uploaded || w->reps.empty()) GSI_ERROR("nothing to write: workspace not initialised", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
   replica *r = w->reps[0];
-  std::vector<char> image;
-  try
-    {
-      image.resize((size_t) w->hdr.total_bytes);
-    }
-  catch (const std::bad_alloc &)
-    {
-      GSI_ERROR("out of host memory for the slab image", GSL_SCATTERED_ENOMEM);
-    }
+  std::vector<char> image((size_t) w->hdr.total_bytes);
   {
-    std::lock_guard<std::mutex> lock(r->mu);
+    device_guard restore;
     CU(cudaSetDevice(r->dev));
-    CU(cudaStreamSynchronize(r->s_k));
     CU(cudaMemcpy(image.data(), r->slab, image.size(), cudaMemcpyDeviceToHost));
   }
   gsi_slab_header h;
@@ -1235,27 +1622,21 @@ gsl_scattered_cuda_fwrite(FILE *stream, const gsl_scattered_cuda *w)
   if (fwrite(image.data(), 1, image.size(), stream) != image.size())
     GSI_ERROR("fwrite failed", GSL_SCATTERED_EFAILED);
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
 gsl_scattered_cuda_fread(FILE *stream, gsl_scattered_cuda *w)
 {
   if (!stream || !w) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
   gsi_slab_header h;
   if (fread(&h, 1, sizeof h, stream) != sizeof h) GSI_ERROR("fread failed", GSL_SCATTERED_EFAILED);
   if (h.magic != GSI_SLAB_MAGIC || h.version != GSI_SLAB_VERSION || h.total_bytes < sizeof h
       || h.total_bytes > ((uint64_t) 1 << 40))
     GSI_ERROR("not a slab image of this library version", GSL_SCATTERED_EINVAL);
   if (h.n_fields != w->n_fields) GSI_ERROR("n_fields differs from alloc", GSL_SCATTERED_EBADLEN);
-  std::vector<char> image;
-  try
-    {
-      image.resize((size_t) h.total_bytes);
-    }
-  catch (const std::bad_alloc &)
-    {
-      GSI_ERROR("out of host memory for the slab image", GSL_SCATTERED_ENOMEM);
-    }
+  std::vector<char> image((size_t) h.total_bytes);
   std::memcpy(image.data(), &h, sizeof h);
   const size_t rest = image.size() - sizeof h;
   if (fread(image.data() + sizeof h, 1, rest, stream) != rest) GSI_ERROR("fread failed", GSL_SCATTERED_EFAILED);
@@ -1265,6 +1646,7 @@ gsl_scattered_cuda_fread(FILE *stream, gsl_scattered_cuda *w)
     GSI_ERROR("no CUDA device available: libgsl_scattered_cuda has no CPU evaluation path",
               GSL_SCATTERED_EFAILED);
   return adopt_slab(w, h, image.data(), image.size());
+  GSI_GUARD_END
 }
 
 int
@@ -1317,8 +1699,9 @@ gsl_scattered_cuda_generate_uniform_device(const gsl_scattered_cuda *w, int dev,
   if (!w || !w->uploaded) GSI_ERROR("workspace not initialised on a GPU", GSL_SCATTERED_EFAILED);
   replica *r = find_replica(w, dev);
   if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
+  device_guard restore;
   CU(cudaSetDevice(dev));
-  cudaStream_t st = stream ? (cudaStream_t) stream : r->s_k;
+  cudaStream_t st = (cudaStream_t) stream;
   CU(gsi_launch_gen_uniform(seed, first, nq, xlo, xhi, ylo, yhi, d_xq, d_yq, r->sm_count, st));
   if (!stream) CU(cudaStreamSynchronize(st));
   return GSL_SCATTERED_SUCCESS;
@@ -1347,13 +1730,16 @@ gsl_scattered_cuda_checksum_device(const gsl_scattered_cuda *w, int dev, const i
   if (!w || !w->uploaded || !out) GSI_ERROR("bad argument", GSL_SCATTERED_EINVAL);
   replica *r = find_replica(w, dev);
   if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
-  std::lock_guard<std::mutex> lock(r->mu);
+  GSI_GUARD_BEGIN
+  device_guard restore;
   CU(cudaSetDevice(dev));
-  cudaStream_t st = stream ? (cudaStream_t) stream : r->s_k;
-  CU(gsi_launch_checksum(d_leaf, d_val, n, r->scratch2, r->sm_count, st));
-  CU(cudaMemcpyAsync(out, r->scratch2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  ctx_lease lease(r, (cudaStream_t) stream);
+  if (lease.status) return lease.status;
+  CU(gsi_launch_checksum(d_leaf, d_val, n, lease.c->scratch2, r->sm_count, lease.st));
+  CU(cudaMemcpyAsync(out, lease.c->scratch2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, lease.st));
+  CU(cudaStreamSynchronize(lease.st));
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 int
@@ -1365,13 +1751,16 @@ gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, const in
   if (!w || !w->uploaded || !out) GSI_ERROR("bad argument", GSL_SCATTERED_EINVAL);
   replica *r = find_replica(w, dev);
   if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
-  std::lock_guard<std::mutex> lock(r->mu);
+  GSI_GUARD_BEGIN
+  device_guard restore;
   CU(cudaSetDevice(dev));
-  cudaStream_t st = stream ? (cudaStream_t) stream : r->s_k;
-  CU(gsi_launch_compare(d_leaf_a, d_leaf_b, d_val_a, d_val_b, n, n_val, r->scratch2, r->sm_count, st));
-  CU(cudaMemcpyAsync(out, r->scratch2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  ctx_lease lease(r, (cudaStream_t) stream);
+  if (lease.status) return lease.status;
+  CU(gsi_launch_compare(d_leaf_a, d_leaf_b, d_val_a, d_val_b, n, n_val, lease.c->scratch2, r->sm_count, lease.st));
+  CU(cudaMemcpyAsync(out, lease.c->scratch2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, lease.st));
+  CU(cudaStreamSynchronize(lease.st));
   return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
 }
 
 } /* extern "C" */

@@ -14,9 +14,10 @@
  *                  edge/vertex tie-breaks, cage leaves, stale-coords quirk.  Runs on the deferred
  *                  list, on grid-cell centres (seeding), or on every query; starts at the cell's
  *                  certified entry node (k_entry_cells).
- *   k_bin -> k_tile_locate -> k_unpermute
- *                  opt-in reorder pipeline for incoherent query arrays (chunk-local counting sort
- *                  by spatial tile, tile-major walk, inverse permutation).
+ *   k_bin -> k_tile_walk -> k_unpermute
+ *                  reorder pipeline for large incoherent query batches on triangulations beyond
+ *                  the L2 (chunk-local counting sort by spatial tile, tile-major walk out of
+ *                  TMA-staged shared memory, inverse permutation).
  *
  * This path is gather/latency bound: no tensor cores, no FMA contraction (gsi_core.h).
  * Measured bounds and the experiments that did not pay off are in DESIGN.md section 4.
@@ -389,24 +390,28 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
     atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
 }
 
-/* ---- reorder pipeline: k_bin -> k_tile_locate -> k_unpermute ---------------------------------
- * Uniformly random queries make every leaf fetch an isolated L2/DRAM access.  The pipeline
- * gives the walk spatial coherence without a global sort and without scattered global writes:
- *   k_bin          one CTA per chunk of <= 8192 consecutive queries: counting sort by spatial
- *                  tile (Morton-key prefix of the query position: the leaf order's own key, so a
- *                  tile's leaves are one contiguous slot range) entirely in shared memory,
- *                  then coalesced stores of the binned coordinates, the 16-bit in-chunk index
- *                  of every binned query and the chunk's run table (start of each tile's run);
- *   k_tile_locate  tile-major: the CTAs of tile t gather t's run from every chunk (32 chunks
- *                  per warp step, lane-parallel prefix over the run lengths) and walk them, so
- *                  the tile's ~1000 leaves and its seed cells stay in that SM's L1; results go
- *                  to the binned slots (neighbouring tiles are resident together, so the runs'
- *                  shared sectors merge in L2);
+/* ---- reorder pipeline: k_bin -> k_tile_walk -> k_unpermute -----------------------------------
+ * Uniformly random queries make every leaf fetch an isolated L2/DRAM line fill: at 10^6 nodes the
+ * direct walk moves ~220 bytes per query through HBM for 28 algorithmic bytes.  The pipeline
+ * trades those fills for three streaming passes (~90 bytes per query) and keeps the structure
+ * on chip:
+ *   k_bin          one CTA per chunk of <= 8192 consecutive queries: counting sort by spatial tile
+ *                  (the leaf order's own Morton-key prefix, so a tile's leaves are one contiguous
+ *                  slot range) entirely in shared memory, then coalesced stores of the binned
+ *                  coordinates, the 16-bit in-chunk index of every binned query and the chunk's
+ *                  runs (bin-major table: one contiguous row per tile);
+ *   k_tile_walk    tile-major, persistent CTAs pulling (tile, range) work items from a counter:
+ *                  the tile's leaf records arrive in shared memory by one TMA bulk copy
+ *                  (cp.async.bulk + mbarrier), its seed cells beside them; every warp flattens the
+ *                  tile's runs of 32 chunks at a time into a dense position list and consumes it
+ *                  through a warp-wide work queue (one walk step per iteration for whatever query
+ *                  each lane holds -- a lane that finished takes the next query at once), reading
+ *                  seeds, records and tails from shared memory;
  *   k_unpermute    one CTA per chunk: the inverse permutation through shared memory, coalesced
  *                  loads and stores.
- * The arithmetic per query is the one of k_locate (gsi_walk_step), so accepted results are
- * bit-identical; deferred queries go to the same list (original query index) and are replayed
- * after k_unpermute. */
+ * The arithmetic per query is the one of every other fast-path kernel (gsi_walk_step), so
+ * accepted results are bit-identical; deferred queries go to the same list (original query index)
+ * and are replayed exactly after k_unpermute. */
 __device__ __forceinline__ unsigned
 spread16(unsigned x) /* the low 16 bits of x on the even bit positions */
 {
@@ -418,39 +423,42 @@ spread16(unsigned x) /* the low 16 bits of x on the even bit positions */
   return x;
 }
 
-__device__ __forceinline__ unsigned
-compact16(unsigned x) /* inverse of spread16 */
+/* Tiles are the 2^P prefixes of the 32-bit Morton key gsi_flatten.cpp sorts the leaves' centroids
+ * by (16 bits per axis, y on the odd bits): the prefix holds ceil(P/2) bits of y and floor(P/2) of
+ * x.  k_bin numbers its bins row-major, bin = (ty << bx_bits) | tx, from one fused multiply-add per
+ * axis; the tile kernel turns a bin into the Morton prefix that indexes V.tiles.  Binning is a
+ * heuristic only: a query binned next door still walks to its leaf through global memory.  NaN
+ * converts to 0 and +-inf saturate, so every query gets a bin. */
+struct gsi_tile_map
 {
-  x &= 0x55555555u;
-  x = (x | (x >> 1)) & 0x33333333u;
-  x = (x | (x >> 2)) & 0x0f0f0f0fu;
-  x = (x | (x >> 4)) & 0x00ff00ffu;
-  x = (x | (x >> 8)) & 0x0000ffffu;
-  return x;
+  double ax, bx, ay, by; /* tx = floor(qx*ax + bx), ty = floor(qy*ay + by) before clamping */
+  int bx_bits, by_bits;
+};
+
+__device__ __forceinline__ unsigned
+bin_of(const gsi_tile_map &M, double qx, double qy)
+{
+  const int tx = min(max(__double2int_rd(__fma_rn(qx, M.ax, M.bx)), 0), (1 << M.bx_bits) - 1);
+  const int ty = min(max(__double2int_rd(__fma_rn(qy, M.ay, M.by)), 0), (1 << M.by_bits) - 1);
+  return ((unsigned) ty << M.bx_bits) | (unsigned) tx;
 }
 
-/* Tile of a query = the tile_bits-bit prefix of the 32-bit Morton key of its position in the data
- * bounding box (16 bits per axis, y on the odd bits) -- the key gsi_flatten.cpp sorts the leaves'
- * centroids by, so tile t's leaves are the slots [V.tiles[t], V.tiles[t+1]).  Non-finite and
- * outside coordinates are clamped (they are deferred by the walk anyway). */
 __device__ __forceinline__ unsigned
-tile_of(const gsi_view &V, double qx, double qy)
+bin_to_prefix(const gsi_tile_map &M, unsigned bin)
 {
-  const double u = (qx - V.xf.cx) * V.xf.sx, v = (qy - V.xf.cy) * V.xf.sy;
-  const double k = 65536.0 / (double) V.grid_g; /* (u - u0) * inv_du is in grid cells */
-  const unsigned ix = (unsigned) __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du * k, 0.0), 65535.0));
-  const unsigned iy = (unsigned) __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv * k, 0.0), 65535.0));
-  return (spread16(ix) | (spread16(iy) << 1)) >> (32 - V.tile_bits);
+  const unsigned tx = bin & ((1u << M.bx_bits) - 1u), ty = bin >> M.bx_bits;
+  /* odd P: the lowest prefix bit belongs to y */
+  return (M.by_bits > M.bx_bits) ? (spread16(ty) | (spread16(tx) << 1)) : (spread16(tx) | (spread16(ty) << 1));
 }
 
 /* One coordinate is staged at a time (96 KB of shared memory for 8192-query chunks) so that two
  * CTAs share an SM and one CTA's global loads overlap the other's scan / copy-out. */
 __global__ void __launch_bounds__(GSI_BIN_THREADS, 2)
-k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict__ yq, size_t nq, int S,
-       int nt, double *__restrict__ bx, double *__restrict__ by,
-       unsigned short *__restrict__ bi, unsigned short *__restrict__ off)
+k_bin(const gsi_tile_map M, const double *__restrict__ xq, const double *__restrict__ yq, size_t nq, int S,
+      int nt, double *__restrict__ bx, double *__restrict__ by, unsigned short *__restrict__ bi,
+      unsigned *__restrict__ runs)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double *sbuf = reinterpret_cast<double *>(smem_raw);
   unsigned *hist = reinterpret_cast<unsigned *>(sbuf + S);
   unsigned short *si = reinterpret_cast<unsigned short *>(hist + nt);
@@ -461,7 +469,6 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
   const unsigned FULL = 0xffffffffu;
   const unsigned tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
-  const size_t ntp = (size_t) nt + 2;
   const unsigned per = ((unsigned) nt + T - 1) / T;
   for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
     {
@@ -477,7 +484,7 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
           pk[k] = 0xffffffffu;
           if (i < n)
             {
-              const unsigned t = tile_of(V, __ldg(xq + q0 + i), __ldg(yq + q0 + i));
+              const unsigned t = bin_of(M, __ldg(xq + q0 + i), __ldg(yq + q0 + i));
               pk[k] = t | (atomicAdd(hist + t, 1u) << 12);
             }
         }
@@ -503,16 +510,16 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
 #pragma unroll
       for (unsigned w = 0; w < WPC; w++)
         if (w < wid) run += warp_sum[w];
-      unsigned short *row = off + c * ntp;
 #pragma unroll
       for (unsigned j = 0; j < PER; j++)
         if (j < per && b + j < (unsigned) nt)
           {
             hist[b + j] = run;
-            row[b + j] = (unsigned short) run;
+            /* bin-major run table: neighbouring chunks (sorted by neighbouring CTAs at about the
+               same time) fill neighbouring words of a row, so the sectors merge in L2 */
+            runs[(size_t) (b + j) * n_chunks + c] = run | ((run + loc[j]) << 16);
             run += loc[j];
           }
-      if (tid == 0) row[nt] = (unsigned short) n;
       __syncthreads();
       /* x: permute in shared memory, copy out; then y through the same buffer */
 #pragma unroll
@@ -545,156 +552,53 @@ k_bin(const gsi_view V, const double *__restrict__ xq, const double *__restrict_
     }
 }
 
-/* one converged warp step of the tile kernels: every live lane walks the binned query at slot
- * `pos` of the window (chunk base `cbase`) and stores its result to the binned outputs;
- * deferred queries are appended to the list under their original index */
-template <bool STATS>
-__device__ __forceinline__ void
-tile_direct_step(const gsi_view &V, const double *__restrict__ bx, const double *__restrict__ by,
-                 const unsigned short *__restrict__ bi, bool live, size_t pos, size_t cbase, double *zb,
-                 int *lb, size_t ldb, unsigned *list, unsigned list_cap, unsigned *ovf_mask,
-                 unsigned *counters, int max_steps, unsigned long long &steps_acc)
-{
-  const unsigned FULL = 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  int status = GSI_STEP_MOVE; /* = not a live query */
-  int slot = 0;
-  double c0 = 0, c1 = 0;
-  if (live)
-    {
-      const double qx = __ldcs(bx + pos), qy = __ldcs(by + pos);
-      status = GSI_STEP_DEFER;
-      if (isfinite(qx) && isfinite(qy))
-        {
-          slot = gsi_ld_seed(V.seeds + gsi_cell_of(&V, qx, qy));
-          for (int step = 0; step < max_steps; step++)
-            {
-              gsi_rec rec;
-              const int at = slot;
-              gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
-              const int st = gsi_walk_step(&V.xf, &rec, qx, qy, &slot, &c0, &c1);
-              if (st != GSI_STEP_MOVE)
-                {
-                  status = st;
-                  slot = at;
-                  if (STATS && st == GSI_STEP_ACCEPT) steps_acc += (unsigned) step + 1u;
-                  break;
-                }
-            }
-        }
-    }
-  __syncwarp();
-  if (status == GSI_STEP_ACCEPT)
-    {
-      gsi_leaf_tail tl;
-      gsi_fetch_tail(&tl, gsi_leaf_at(&V, slot));
-      if (lb) lb[pos] = tl.g.node;
-      if (zb) gsi_blend_store(&V, &tl, c0, c1, zb, ldb, pos);
-    }
-  const bool defer = status == GSI_STEP_DEFER;
-  const unsigned dm = __ballot_sync(FULL, defer);
-  if (dm)
-    {
-      const int leader = __ffs(dm) - 1;
-      unsigned at0 = 0;
-      if (lane == (unsigned) leader) at0 = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
-      at0 = __shfl_sync(FULL, at0, leader);
-      if (defer)
-        {
-          const size_t q = cbase + bi[pos];
-          const unsigned at = at0 + __popc(dm & ((1u << lane) - 1u));
-          if (at < list_cap)
-            list[at] = (unsigned) q;
-          else
-            mark_overflow(ovf_mask, q, counters);
-        }
-    }
-}
-
-/* lane <-> chunk: load tile t's run in chunk (cb*32 + lane) and the inclusive prefix of the run
- * lengths over the warp; returns the warp's total */
+/* ---- mbarrier + TMA 1-D bulk copy (cp.async.bulk; SASS: UBLKCP, SYNCS) ---------------------------- */
 __device__ __forceinline__ unsigned
-tile_runs(const unsigned short *__restrict__ off, size_t ntp, unsigned t, unsigned cb, unsigned n_blocks,
-          unsigned n_chunks, unsigned &o0, unsigned &len, unsigned &incl)
+smem_u32(const void *p)
 {
-  const unsigned FULL = 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned c = (cb << 5) + lane;
-  o0 = 0;
-  len = 0;
-  if (cb < n_blocks && c < n_chunks)
-    {
-      const unsigned short *row = off + (size_t) c * ntp + t;
-      o0 = row[0];
-      len = (unsigned) row[1] - o0;
-    }
-  incl = len;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1)
-    {
-      const unsigned v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= (unsigned) o) incl += v;
-    }
-  return __shfl_sync(FULL, incl, 31);
+  return (unsigned) __cvta_generic_to_shared(p);
 }
 
-/* item k (< total) of the warp's concatenated runs -> binned slot of the window; *cbase = first
- * slot of the item's chunk.  Must be called by the whole warp. */
-__device__ __forceinline__ size_t
-tile_item(unsigned k, unsigned cb, int S, unsigned o0, unsigned len, unsigned incl, size_t *cbase)
+__device__ __forceinline__ void
+mbar_init(unsigned long long *bar, unsigned count)
 {
-  const unsigned FULL = 0xffffffffu;
-  unsigned j = 0; /* number of chunks whose inclusive prefix is <= k = the chunk holding item k */
-#pragma unroll
-  for (unsigned step = 16; step; step >>= 1)
-    {
-      const unsigned v = __shfl_sync(FULL, incl, j + step - 1);
-      if (v <= k) j += step;
-    }
-  const unsigned incl_j = __shfl_sync(FULL, incl, j), len_j = __shfl_sync(FULL, len, j),
-                 o0_j = __shfl_sync(FULL, o0, j);
-  *cbase = (size_t) ((cb << 5) + j) * (size_t) S;
-  return *cbase + o0_j + (k - (incl_j - len_j));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(GSI_TILE_THREADS, 2)
-k_tile_locate(const gsi_view V, const double *__restrict__ bx, const double *__restrict__ by,
-              const unsigned short *__restrict__ bi, const unsigned short *__restrict__ off,
-              unsigned n_chunks, int S, int nt, int ranges, double *zb, int *lb, size_t ldb,
-              unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters, int max_steps)
+__device__ __forceinline__ void
+mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
 {
-  const unsigned t = blockIdx.x / (unsigned) ranges, r = blockIdx.x - t * (unsigned) ranges;
-  constexpr unsigned WPC = GSI_TILE_THREADS / 32;
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const unsigned n_blocks = (n_chunks + 31u) >> 5;
-  const size_t ntp = (size_t) nt + 2;
-  unsigned long long steps_acc = 0;
-  for (unsigned cb = r * WPC + warp; cb < n_blocks; cb += (unsigned) ranges * WPC)
-    {
-      unsigned o0, len, incl;
-      const unsigned total = tile_runs(off, ntp, t, cb, n_blocks, n_chunks, o0, len, incl);
-      for (unsigned base = 0; base < total; base += 32)
-        {
-          const bool live = base + lane < total;
-          size_t cbase;
-          const size_t pos = tile_item(live ? base + lane : total - 1, cb, S, o0, len, incl, &cbase);
-          tile_direct_step<STATS>(V, bx, by, bi, live, pos, cbase, zb, lb, ldb, list, list_cap, ovf_mask,
-                                  counters, max_steps, steps_acc);
-        }
-    }
-  if (STATS && steps_acc)
-    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-/* ---- tile kernel with the tile staged in shared memory ---------------------------------------------
- * k_tile_locate gathers every leaf sector through L1, and a divergent L1 access costs the same
- * L1 cycles whether it hits or not (0.77 sectors/clk/SM measured).  Here the CTA first copies its
- * tile -- the contiguous slot range [V.tiles[t], V.tiles[t+1]) of 96-byte leaf records and the
- * block of seed cells under the tile's rectangle -- into shared memory with coalesced loads, and
- * the walk reads seeds, records and tails from there; only leaves outside the tile (walks that
- * leave it, tiles larger than the staging area) and the query coordinates come from global
- * memory.  Same per-query operations as every other fast-path kernel. */
+__device__ __forceinline__ bool
+mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+  unsigned done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(done)
+               : "r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+  return done != 0;
+}
+
+/* global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is
+ * signalled on `bar` as a transaction count */
+__device__ __forceinline__ void
+bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void
+fence_proxy_async()
+{
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ void
 fetch_rec_smem(gsi_rec *r, const uint4 *p)
 {
@@ -722,135 +626,242 @@ fetch_tail_smem(gsi_leaf_tail *t, const uint4 *p)
   t->s.z[2] = __hiloint2double((int) f.w, (int) f.z);
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(GSI_TILE_THREADS, 2)
-k_tile_locate_smem(const gsi_view V, const double *__restrict__ bx, const double *__restrict__ by,
-                   const unsigned short *__restrict__ bi, const unsigned short *__restrict__ off,
-                   unsigned n_chunks, int S, int nt, int ranges, int leaf_cap, int seed_rows, int seed_pitch,
-                   double *zb, int *lb, size_t ldb, unsigned *list, unsigned list_cap, unsigned *ovf_mask,
-                   unsigned *counters, int max_steps)
+struct gsi_tile_args
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  gsi_tile_map M;
+  const double *bx, *by;
+  const unsigned short *bi;
+  const unsigned *runs; /* [n_bins][n_chunks] */
+  unsigned *work;       /* work-item counter (zero at launch) */
+  unsigned n_chunks;
+  int S, nt, ranges;
+  int leaf_cap, seed_rows, seed_pitch;
+  double *zb;
+  int *lb;
+  size_t ldb;
+  unsigned *list;
+  unsigned list_cap;
+  unsigned *ovf_mask;
+  unsigned *counters;
+  int max_steps;
+};
+
+#define GSI_SEED_FAR 0xffffu /* staged seed cell whose leaf lies outside the staged slot range */
+
+template <bool STATS, bool ONE_FIELD>
+__global__ void __launch_bounds__(GSI_TILE_THREADS, 1)
+k_tile_walk(const gsi_view V, const gsi_tile_args A)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ unsigned long long mbar;
+  __shared__ unsigned s_item;
   uint4 *sleaf = reinterpret_cast<uint4 *>(smem_raw);
-  int *sseed = reinterpret_cast<int *>(sleaf + (size_t) leaf_cap * 6);
+  unsigned short *sseed = reinterpret_cast<unsigned short *>(sleaf + (size_t) A.leaf_cap * 6);
+  unsigned *spos_all = reinterpret_cast<unsigned *>(smem_raw + (((size_t) A.leaf_cap * 96 + (size_t) A.seed_rows * A.seed_pitch * 2 + 15) & ~(size_t) 15));
   const unsigned FULL = 0xffffffffu;
-  const unsigned t = blockIdx.x / (unsigned) ranges, r = blockIdx.x - t * (unsigned) ranges;
-  constexpr unsigned WPC = GSI_TILE_THREADS / 32;
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, WPC = blockDim.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned n_blocks = (n_chunks + 31u) >> 5;
-  const size_t ntp = (size_t) nt + 2;
-
-  /* ---- stage the tile ---- */
-  const int slot0 = V.tiles[t];
-  const int n_staged = min(V.tiles[t + 1] - slot0, leaf_cap);
-  if (V.leaf_stride == (int) sizeof(gsi_leaf))
-    {
-      const uint4 *src = reinterpret_cast<const uint4 *>(V.leaf + (size_t) slot0 * sizeof(gsi_leaf));
-      for (int i = threadIdx.x; i < n_staged * 6; i += GSI_TILE_THREADS) sleaf[i] = __ldg(src + i);
-    }
-  else
-    for (int i = threadIdx.x; i < n_staged * 6; i += GSI_TILE_THREADS)
-      sleaf[i] = __ldg(reinterpret_cast<const uint4 *>(V.leaf + (size_t) (slot0 + i / 6) * (size_t) V.leaf_stride) + i % 6);
-  /* the tile's rectangle in 16-bit Morton coordinates -> block of seed cells */
-  const int by_bits = (V.tile_bits + 1) >> 1, bx_bits = V.tile_bits >> 1;
-  const unsigned key_hi = t << (32 - V.tile_bits);
-  const unsigned qx_lo = compact16(key_hi), qy_lo = compact16(key_hi >> 1);
-  const double cells_per_q = (double) V.grid_g / 65536.0;
-  const int cx0 = max(0, (int) floor((double) qx_lo * cells_per_q) - 1);
-  const int cy0 = max(0, (int) floor((double) qy_lo * cells_per_q) - 1);
-  const int ncx = min(seed_pitch, V.grid_g - cx0), ncy = min(seed_rows, V.grid_g - cy0);
-  (void) bx_bits;
-  (void) by_bits;
-  for (int i = threadIdx.x; i < ncy * seed_pitch; i += GSI_TILE_THREADS)
-    {
-      const int ry = i / seed_pitch, rx = i - ry * seed_pitch;
-      if (rx < ncx) sseed[i] = __ldg(V.seeds + (size_t) (cy0 + ry) * (size_t) V.grid_g + (size_t) (cx0 + rx));
-    }
-  __syncthreads();
-
+  unsigned *spos = spos_all + (size_t) warp * GSI_TILE_SPOS;
+  const unsigned n_blocks = (A.n_chunks + 31u) >> 5;
+  const unsigned n_items = (unsigned) A.nt * (unsigned) A.ranges;
   const double gmax = (double) (V.grid_g - 1);
   unsigned long long steps_acc = 0;
-  for (unsigned cb = r * WPC + warp; cb < n_blocks; cb += (unsigned) ranges * WPC)
+  unsigned parity = 0;
+  if (tid == 0) mbar_init(&mbar, 1);
+
+  for (;;)
     {
-      unsigned o0, len, incl;
-      const unsigned total = tile_runs(off, ntp, t, cb, n_blocks, n_chunks, o0, len, incl);
-      for (unsigned base = 0; base < total; base += 32)
+      if (tid == 0) s_item = atomicAdd(A.work, 1u);
+      __syncthreads(); /* every warp is done with the previous item's shared memory */
+      const unsigned item = s_item;
+      if (item >= n_items) break;
+      const unsigned bin = item / (unsigned) A.ranges, range = item - bin * (unsigned) A.ranges;
+      const unsigned prefix = bin_to_prefix(A.M, bin);
+      const int slot0 = V.tiles[prefix];
+      const int n_staged = min(V.tiles[prefix + 1] - slot0, A.leaf_cap);
+      const bool packed = V.leaf_stride == (int) sizeof(gsi_leaf);
+      /* ---- stage the tile: leaf records by TMA bulk copy, seed cells by the threads ---- */
+      if (packed && n_staged > 0 && tid == 0)
         {
-          const bool live = base + lane < total;
-          size_t cbase;
-          const size_t pos = tile_item(live ? base + lane : total - 1, cb, S, o0, len, incl, &cbase);
-          int status = GSI_STEP_MOVE; /* = not a live query */
-          int slot = 0;
-          double c0 = 0, c1 = 0;
-          if (live)
+          const unsigned bytes = (unsigned) n_staged * 96u;
+          const char *src = V.leaf + (size_t) slot0 * sizeof(gsi_leaf);
+          fence_proxy_async();
+          mbar_arrive_expect_tx(&mbar, bytes);
+          for (unsigned o = 0; o < bytes; o += 32768u)
+            bulk_load(reinterpret_cast<char *>(sleaf) + o, src + o, min(32768u, bytes - o), &mbar);
+        }
+      if (!packed)
+        for (int i = tid; i < n_staged * 6; i += blockDim.x)
+          sleaf[i] = __ldg(reinterpret_cast<const uint4 *>(V.leaf + (size_t) (slot0 + i / 6) * (size_t) V.leaf_stride) + i % 6);
+      /* the tile's rectangle of grid cells, one cell of margin */
+      const unsigned tx = bin & ((1u << A.M.bx_bits) - 1u), ty = bin >> A.M.bx_bits;
+      const int cx0 = max(0, (int) (((unsigned long long) tx * (unsigned) V.grid_g) >> A.M.bx_bits) - 1);
+      const int cy0 = max(0, (int) (((unsigned long long) ty * (unsigned) V.grid_g) >> A.M.by_bits) - 1);
+      const int ncx = min(A.seed_pitch, V.grid_g - cx0), ncy = min(A.seed_rows, V.grid_g - cy0);
+      for (int i = tid; i < ncy * A.seed_pitch; i += blockDim.x)
+        {
+          const int ry = i / A.seed_pitch, rx = i - ry * A.seed_pitch;
+          if (rx < ncx)
             {
-              const double qx = __ldcs(bx + pos), qy = __ldcs(by + pos);
-              status = GSI_STEP_DEFER;
-              if (isfinite(qx) && isfinite(qy))
+              const unsigned rel = (unsigned) (__ldg(V.seeds + (size_t) (cy0 + ry) * (size_t) V.grid_g + (size_t) (cx0 + rx)) - slot0);
+              sseed[i] = rel < (unsigned) n_staged && rel < GSI_SEED_FAR ? (unsigned short) rel : (unsigned short) GSI_SEED_FAR;
+            }
+        }
+      __syncthreads(); /* seeds (and the fallback copy of the records) are visible */
+      if (packed && n_staged > 0)
+        {
+          while (!mbar_try_wait(&mbar, parity)) {}
+          parity ^= 1u;
+        }
+
+      /* ---- walk the tile's queries ---- */
+      const unsigned *runs_row = A.runs + (size_t) bin * A.n_chunks;
+      unsigned cb = range * WPC + warp;
+      const unsigned cb_stride = (unsigned) A.ranges * WPC;
+      unsigned r_pos0 = 0, r_len = 0, r_excl = 0; /* this lane's run of the current block */
+      unsigned b_total = 0, win_lo = 0, win_n = 0, next = 0;
+      bool cur_v = false;
+      double cur_x = 0, cur_y = 0;
+      unsigned cur_pos = 0;
+      int cur_slot = 0, cur_steps = 0;
+      for (;;)
+        {
+          if (next >= win_n) /* warp-uniform: the dense list is used up */
+            {
+              bool have = true;
+              if (win_lo + win_n < b_total)
+                win_lo += win_n; /* next window of a block that exceeds the list */
+              else if (cb < n_blocks)
                 {
-                  /* the cell of gsi_cell_of; its seed from the staged block when it is inside */
-                  const double u = (qx - V.xf.cx) * V.xf.sx, v = (qy - V.xf.cy) * V.xf.sy;
-                  const int ix = __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du, 0.0), gmax));
-                  const int iy = __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv, 0.0), gmax));
-                  const unsigned rx = (unsigned) (ix - cx0), ry = (unsigned) (iy - cy0);
-                  slot = (rx < (unsigned) ncx && ry < (unsigned) ncy)
-                             ? sseed[ry * seed_pitch + rx]
-                             : gsi_ld_seed(V.seeds + (size_t) iy * (size_t) V.grid_g + (size_t) ix);
-                  for (int step = 0; step < max_steps; step++)
+                  const unsigned c = (cb << 5) + lane;
+                  const unsigned run = c < A.n_chunks ? __ldg(runs_row + c) : 0u;
+                  const unsigned start = run & 0xffffu;
+                  r_len = (run >> 16) - start;
+                  r_pos0 = c * (unsigned) A.S + start;
+                  unsigned incl = r_len;
+#pragma unroll
+                  for (int o = 1; o < 32; o <<= 1)
                     {
-                      gsi_rec rec;
-                      const int at = slot;
-                      const unsigned rel = (unsigned) (at - slot0);
-                      if (rel < (unsigned) n_staged)
-                        fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
-                      else
-                        gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
-                      const int st = gsi_walk_step(&V.xf, &rec, qx, qy, &slot, &c0, &c1);
-                      if (st != GSI_STEP_MOVE)
-                        {
-                          status = st;
-                          slot = at;
-                          if (STATS && st == GSI_STEP_ACCEPT) steps_acc += (unsigned) step + 1u;
-                          break;
-                        }
+                      const unsigned v = __shfl_up_sync(FULL, incl, o);
+                      if (lane >= (unsigned) o) incl += v;
+                    }
+                  r_excl = incl - r_len;
+                  b_total = __shfl_sync(FULL, incl, 31);
+                  win_lo = 0;
+                  cb += cb_stride;
+                }
+              else
+                have = false;
+              next = 0;
+              win_n = 0;
+              if (have)
+                {
+                  win_n = min((unsigned) GSI_TILE_SPOS, b_total - win_lo);
+                  /* items [win_lo, win_lo + win_n) of the block's concatenated runs */
+                  const unsigned k0 = win_lo > r_excl ? win_lo - r_excl : 0u;
+                  const unsigned k1 = min(r_len, win_lo + win_n > r_excl ? win_lo + win_n - r_excl : 0u);
+                  for (unsigned k = k0; k < k1; k++) spos[r_excl + k - win_lo] = r_pos0 + k;
+                  __syncwarp();
+                  if (win_n == 0) continue; /* empty block */
+                }
+              else if (!__any_sync(FULL, cur_v))
+                break;
+            }
+          /* refill: a lane without a query takes the next position of the list */
+          bool defer = false;
+          const bool need = !cur_v;
+          const unsigned take = __ballot_sync(FULL, need);
+          if (need)
+            {
+              const unsigned off = next + __popc(take & lt_mask);
+              if (off < win_n)
+                {
+                  cur_pos = spos[off];
+                  cur_x = __ldcs(A.bx + cur_pos);
+                  cur_y = __ldcs(A.by + cur_pos);
+                  cur_steps = 0;
+                  cur_v = true;
+                  if (isfinite(cur_x) && isfinite(cur_y))
+                    {
+                      /* the cell of gsi_cell_of; its seed from the staged block when it is inside */
+                      const double u = (cur_x - V.xf.cx) * V.xf.sx, v = (cur_y - V.xf.cy) * V.xf.sy;
+                      const int ix = __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du, 0.0), gmax));
+                      const int iy = __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv, 0.0), gmax));
+                      const unsigned rx = (unsigned) (ix - cx0), ry = (unsigned) (iy - cy0);
+                      unsigned rel = GSI_SEED_FAR;
+                      if (rx < (unsigned) ncx && ry < (unsigned) ncy) rel = sseed[ry * A.seed_pitch + rx];
+                      cur_slot = rel != GSI_SEED_FAR ? slot0 + (int) rel
+                                                     : gsi_ld_seed(V.seeds + (size_t) iy * (size_t) V.grid_g + (size_t) ix);
+                    }
+                  else
+                    {
+                      defer = true;
+                      cur_v = false;
                     }
                 }
             }
-          __syncwarp();
-          if (status == GSI_STEP_ACCEPT)
+          next = min(next + (unsigned) __popc(take), win_n);
+          /* one walk step for every lane that holds a query */
+          if (cur_v)
             {
-              gsi_leaf_tail tl;
-              const unsigned rel = (unsigned) (slot - slot0);
-              if (rel < (unsigned) n_staged)
-                fetch_tail_smem(&tl, sleaf + (size_t) rel * 6);
+              gsi_rec rec;
+              const int at = cur_slot;
+              const unsigned rel = (unsigned) (at - slot0);
+              const bool staged = rel < (unsigned) n_staged;
+              if (staged)
+                fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
               else
-                gsi_fetch_tail(&tl, gsi_leaf_at(&V, slot));
-              if (lb) lb[pos] = tl.g.node;
-              if (zb) gsi_blend_store(&V, &tl, c0, c1, zb, ldb, pos);
+                gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
+              double c0, c1;
+              const int st = gsi_walk_step(&V.xf, &rec, cur_x, cur_y, &cur_slot, &c0, &c1);
+              ++cur_steps;
+              if (st == GSI_STEP_ACCEPT)
+                {
+                  gsi_leaf_tail tl;
+                  if (staged)
+                    fetch_tail_smem(&tl, sleaf + (size_t) rel * 6);
+                  else
+                    gsi_fetch_tail(&tl, gsi_leaf_at(&V, at));
+                  if (A.lb) __stcs(A.lb + cur_pos, tl.g.node);
+                  if (A.zb)
+                    {
+                      if (ONE_FIELD)
+                        __stcs(A.zb + cur_pos, gsi_blend(c0, c1, (int) (tl.s.vflags & 1u), tl.s.z[0], (int) (tl.s.vflags & 2u),
+                                                         tl.s.z[1], (int) (tl.s.vflags & 4u), tl.s.z[2]));
+                      else
+                        gsi_blend_store(&V, &tl, c0, c1, A.zb, A.ldb, cur_pos);
+                    }
+                  if (STATS) steps_acc += (unsigned) cur_steps;
+                  cur_v = false;
+                }
+              else if (st == GSI_STEP_DEFER || cur_steps >= A.max_steps)
+                {
+                  defer = true;
+                  cur_v = false;
+                }
             }
-          const bool defer = status == GSI_STEP_DEFER;
+          /* warp-aggregated append to the deferred list (original query index) */
           const unsigned dm = __ballot_sync(FULL, defer);
           if (dm)
             {
               const int leader = __ffs(dm) - 1;
               unsigned at0 = 0;
-              if (lane == (unsigned) leader) at0 = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+              if (lane == (unsigned) leader) at0 = atomicAdd(A.counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
               at0 = __shfl_sync(FULL, at0, leader);
               if (defer)
                 {
-                  const size_t q = cbase + bi[pos];
+                  const size_t q = (size_t) (cur_pos / (unsigned) A.S) * (size_t) A.S + A.bi[cur_pos];
                   const unsigned at = at0 + __popc(dm & lt_mask);
-                  if (at < list_cap)
-                    list[at] = (unsigned) q;
+                  if (at < A.list_cap)
+                    A.list[at] = (unsigned) q;
                   else
-                    mark_overflow(ovf_mask, q, counters);
+                    mark_overflow(A.ovf_mask, q, A.counters);
                 }
             }
         }
     }
   if (STATS && steps_acc)
-    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
+    atomicAdd(reinterpret_cast<unsigned long long *>(A.counters + GSI_CNT_STEPS), steps_acc);
 }
 
 __global__ void __launch_bounds__(GSI_UNPERMUTE_THREADS, 2)
@@ -858,7 +869,7 @@ k_unpermute(const double *__restrict__ zb, const int *__restrict__ lb, const uns
             size_t nq, int S, int n_fields, size_t ldb, double *__restrict__ val, size_t ld,
             int *__restrict__ leaf_out)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double *sz = reinterpret_cast<double *>(smem_raw);
   int *sl = reinterpret_cast<int *>(sz + S);
   const unsigned tid = threadIdx.x;
@@ -963,6 +974,56 @@ k_compare(const int *leaf_a, const int *leaf_b, const double *val_a, const doubl
     }
 }
 
+/* Range check of every index a kernel will follow in an adopted slab image (file, peer process):
+ * DAG links, leaf slots, neighbour slots, vertex slots, node ids, seed cells, entry nodes, tile
+ * boundaries.  A foreign or damaged image is rejected with GSL_SCATTERED_EINVAL instead of
+ * faulting the context. */
+__global__ void __launch_bounds__(256)
+k_validate_slab(const gsi_view V, unsigned long long n_points, unsigned long long *bad)
+{
+  const size_t cells = (size_t) V.grid_g * (size_t) V.grid_g;
+  const size_t nt1 = ((size_t) 1 << V.tile_bits) + 1;
+  size_t n = (size_t) V.n_dag;
+  if ((size_t) V.n_leaves > n) n = (size_t) V.n_leaves;
+  if (cells > n) n = cells;
+  if (nt1 > n) n = nt1;
+  unsigned long long mine = 0;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+      if (i < (size_t) V.n_dag)
+        {
+          const gsi_rec &r = V.dag[i];
+          const uint32_t type = r.meta & GSI_META_TYPE_MASK;
+          if (type == GSI_LEAF)
+            mine += (unsigned) r.lnk[0] >= (unsigned) V.n_leaves;
+          else
+            for (int k = 0; k < 3; k++) mine += (unsigned) r.lnk[k] >= (unsigned) V.n_dag;
+        }
+      if (i < (size_t) V.n_leaves)
+        {
+          const gsi_leaf *lf = gsi_leaf_at(&V, (int) i);
+          for (int k = 0; k < 3; k++)
+            {
+              mine += lf->r.lnk[k] < -1 || lf->r.lnk[k] >= V.n_leaves;
+              if (V.n_fields > 1) mine += lf->t.g.v[k] < -1 || (lf->t.g.v[k] >= 0 && (unsigned long long) lf->t.g.v[k] >= n_points);
+            }
+          mine += (unsigned) lf->t.g.node >= (unsigned) V.n_dag;
+        }
+      if (i < cells)
+        {
+          mine += (unsigned) V.seeds[i] >= (unsigned) V.n_leaves;
+          if (V.entry) mine += (unsigned) V.entry[i] >= (unsigned) V.n_dag;
+        }
+      if (i < nt1)
+        {
+          const int t = V.tiles[i];
+          mine += t < 0 || t > V.n_leaves || (i + 1 < nt1 && V.tiles[i + 1] < t) || (i + 1 == nt1 && t != V.n_leaves);
+        }
+    }
+  if (mine) atomicAdd(bad, mine);
+}
+
 __global__ void
 k_accumulate_deferred(unsigned *counters)
 {
@@ -995,52 +1056,83 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
   const gsi_reorder_scratch *R = cfg.reorder;
   if (!R || nq > R->cap || R->chunk < 32 || R->chunk > GSI_BIN_CHUNK_MAX || V.tile_bits < 1 || V.tile_bits > 12)
     return false;
-  const int S = R->chunk, nt = 1 << V.tile_bits;
+  const int S = R->chunk, P = V.tile_bits, nt = 1 << P;
   const size_t n_chunks = (nq + (size_t) S - 1) / (size_t) S;
+  gsi_tile_map M;
+  M.bx_bits = P >> 1;
+  M.by_bits = (P + 1) >> 1;
+  {
+    /* tx = floor(((qx - cx) * sx - u0) * inv_du * 2^bx_bits / G) as one fused multiply-add */
+    const double kx = V.inv_du * (double) (1 << M.bx_bits) / (double) V.grid_g;
+    const double ky = V.inv_dv * (double) (1 << M.by_bits) / (double) V.grid_g;
+    M.ax = V.xf.sx * kx;
+    M.bx = (-V.xf.cx * V.xf.sx - V.u0) * kx;
+    M.ay = V.xf.sy * ky;
+    M.by = (-V.xf.cy * V.xf.sy - V.v0) * ky;
+  }
   const size_t smem_bin = (size_t) S * 10 + (size_t) nt * 4, smem_unp = (size_t) S * 12;
-  /* staging area of the tile kernel: the largest tile's records (capped) + the seed cells under a
-     tile's rectangle (x gets floor(P/2) bits of the prefix, y the rest), two cells of margin */
-  const int bx_bits = V.tile_bits >> 1, by_bits = (V.tile_bits + 1) >> 1;
-  const int seed_pitch = (V.grid_g >> bx_bits) + 4, seed_rows = (V.grid_g >> by_bits) + 4;
-  const size_t seed_bytes = (size_t) seed_pitch * seed_rows * 4;
-  int leaf_cap = R->tile_max_leaves < 1 ? 1 : R->tile_max_leaves;
-  const size_t budget = 110 * 1024; /* two CTAs per SM */
-  if (seed_bytes + 96 > budget) leaf_cap = 0;
-  else if ((size_t) leaf_cap * 96 + seed_bytes > budget) leaf_cap = (int) ((budget - seed_bytes) / 96);
-  const size_t smem_tile = (size_t) leaf_cap * 96 + seed_bytes;
   /* per device (the current one), so not cached in a process-wide flag */
   cudaFuncSetAttribute(k_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 10 + 4096 * 4);
   cudaFuncSetAttribute(k_unpermute, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_BIN_CHUNK_MAX * 12);
   const int g_bin = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
-  k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(V, src.x, src.y, nq, S, nt, R->bx, R->by, R->bi, R->off);
-  /* CTAs per tile: every warp of a CTA should get a few 32-chunk blocks, else one CTA per tile */
-  const size_t n_blocks = (n_chunks + 31) / 32;
-  int ranges = (int) (n_blocks / (4 * (GSI_TILE_THREADS / 32)));
-  if (ranges > R->ranges) ranges = R->ranges;
-  if (ranges < 1) ranges = 1;
-  double *zb = val ? R->zb : nullptr;
-  int *lb = leaf_out ? R->lb : nullptr;
-  if (R->tile_smem && leaf_cap > 0)
+  k_bin<<<g_bin, GSI_BIN_THREADS, smem_bin, st>>>(M, src.x, src.y, nq, S, nt, R->bx, R->by, R->bi, R->runs);
+
+  /* tile kernel: one persistent CTA per SM; shared memory = the largest tile's records (capped) +
+     the seed cells under a tile's rectangle (16-bit, relative to the tile's first slot) + a dense
+     position list per warp */
+  int threads = R->tile_threads < 32 ? 32 : (R->tile_threads > GSI_TILE_THREADS ? GSI_TILE_THREADS : R->tile_threads);
+  threads &= ~31;
+  const int wpc = threads / 32;
+  gsi_tile_args A;
+  A.M = M;
+  A.bx = R->bx; A.by = R->by; A.bi = R->bi; A.runs = R->runs; A.work = R->work;
+  A.n_chunks = (unsigned) n_chunks;
+  A.S = S; A.nt = nt;
+  A.seed_pitch = (V.grid_g >> M.bx_bits) + 4;
+  A.seed_rows = (V.grid_g >> M.by_bits) + 4;
+  const size_t budget = 227 * 1024 - 512;
+  const size_t spos_bytes = (size_t) wpc * GSI_TILE_SPOS * 4;
+  size_t seed_bytes = (size_t) A.seed_pitch * A.seed_rows * 2;
+  if (seed_bytes + spos_bytes + 4096 > budget)
     {
-      cudaFuncSetAttribute(k_tile_locate_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget);
-      cudaFuncSetAttribute(k_tile_locate_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget);
-      if (cfg.stats)
-        k_tile_locate_smem<true><<<nt * ranges, GSI_TILE_THREADS, smem_tile, st>>>(
-            V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, leaf_cap, seed_rows, seed_pitch, zb,
-            lb, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
-      else
-        k_tile_locate_smem<false><<<nt * ranges, GSI_TILE_THREADS, smem_tile, st>>>(
-            V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, leaf_cap, seed_rows, seed_pitch, zb,
-            lb, R->cap, cfg.list, list_cap, cfg.ovf_mask, cfg.counters, cfg.max_steps);
+      /* a grid far finer than the tiles (explicit "grid_g"): seeds come from global memory */
+      A.seed_pitch = A.seed_rows = 0;
+      seed_bytes = 0;
     }
-  else if (cfg.stats)
-    k_tile_locate<true><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
-        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, zb, lb, R->cap, cfg.list, list_cap,
-        cfg.ovf_mask, cfg.counters, cfg.max_steps);
-  else
-    k_tile_locate<false><<<nt * ranges, GSI_TILE_THREADS, 0, st>>>(
-        V, R->bx, R->by, R->bi, R->off, (unsigned) n_chunks, S, nt, ranges, zb, lb, R->cap, cfg.list, list_cap,
-        cfg.ovf_mask, cfg.counters, cfg.max_steps);
+  int leaf_cap = R->tile_max_leaves < 1 ? 1 : R->tile_max_leaves;
+  const size_t room = (budget - seed_bytes - spos_bytes - 16) / 96;
+  if ((size_t) leaf_cap > room) leaf_cap = (int) room;
+  if (leaf_cap > 65000) leaf_cap = 65000; /* 16-bit relative seeds */
+  A.leaf_cap = leaf_cap;
+  const size_t smem_tile = (((size_t) leaf_cap * 96 + seed_bytes + 15) & ~(size_t) 15) + spos_bytes;
+  /* work items per tile: a few dozen items per CTA for balance, at least two 32-chunk blocks per warp */
+  const size_t n_blocks = (n_chunks + 31) / 32;
+  int ranges = R->ranges;
+  if (ranges <= 0) ranges = (24 * cfg.sm_count + nt - 1) / nt;
+  const int ranges_max = (int) (n_blocks / (size_t) (2 * wpc));
+  if (ranges > ranges_max) ranges = ranges_max;
+  if (ranges < 1) ranges = 1;
+  A.ranges = ranges;
+  A.zb = val ? R->zb : nullptr;
+  A.lb = leaf_out ? R->lb : nullptr;
+  A.ldb = R->cap;
+  A.list = cfg.list; A.list_cap = list_cap; A.ovf_mask = cfg.ovf_mask; A.counters = cfg.counters;
+  A.max_steps = cfg.max_steps;
+  cudaMemsetAsync(R->work, 0, sizeof(unsigned), st);
+  const unsigned n_items = (unsigned) nt * (unsigned) ranges;
+  const int g_tile = (int) (n_items < (unsigned) cfg.sm_count ? n_items : (unsigned) cfg.sm_count);
+#define GSI_LAUNCH_TILE(STATS, ONE)                                                             \
+  do                                                                                            \
+    {                                                                                           \
+      cudaFuncSetAttribute(k_tile_walk<STATS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); \
+      k_tile_walk<STATS, ONE><<<g_tile, threads, smem_tile, st>>>(V, A);                        \
+    }                                                                                           \
+  while (0)
+  if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_TILE(true, true);
+  else if (cfg.stats) GSI_LAUNCH_TILE(true, false);
+  else if (V.n_fields == 1) GSI_LAUNCH_TILE(false, true);
+  else GSI_LAUNCH_TILE(false, false);
+#undef GSI_LAUNCH_TILE
   const int g_unp = (int) (n_chunks < (size_t) (2 * cfg.sm_count) ? n_chunks : (size_t) (2 * cfg.sm_count));
   k_unpermute<<<g_unp, GSI_UNPERMUTE_THREADS, smem_unp, st>>>(R->zb, R->lb, R->bi, nq, S, V.n_fields, R->cap, val, ld,
                                                               leaf_out);
@@ -1182,5 +1274,15 @@ gsi_launch_compare(const int *leaf_a, const int *leaf_b, const double *val_a, co
   if (m == 0) return cudaSuccess;
   k_compare<<<grid_for(m, 256, sm_count, 8), 256, 0, st>>>(leaf_a, leaf_b, val_a, val_b, n, n_val,
                                                            out2);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_validate_slab(const gsi_view &V, unsigned long long *bad, int sm_count, cudaStream_t st)
+{
+  cudaError_t e = cudaMemsetAsync(bad, 0, sizeof *bad, st);
+  if (e != cudaSuccess) return e;
+  const unsigned long long n_points = V.n_points;
+  k_validate_slab<<<grid_for((size_t) V.n_dag, 256, sm_count, 8), 256, 0, st>>>(V, n_points, bad);
   return cudaGetLastError();
 }

@@ -12,8 +12,9 @@
 #define GSI_WALK_THREADS 128
 #define GSI_BIN_THREADS 512        /* k_bin: one CTA sorts one chunk in shared memory, two CTAs per SM */
 #define GSI_UNPERMUTE_THREADS 1024 /* k_unpermute */
-#define GSI_BIN_CHUNK_MAX 8192  /* queries per chunk (16-bit in-chunk indices, 160 KB of shared memory) */
-#define GSI_TILE_THREADS 512    /* k_tile_locate */
+#define GSI_BIN_CHUNK_MAX 8192  /* queries per chunk (16-bit in-chunk indices, 96 KB of shared memory) */
+#define GSI_TILE_THREADS 768    /* k_tile_walk: one persistent CTA per SM, 24 warps, <= 85 registers */
+#define GSI_TILE_SPOS 256       /* k_tile_walk: entries of a warp's dense position list */
 
 /* device counters (unsigned[16]) */
 #define GSI_CNT_DEFERRED 0       /* u32: length of the deferred list of the current launch */
@@ -30,24 +31,26 @@
 #define GSI_KERNEL_SIMPLE 1 /* k_locate: one thread per query, two-phase (coherent query sets) */
 #define GSI_KERNEL_AUTO 2   /* k_walk for query arrays, k_locate for rasters (default) */
 
-/* Scratch of the reorder pipeline (k_bin -> k_tile_locate -> k_unpermute), one per replica.
- * Queries are processed in windows of `cap` queries; a window is cut into chunks of `chunk`
- * consecutive queries and every chunk is sorted by spatial tile (Morton-key prefix, the tiles of
- * the slab's tile table) inside shared memory, so both the reorder and its inverse
- * are chunk-local permutations with coalesced global traffic. */
+/* Scratch of the reorder pipeline (k_bin -> k_tile_walk -> k_unpermute), one per evaluation
+ * context.  Queries are processed in windows of `cap` queries; a window is cut into chunks of
+ * `chunk` consecutive queries and every chunk is counting-sorted by spatial tile (Morton-key
+ * prefix, the tiles of the slab's tile table) inside shared memory, so both the reorder and its
+ * inverse are chunk-local permutations with coalesced global traffic. */
 struct gsi_reorder_scratch
 {
   double *bx = nullptr, *by = nullptr; /* query coordinates, tile order inside every chunk */
   unsigned short *bi = nullptr;        /* position of the binned query inside its chunk */
-  unsigned short *off = nullptr;       /* [n_chunks][nt + 2]: first binned slot of every tile's
-                                          run inside the chunk; entry nt = chunk length */
+  unsigned *runs = nullptr;            /* [n_bins][n_chunks] (bin-major, so the tile kernel reads one
+                                          contiguous row per tile): start | end << 16 of the bin's run
+                                          inside the chunk */
+  unsigned *work = nullptr;            /* dynamic work counter of the tile kernel */
   double *zb = nullptr;                /* results in binned order, field-major, ld = cap */
   int *lb = nullptr;
   size_t cap = 0;     /* queries per window */
   int chunk = 0;      /* queries per chunk */
   int tile_max_leaves = 0; /* leaves of the largest tile (slab header): size of the staging area */
-  int tile_smem = 1;  /* 1 = k_tile_locate_smem (tile staged in shared memory), 0 = k_tile_locate (L1) */
-  int ranges = 4;     /* tile-kernel CTAs per tile, each taking a share of the chunks */
+  int ranges = 0;     /* tile-kernel work items per tile (0 = derive from the launch size) */
+  int tile_threads = GSI_TILE_THREADS;
 };
 
 struct gsi_launch_cfg
@@ -88,6 +91,9 @@ cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_coun
 /* fill the entry section (per-cell start node of the exact replay); run before the seeding */
 cudaError_t gsi_launch_entry_cells(const gsi_view &V, int32_t *entry, int sm_count,
                                    cudaStream_t st);
+
+/* count out-of-range indices in an adopted slab image (*bad, device memory) */
+cudaError_t gsi_launch_validate_slab(const gsi_view &V, unsigned long long *bad, int sm_count, cudaStream_t st);
 
 cudaError_t gsi_launch_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo,
                                    double xhi, double ylo, double yhi, double *xq, double *yq,

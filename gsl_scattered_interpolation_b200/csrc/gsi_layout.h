@@ -111,6 +111,7 @@ typedef struct
   int32_t n_dag;
   int32_t n_leaves;
   int32_t leaf_stride;
+  uint64_t n_points;
 } gsi_view;
 
 #if defined(__CUDACC__)
@@ -144,6 +145,7 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   v.n_fields = (int32_t) h->n_fields;
   v.n_dag = (int32_t) h->n_dag;
   v.n_leaves = (int32_t) h->n_leaves;
+  v.n_points = h->n_points;
   return v;
 }
 

@@ -90,14 +90,16 @@ int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_
  * Exact replay: "exact_entry" (1 = start at the grid cell's certified entry node, default;
  * 0 = at the root; may be changed at any time).
  * Reorder pipeline for incoherent query arrays (chunk-local counting sort by spatial tile ->
- * tile-major walk -> inverse permutation): "reorder" (0 = off, default; 1 = always; 2 = large
- * few-field batches on triangulations beyond the L2), "reorder_window" (queries per window,
- * default 2^27), "reorder_chunk" (queries per sorted chunk, <= 8192), "reorder_min",
- * "reorder_max_fields", "tile_leaves" (target leaves per Morton-prefix tile, default 1000; fixed
- * at init/upload), "tile_smem" (1 = stage the tile's leaf records and seed cells in shared
- * memory, default; 0 = read them through L1), "tile_ranges" (CTAs per tile, default 4).
- * Calls on one workspace share per-replica scratch (deferred list, counters, reorder buffers):
- * issue them on one stream at a time per device. */
+ * tile-major walk out of TMA-staged shared memory -> inverse permutation): "reorder" (0 = off,
+ * 1 = always, 2 = auto, default: batches of at least "reorder_min" queries (2^24) with at most
+ * "reorder_max_fields" fields (2) on triangulations of at least "reorder_min_leaves" leaves
+ * (600000: leaf records beyond the reach of the L2)), "reorder_window" (queries per window,
+ * default 2^27), "reorder_chunk" (queries per sorted chunk, <= 8192), "tile_leaves" (target
+ * leaves per Morton-prefix tile, default 1000; fixed at init/upload), "tile_ranges" (work items
+ * per tile, 0 = derived from the launch size), "tile_threads" (threads of the tile kernel's CTA).
+ * Host pipeline: "copy_threads" (host threads that move pageable caller arrays through pinned
+ * staging, default 4), "pageable_min" (smaller pageable batches go straight to cudaMemcpyAsync).
+ * Parameters are read when a call starts: change them between calls, not during one. */
 int gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double value);
 
 /* order[] for init: what gsl_ran_shuffle(rng, shuffle, n, sizeof(size_t)) leaves in
@@ -182,6 +184,7 @@ typedef struct
   double locate_seconds;   /* device time in the fast-path kernel (only with param "profile") */
   double exact_seconds;    /* device time in the exact-replay kernel (only with param "profile") */
   gsl_scattered_cuda_u64 n_reordered; /* queries that went through the reorder pipeline since reset */
+  size_t n_contexts;       /* evaluation contexts created so far (one per concurrent eval call and device) */
 } gsl_scattered_cuda_info;
 int gsl_scattered_cuda_get_info(const gsl_scattered_cuda *w, gsl_scattered_cuda_info *info);
 int gsl_scattered_cuda_reset_counters(const gsl_scattered_cuda *w);

@@ -407,15 +407,15 @@ def test_million_nodes_properties():
 
 # ---- reorder pipeline (k_bin -> k_tile_locate -> k_unpermute) -------------------------------
 
-@pytest.mark.parametrize("chunk,tile_leaves,smem", [(8192, 1000, 1), (8192, 3, 1), (4096, 40, 1), (96, 10, 1), (1024, 100000, 1),
-                                                    (8192, 1000, 0), (96, 3, 0)])
-def test_reorder_pipeline_on_the_golden_sets(golden, chunk, tile_leaves, smem):
+@pytest.mark.parametrize("chunk,tile_leaves,threads", [(8192, 1000, 768), (8192, 3, 768), (4096, 40, 768), (96, 10, 768),
+                                                       (1024, 100000, 768), (8192, 1000, 64), (96, 3, 32)])
+def test_reorder_pipeline_on_the_golden_sets(golden, chunk, tile_leaves, threads):
     """Forced reorder (param reorder=1) on config 1 and on the config-3 mix (3 fields, on-edge /
     on-vertex / outside-hull queries that are deferred to the exact replay): every chunk size, tile
-    size (staging area smaller or larger than the tiles) and both tile kernels must give the reference's leaf ids and value bits."""
+    size (one tile for everything, tiles of a handful of leaves) and CTA shape of the tile kernel must give the reference's leaf ids and value bits."""
     xa, ya = synth.uniform_nodes(1000)
     w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
-             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_smem=smem)
+             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_threads=threads)
     xq, yq = synth.uniform_queries(10000)
     st, zq, leaf = w.eval_e(xq, yq)
     assert st == g.SUCCESS
@@ -431,7 +431,7 @@ def test_reorder_pipeline_on_the_golden_sets(golden, chunk, tile_leaves, smem):
     n = 3000
     xa, ya = synth.clustered_nodes(n)
     w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n),
-             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_smem=smem)
+             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_threads=threads)
     xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
     st, zq, leaf = w.eval_e(xq, yq)
     assert st == g.SUCCESS
