@@ -33,6 +33,21 @@ class Info(ctypes.Structure):
 
 ERROR_HANDLER = ctypes.CFUNCTYPE(None, c_char_p, c_char_p, c_int, c_int)
 
+_BATCH_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
+
+
+class TypeDescriptor(ctypes.Structure):
+    """gsl_scattered_cuda_type (include/gsl_scattered_cuda.h), cf. gsl_interp2d_type"""
+    _fields_ = [
+        ("name", c_char_p), ("min_size", ctypes.c_uint),
+        ("alloc", ctypes.CFUNCTYPE(c_void_p, c_size_t, c_size_t)),
+        ("init", ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p)),
+        ("eval_e", ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p)),
+        ("eval_deriv_x_e", _BATCH_FN), ("eval_deriv_y_e", _BATCH_FN), ("eval_deriv_xx_e", _BATCH_FN),
+        ("eval_deriv_xy_e", _BATCH_FN), ("eval_deriv_yy_e", _BATCH_FN),
+        ("free", ctypes.CFUNCTYPE(None, c_void_p)),
+    ]
+
 _PROTOS = {
     "gsl_scattered_cuda_version": (c_char_p, []),
     "gsl_scattered_cuda_set_error_handler": (c_void_p, [c_void_p]),
@@ -59,6 +74,20 @@ _PROTOS = {
     "gsl_scattered_cuda_eval_raster_device_e": (c_int, [c_void_p, c_int, c_double, c_double,
                                                         c_size_t, c_double, c_double, c_size_t,
                                                         c_void_p, c_void_p, c_void_p]),
+    "gsl_scattered_cuda_eval_deriv_e": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gsl_scattered_cuda_eval_deriv_x_e": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gsl_scattered_cuda_eval_deriv_y_e": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gsl_scattered_cuda_eval_deriv_xx_e": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gsl_scattered_cuda_eval_deriv_yy_e": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gsl_scattered_cuda_eval_deriv_xy_e": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gsl_scattered_cuda_eval_deriv_x": (c_double, [c_void_p, c_double, c_double]),
+    "gsl_scattered_cuda_eval_deriv_y": (c_double, [c_void_p, c_double, c_double]),
+    "gsl_scattered_cuda_eval_deriv_device_e": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p,
+                                                       c_void_p, c_size_t, c_void_p, c_void_p]),
+    "gsl_scattered_cuda_type_linear_simplex": (c_void_p, []),
+    "gsl_scattered_cuda_name": (c_char_p, [c_void_p]),
+    "gsl_scattered_cuda_min_size": (ctypes.c_uint, [c_void_p]),
+    "gsl_scattered_cuda_type_min_size": (ctypes.c_uint, [c_void_p]),
     "gsl_scattered_cuda_get_info": (c_int, [c_void_p, POINTER(Info)]),
     "gsl_scattered_cuda_reset_counters": (c_int, [c_void_p]),
     "gsl_scattered_cuda_get_tree": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

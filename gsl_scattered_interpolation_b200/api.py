@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import (DEFAULT, EBADLEN, EDOM, EFAILED, EINVAL, ENOMEM, ISOSCALE, NOSTANDARDIZE,
                    SUCCESS, Info)
 
-__all__ = ["ScatteredCuda", "GslError", "shuffle_mt19937", "device_count", "generate_uniform_host",
+__all__ = ["ScatteredCuda", "GslError", "shuffle_mt19937", "device_count", "generate_uniform_host", "type_descriptor",
            "SUCCESS", "EDOM", "EINVAL", "EFAILED", "ENOMEM", "EBADLEN", "DEFAULT",
            "NOSTANDARDIZE", "ISOSCALE"]
 
@@ -45,6 +45,12 @@ def shuffle_mt19937(seed, n):
     if st:
         raise GslError(st, "shuffle_mt19937")
     return order
+
+
+def type_descriptor():
+    """the gsl_scattered_cuda_type of the library (cf. gsl_interp2d_bilinear)"""
+    p = _lib.load().gsl_scattered_cuda_type_linear_simplex()
+    return ctypes.cast(p, ctypes.POINTER(_lib.TypeDescriptor)).contents
 
 
 def generate_uniform_host(seed, first, nq, xlo, xhi, ylo, yhi):
@@ -160,6 +166,42 @@ class ScatteredCuda:
                                                       _ptr(leaf))
         self._check(st, "eval_raster_e", allow=(EDOM,))
         return st, zq, leaf
+
+    # -- derivatives (gsl_interp2d's eval_deriv_x / eval_deriv_y for the scattered method) ----
+    def eval_deriv_e(self, xq, yq, want_x=True, want_y=True):
+        """Returns (status, dzdx[n_fields, nq] | None, dzdy[n_fields, nq] | None)."""
+        xq, yq = _f64(xq), _f64(yq)
+        nq = xq.size
+        dx = np.empty((self.n_fields, nq), dtype=np.float64) if want_x else None
+        dy = np.empty((self.n_fields, nq), dtype=np.float64) if want_y else None
+        st = self._L.gsl_scattered_cuda_eval_deriv_e(self._w, _ptr(xq), _ptr(yq), nq, _ptr(dx), _ptr(dy))
+        self._check(st, "eval_deriv_e", allow=(EDOM,))
+        return st, dx, dy
+
+    def eval_deriv2_e(self, xq, yq, which="xx"):
+        xq, yq = _f64(xq), _f64(yq)
+        d = np.empty((self.n_fields, xq.size), dtype=np.float64)
+        fn = getattr(self._L, f"gsl_scattered_cuda_eval_deriv_{which}_e")
+        st = fn(self._w, _ptr(xq), _ptr(yq), xq.size, _ptr(d))
+        self._check(st, f"eval_deriv_{which}_e", allow=(EDOM,))
+        return st, d
+
+    def eval_deriv_x(self, x, y):
+        return self._L.gsl_scattered_cuda_eval_deriv_x(self._w, float(x), float(y))
+
+    def eval_deriv_y(self, x, y):
+        return self._L.gsl_scattered_cuda_eval_deriv_y(self._w, float(x), float(y))
+
+    def eval_deriv_device_e(self, dev, d_xq, d_yq, nq, d_dzdx, d_dzdy, ld, d_leaf=None, stream=None):
+        st = self._L.gsl_scattered_cuda_eval_deriv_device_e(self._w, dev, d_xq, d_yq, nq, d_dzdx, d_dzdy, ld,
+                                                            d_leaf, stream)
+        return self._check(st, "eval_deriv_device_e", allow=(EDOM,))
+
+    def name(self):
+        return self._L.gsl_scattered_cuda_name(self._w).decode()
+
+    def min_size(self):
+        return int(self._L.gsl_scattered_cuda_min_size(self._w))
 
     # -- eval (device buffers) --------------------------------------------------------------
     def eval_device_e(self, dev, d_xq, d_yq, nq, d_zq, ld, d_leaf, stream=None):

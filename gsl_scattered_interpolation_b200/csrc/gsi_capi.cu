@@ -1764,3 +1764,239 @@ gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, const in
 }
 
 } /* extern "C" */
+
+/* ---- derivatives and the type descriptor --------------------------------------------------- */
+namespace
+{
+
+/* locate (leaf ids only) + gradient kernel on device data, all on stream st; d_leaf is scratch of
+ * nq ints (caller's or the context's) */
+int
+deriv_on_device(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, const double *d_x, const double *d_y,
+                size_t nq, double *d_dzdx, double *d_dzdy, size_t ld, int *d_leaf, cudaStream_t st)
+{
+  int s = eval_on_device(w, r, c, d_x, d_y, nullptr, nq, nullptr, 0, d_leaf, st);
+  if (s) return s;
+  CU(gsi_launch_deriv(r->view, d_leaf, nq, d_dzdx, d_dzdy, ld, r->sm_count, st));
+  c->n_launches += 1;
+  return 0;
+}
+
+/* host arrays through the context's device staging, chunk by chunk (not the hot path: plain
+ * synchronous copies).  order: 1 = first derivatives, 2 = second derivatives (zero inside the
+ * cage, NaN outside) written to dzdx */
+int
+deriv_host(const gsl_scattered_cuda *w, const double *xq, const double *yq, size_t nq, double *dzdx, double *dzdy,
+           int order)
+{
+  if (!w || !w->uploaded || w->reps.empty())
+    GSI_ERROR("workspace not initialised on a GPU", GSL_SCATTERED_EFAILED);
+  if (nq && (!xq || !yq)) GSI_ERROR("null query array", GSL_SCATTERED_EINVAL);
+  if (nq == 0) return GSL_SCATTERED_SUCCESS;
+  device_guard restore;
+  replica *r = w->reps[0];
+  CU(cudaSetDevice(r->dev));
+  ctx_lease lease(r, nullptr);
+  if (lease.status) return lease.status;
+  eval_ctx *c = lease.c;
+  const size_t F = w->n_fields;
+  const size_t C = std::max<size_t>(1, std::min(w->host_chunk, nq));
+  int s = ensure_stage(c, C, F);
+  if (s) return s;
+  unsigned c0[GSI_CNT_WORDS], c1[GSI_CNT_WORDS];
+  CU(cudaStreamSynchronize(c->s_k));
+  if ((s = read_counters(c, c0))) return s;
+  std::vector<int> hl;
+  if (order == 2) hl.resize(C);
+  for (size_t off = 0; off < nq; off += C)
+    {
+      const size_t n = std::min(C, nq - off);
+      stage_buf &a = c->st[0], &b = c->st[1];
+      CU(cudaMemcpyAsync(a.x, xq + off, n * sizeof(double), cudaMemcpyHostToDevice, c->s_k));
+      CU(cudaMemcpyAsync(a.y, yq + off, n * sizeof(double), cudaMemcpyHostToDevice, c->s_k));
+      if (order == 1)
+        {
+          s = deriv_on_device(w, r, c, a.x, a.y, n, dzdx ? a.z : nullptr, dzdy ? b.z : nullptr, C, a.leaf, c->s_k);
+          if (s) return s;
+          for (size_t f = 0; f < F; f++)
+            {
+              if (dzdx) CU(cudaMemcpyAsync(dzdx + f * nq + off, a.z + f * C, n * sizeof(double), cudaMemcpyDeviceToHost, c->s_k));
+              if (dzdy) CU(cudaMemcpyAsync(dzdy + f * nq + off, b.z + f * C, n * sizeof(double), cudaMemcpyDeviceToHost, c->s_k));
+            }
+          CU(cudaStreamSynchronize(c->s_k));
+        }
+      else
+        {
+          s = eval_on_device(w, r, c, a.x, a.y, nullptr, n, nullptr, 0, a.leaf, c->s_k);
+          if (s) return s;
+          CU(cudaMemcpyAsync(hl.data(), a.leaf, n * sizeof(int), cudaMemcpyDeviceToHost, c->s_k));
+          CU(cudaStreamSynchronize(c->s_k));
+          if (dzdx)
+            for (size_t f = 0; f < F; f++)
+              for (size_t q = 0; q < n; q++)
+                dzdx[f * nq + off + q] = hl[q] >= 0 ? 0.0 : std::numeric_limits<double>::quiet_NaN();
+        }
+    }
+  if ((s = read_counters(c, c1))) return s;
+  if (c1[GSI_CNT_OUTSIDE] != c0[GSI_CNT_OUTSIDE])
+    GSI_ERROR("query point outside the domain (cage)", GSL_SCATTERED_EDOM);
+  return GSL_SCATTERED_SUCCESS;
+}
+
+const gsl_scattered_cuda_type linear_simplex_type = {
+    "linear-simplex-cuda",
+    3,
+    &gsl_scattered_cuda_alloc,
+    &gsl_scattered_cuda_init,
+    &gsl_scattered_cuda_eval_e,
+    &gsl_scattered_cuda_eval_deriv_x_e,
+    &gsl_scattered_cuda_eval_deriv_y_e,
+    &gsl_scattered_cuda_eval_deriv_xx_e,
+    &gsl_scattered_cuda_eval_deriv_xy_e,
+    &gsl_scattered_cuda_eval_deriv_yy_e,
+    &gsl_scattered_cuda_free,
+};
+
+} // namespace
+
+extern "C" {
+
+const gsl_scattered_cuda_type *gsl_scattered_cuda_linear_simplex = &linear_simplex_type;
+
+const gsl_scattered_cuda_type *
+gsl_scattered_cuda_type_linear_simplex(void)
+{
+  return &linear_simplex_type;
+}
+
+const char *
+gsl_scattered_cuda_name(const gsl_scattered_cuda *w)
+{
+  (void) w;
+  return linear_simplex_type.name;
+}
+
+unsigned int
+gsl_scattered_cuda_min_size(const gsl_scattered_cuda *w)
+{
+  (void) w;
+  return linear_simplex_type.min_size;
+}
+
+unsigned int
+gsl_scattered_cuda_type_min_size(const gsl_scattered_cuda_type *T)
+{
+  return T ? T->min_size : 0;
+}
+
+int
+gsl_scattered_cuda_eval_deriv_e(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq,
+                                double dzdx[], double dzdy[])
+{
+  GSI_GUARD_BEGIN
+  return deriv_host(w, xq, yq, nq, dzdx, dzdy, 1);
+  GSI_GUARD_END
+}
+
+int
+gsl_scattered_cuda_eval_deriv_x_e(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[])
+{
+  return gsl_scattered_cuda_eval_deriv_e(w, xq, yq, nq, d, nullptr);
+}
+
+int
+gsl_scattered_cuda_eval_deriv_y_e(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[])
+{
+  return gsl_scattered_cuda_eval_deriv_e(w, xq, yq, nq, nullptr, d);
+}
+
+int
+gsl_scattered_cuda_eval_deriv_xx_e(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[])
+{
+  GSI_GUARD_BEGIN
+  return deriv_host(w, xq, yq, nq, d, nullptr, 2);
+  GSI_GUARD_END
+}
+
+int
+gsl_scattered_cuda_eval_deriv_yy_e(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[])
+{
+  return gsl_scattered_cuda_eval_deriv_xx_e(w, xq, yq, nq, d);
+}
+
+int
+gsl_scattered_cuda_eval_deriv_xy_e(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[])
+{
+  return gsl_scattered_cuda_eval_deriv_xx_e(w, xq, yq, nq, d);
+}
+
+double
+gsl_scattered_cuda_eval_deriv_x(const gsl_scattered_cuda *w, double x, double y)
+{
+  try
+    {
+      std::vector<double> d(w ? w->n_fields : 1, std::numeric_limits<double>::quiet_NaN());
+      const int s = deriv_host(w, &x, &y, 1, d.data(), nullptr, 1);
+      return (s == GSL_SCATTERED_SUCCESS || s == GSL_SCATTERED_EDOM) ? d[0] : std::numeric_limits<double>::quiet_NaN();
+    }
+  catch (...)
+    {
+      report("internal error (C++ exception)", __FILE__, __LINE__, GSL_SCATTERED_EFAILED);
+      return std::numeric_limits<double>::quiet_NaN();
+    }
+}
+
+double
+gsl_scattered_cuda_eval_deriv_y(const gsl_scattered_cuda *w, double x, double y)
+{
+  try
+    {
+      std::vector<double> d(w ? w->n_fields : 1, std::numeric_limits<double>::quiet_NaN());
+      const int s = deriv_host(w, &x, &y, 1, nullptr, d.data(), 1);
+      return (s == GSL_SCATTERED_SUCCESS || s == GSL_SCATTERED_EDOM) ? d[0] : std::numeric_limits<double>::quiet_NaN();
+    }
+  catch (...)
+    {
+      report("internal error (C++ exception)", __FILE__, __LINE__, GSL_SCATTERED_EFAILED);
+      return std::numeric_limits<double>::quiet_NaN();
+    }
+}
+
+int
+gsl_scattered_cuda_eval_deriv_device_e(const gsl_scattered_cuda *w, int dev, const double *d_xq, const double *d_yq,
+                                       size_t nq, double *d_dzdx, double *d_dzdy, size_t ld, int *d_leaf, void *stream)
+{
+  if (!w || !w->uploaded) GSI_ERROR("workspace not initialised on a GPU", GSL_SCATTERED_EFAILED);
+  replica *r = find_replica(w, dev);
+  if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
+  if (nq && (!d_xq || !d_yq)) GSI_ERROR("null query array", GSL_SCATTERED_EINVAL);
+  if ((d_dzdx || d_dzdy) && ld < nq) GSI_ERROR("ld < nq", GSL_SCATTERED_EBADLEN);
+  if (nq == 0) return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_BEGIN
+  device_guard restore;
+  CU(cudaSetDevice(dev));
+  ctx_lease lease(r, (cudaStream_t) stream);
+  if (lease.status) return lease.status;
+  eval_ctx *c = lease.c;
+  int s;
+  if (!d_leaf)
+    {
+      /* the context's staging holds the leaf ids: fixed-size pieces */
+      const size_t C = std::max<size_t>(1, std::min(w->host_chunk, nq));
+      if ((s = ensure_stage(c, C, w->n_fields))) return s;
+      for (size_t off = 0; off < nq; off += C)
+        {
+          const size_t n = std::min(C, nq - off);
+          s = deriv_on_device(w, r, c, d_xq + off, d_yq + off, n, d_dzdx ? d_dzdx + off : nullptr,
+                              d_dzdy ? d_dzdy + off : nullptr, ld, c->st[0].leaf, lease.st);
+          if (s) return s;
+        }
+    }
+  else if ((s = deriv_on_device(w, r, c, d_xq, d_yq, nq, d_dzdx, d_dzdy, ld, d_leaf, lease.st)))
+    return s;
+  if (!stream) CU(cudaStreamSynchronize(lease.st));
+  return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
+}
+
+} /* extern "C" */

@@ -365,6 +365,55 @@ gsi_exact_one(const gsi_view *V, double qx, double qy, double *val, int *leaf_ou
   return slot;
 }
 
+/* Gradient of the interpolant on the leaf with reference node id `node` (as returned by the
+ * locate kernels; < 0 = outside the cage): writes d/dx and d/dy of every field, field-major
+ * (out[f*ld + q]); NaN outside the cage and on singular leaves (where gsl_linalg_LU_solve raises
+ * GSL_EDOM, linalg/lu.c:145-148).  Either output may be NULL. */
+GSI_HD void
+gsi_deriv_one(const gsi_view *V, int node, double *dzdx, double *dzdy, size_t ld, size_t q)
+{
+  const int F = V->n_fields;
+  gsi_rec r;
+  int ok = node >= 0 && node < V->n_dag;
+  if (ok)
+    {
+      gsi_fetch_rec(&r, V->dag + node);
+      ok = (r.meta & GSI_META_TYPE_MASK) == GSI_LEAF && !(r.meta & GSI_META_SINGULAR);
+    }
+  if (!ok)
+    {
+      for (int f = 0; f < F; f++)
+        {
+          if (dzdx) dzdx[(size_t) f * ld + q] = GSI_NAN;
+          if (dzdy) dzdy[(size_t) f * ld + q] = GSI_NAN;
+        }
+      return;
+    }
+  const int swap = (int) (r.meta & GSI_META_SWAP);
+  double ax, bx, ay, by; /* d(c0, c1)/dx and d(c0, c1)/dy */
+  gsi_solve_rhs(&r, swap, V->xf.sx, 0.0, &ax, &bx);
+  gsi_solve_rhs(&r, swap, 0.0, V->xf.sy, &ay, &by);
+  gsi_leaf_tail t;
+  gsi_fetch_tail(&t, gsi_leaf_at(V, r.lnk[0]));
+  if (F == 1)
+    {
+      const int ha = (int) (t.s.vflags & 1u), hb = (int) (t.s.vflags & 2u), hx = (int) (t.s.vflags & 4u);
+      if (dzdx) dzdx[q] = gsi_blend_deriv(ax, bx, ha, t.s.z[0], hb, t.s.z[1], hx, t.s.z[2]);
+      if (dzdy) dzdy[q] = gsi_blend_deriv(ay, by, ha, t.s.z[0], hb, t.s.z[1], hx, t.s.z[2]);
+      return;
+    }
+  const int ha = t.g.v[0] >= 0, hb = t.g.v[1] >= 0, hx = t.g.v[2] >= 0;
+  const double *za = V->z + (size_t) (ha ? t.g.v[0] : 0) * F;
+  const double *zb = V->z + (size_t) (hb ? t.g.v[1] : 0) * F;
+  const double *zx = V->z + (size_t) (hx ? t.g.v[2] : 0) * F;
+  for (int f = 0; f < F; f++)
+    {
+      const double a = ha ? GSI_LDG(za + f) : 0.0, b = hb ? GSI_LDG(zb + f) : 0.0, x = hx ? GSI_LDG(zx + f) : 0.0;
+      if (dzdx) dzdx[(size_t) f * ld + q] = gsi_blend_deriv(ax, bx, ha, a, hb, b, hx, x);
+      if (dzdy) dzdy[(size_t) f * ld + q] = gsi_blend_deriv(ay, by, ha, a, hb, b, hx, x);
+    }
+}
+
 #define GSI_STEP_ACCEPT 0 /* strictly inside with margin: the leaf is the answer */
 #define GSI_STEP_MOVE 1   /* clearly outside across one edge: *slot = neighbour */
 #define GSI_STEP_DEFER 2  /* cannot be proven here: exact replay decides */

@@ -914,6 +914,15 @@ k_unpermute(const double *__restrict__ zb, const int *__restrict__ lb, const uns
     }
 }
 
+/* derivative evaluators: gradient of the leaf's plane for leaf ids produced by a locate pass */
+__global__ void __launch_bounds__(256)
+k_deriv(const gsi_view V, const int *__restrict__ leaf, size_t nq, double *dzdx, double *dzdy, size_t ld)
+{
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride)
+    gsi_deriv_one(&V, __ldg(leaf + q), dzdx, dzdy, ld, q);
+}
+
 /* ---- synthetic inputs / verification helpers ------------------------------------------------ */
 __global__ void __launch_bounds__(256)
 k_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo, double xw, double ylo,
@@ -1284,5 +1293,14 @@ gsi_launch_validate_slab(const gsi_view &V, unsigned long long *bad, int sm_coun
   if (e != cudaSuccess) return e;
   const unsigned long long n_points = V.n_points;
   k_validate_slab<<<grid_for((size_t) V.n_dag, 256, sm_count, 8), 256, 0, st>>>(V, n_points, bad);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_deriv(const gsi_view &V, const int *leaf, size_t nq, double *dzdx, double *dzdy, size_t ld, int sm_count,
+                 cudaStream_t st)
+{
+  if (nq == 0) return cudaSuccess;
+  k_deriv<<<grid_for(nq, 256, sm_count, 8), 256, 0, st>>>(V, leaf, nq, dzdx, dzdy, ld);
   return cudaGetLastError();
 }

@@ -92,6 +92,11 @@ cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_coun
 cudaError_t gsi_launch_entry_cells(const gsi_view &V, int32_t *entry, int sm_count,
                                    cudaStream_t st);
 
+/* gradient of the interpolant for the leaf ids of a locate pass (gsi_deriv_one); dzdx / dzdy are
+ * field-major with leading dimension ld and may each be NULL */
+cudaError_t gsi_launch_deriv(const gsi_view &V, const int *leaf, size_t nq, double *dzdx, double *dzdy, size_t ld,
+                             int sm_count, cudaStream_t st);
+
 /* count out-of-range indices in an adopted slab image (*bad, device memory) */
 cudaError_t gsi_launch_validate_slab(const gsi_view &V, unsigned long long *bad, int sm_count, cudaStream_t st);
 

@@ -164,6 +164,68 @@ int gsl_scattered_cuda_eval_raster_device_e(const gsl_scattered_cuda *w, int dev
                                             double dx, size_t nx, double y0, double dy, size_t ny,
                                             double *d_zq, int *d_leaf, void *stream);
 
+/* ---- derivatives and the type descriptor ----------------------------
+ * The counterpart of gsl_interp2d_eval_deriv_x / _y (interpolation/gsl_interp2d.h:37-49,
+ * interpolation/spline2d.c:30-110) for the scattered method.  The interpolant is affine on every
+ * leaf, so the derivatives are the (piecewise constant) gradient of the containing leaf's plane:
+ * the derivatives of the barycentric coordinates come from the same LU solve as the coordinates
+ * (calculate_bary_coords, linear_simplex.c:607-651) with right-hand side scale_k e_k, blended with
+ * the vertex values like interp_point does (linear_simplex.c:689-710: cage vertices contribute
+ * nothing, last weight 1 - tot -> 0 - tot).  The containing leaf is the one find_leaf returns,
+ * tie-breaks included.  Outside the cage and on singular leaves: NaN (status GSL_SCATTERED_EDOM
+ * for a point outside the cage).  Second derivatives are zero wherever the first exist.
+ * dzdx, dzdy: n_fields x nq, field-major, HOST arrays, either may be NULL. */
+int gsl_scattered_cuda_eval_deriv_e(const gsl_scattered_cuda *w, const double xq[], const double yq[],
+                                    size_t nq, double dzdx[], double dzdy[]);
+int gsl_scattered_cuda_eval_deriv_x_e(const gsl_scattered_cuda *w, const double xq[], const double yq[],
+                                      size_t nq, double d[]);
+int gsl_scattered_cuda_eval_deriv_y_e(const gsl_scattered_cuda *w, const double xq[], const double yq[],
+                                      size_t nq, double d[]);
+int gsl_scattered_cuda_eval_deriv_xx_e(const gsl_scattered_cuda *w, const double xq[], const double yq[],
+                                       size_t nq, double d[]);
+int gsl_scattered_cuda_eval_deriv_yy_e(const gsl_scattered_cuda *w, const double xq[], const double yq[],
+                                       size_t nq, double d[]);
+int gsl_scattered_cuda_eval_deriv_xy_e(const gsl_scattered_cuda *w, const double xq[], const double yq[],
+                                       size_t nq, double d[]);
+/* one point, field 0 */
+double gsl_scattered_cuda_eval_deriv_x(const gsl_scattered_cuda *w, double x, double y);
+double gsl_scattered_cuda_eval_deriv_y(const gsl_scattered_cuda *w, double x, double y);
+/* DEVICE pointers, asynchronous on `stream` like eval_device_e; d_leaf (nq ints) receives the
+ * containing leaves (it may be NULL: the library then uses scratch of its own). */
+int gsl_scattered_cuda_eval_deriv_device_e(const gsl_scattered_cuda *w, int dev, const double *d_xq,
+                                           const double *d_yq, size_t nq, double *d_dzdx,
+                                           double *d_dzdy, size_t ld, int *d_leaf, void *stream);
+
+/* Method descriptor in the style of gsl_interp2d_type (interpolation/gsl_interp2d.h:37-49), so
+ * that code written against "a 2-D interpolation type with alloc / init / eval / eval_deriv_* /
+ * free members" can hold the scattered GPU method next to gsl_interp2d_bilinear / _bicubic.  The
+ * members are the batched entry points above (a GPU method is called on arrays, not point by
+ * point; the one-point forms are gsl_scattered_cuda_eval / _eval_deriv_x / _eval_deriv_y). */
+typedef struct
+{
+  const char *name;
+  unsigned int min_size; /* smallest node count that yields a data triangle (fewer are accepted, as in
+                            the reference's trivial_test, and interpolate inside the cage only) */
+  gsl_scattered_cuda *(*alloc)(size_t n_nodes, size_t n_fields);
+  int (*init)(gsl_scattered_cuda *w, const double xa[], const double ya[], const double za[],
+              size_t n_nodes, int init_flags, const size_t order[]);
+  int (*eval_e)(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq,
+                double zq[], int leaf[]);
+  int (*eval_deriv_x_e)(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[]);
+  int (*eval_deriv_y_e)(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[]);
+  int (*eval_deriv_xx_e)(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[]);
+  int (*eval_deriv_xy_e)(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[]);
+  int (*eval_deriv_yy_e)(const gsl_scattered_cuda *w, const double xq[], const double yq[], size_t nq, double d[]);
+  void (*free)(gsl_scattered_cuda *w);
+} gsl_scattered_cuda_type;
+
+/* the one method of this library: piecewise-linear interpolation on the Delaunay triangulation */
+extern const gsl_scattered_cuda_type *gsl_scattered_cuda_linear_simplex;
+const gsl_scattered_cuda_type *gsl_scattered_cuda_type_linear_simplex(void); /* same, for FFI without data symbols */
+const char *gsl_scattered_cuda_name(const gsl_scattered_cuda *w);            /* cf. gsl_interp2d_name */
+unsigned int gsl_scattered_cuda_min_size(const gsl_scattered_cuda *w);       /* cf. gsl_interp2d_min_size */
+unsigned int gsl_scattered_cuda_type_min_size(const gsl_scattered_cuda_type *T);
+
 /* ---- introspection / replication / measurement helpers ------------------------------------- */
 typedef struct
 {

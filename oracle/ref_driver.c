@@ -210,6 +210,74 @@ double ref_eval_fork(const ref_handle *h, const double *xq, const double *yq, lo
   return bad ? -1.0 : dt;
 }
 
+/* Oracle-side definition of the derivative evaluators (the reference has
+ * none -- README:14 "converging to the standard GSL interpolation interface", whose 2-D types carry
+ * eval_deriv_x / eval_deriv_y, interpolation/gsl_interp2d.h:37-49).  The gradient of the leaf's
+ * barycentric plane, built only from the reference's own pieces: calculate_bary_coords
+ * (linear_simplex.c:607-651) leaves the leaf's LU factors and permutation in the accel; the
+ * derivative of the coordinates along axis k is the same gsl_linalg_LU_solve applied to
+ * d/dx_k [(point - x0) * scale] = scale_k e_k; the blend is interp_point's loop
+ * (linear_simplex.c:689-710) with d/dx_k (1 - tot) = 0 - tot.  Singular leaf or outside the
+ * cage: NaN. */
+static double deriv_point(simplex_tree *tree, simplex_index leaf, gsl_matrix *data, const double *z,
+                          gsl_vector *point, simplex_tree_accel *accel, int axis)
+{
+  double rhs_[2] = {0.0, 0.0}, dc_[2] = {0.0, 0.0};
+  gsl_vector_view rhs = gsl_vector_view_array(rhs_, 2), dc = gsl_vector_view_array(dc_, 2);
+  double tot = 0, d = 0;
+  int i, idx;
+  if (GSL_SUCCESS != calculate_bary_coords(tree, leaf, data, point, accel)) return NAN;
+  rhs_[axis] = gsl_vector_get(tree->scale, axis);
+  gsl_linalg_LU_solve(accel->simplex_matrix, accel->perm, &rhs.vector, &dc.vector);
+  for (i = 0; i < 2; i++)
+    {
+      double c = dc_[i];
+      tot += c;
+      idx = POINT(leaf, i);
+      if (idx >= 0) d += c * z[gsl_permutation_get(tree->shuffle, idx)];
+    }
+  idx = POINT(leaf, 2);
+  if (idx >= 0) d += (0.0 - tot) * z[gsl_permutation_get(tree->shuffle, idx)];
+  return d;
+}
+
+/* find_leaf + the gradient of every field; dzdx / dzdy field-major (n_fields x nq), may be NULL */
+long ref_eval_deriv(const ref_handle *h, const double *xq, const double *yq, long nq, const double *z,
+                    int n_fields, int *leaf_out, double *dzdx, double *dzdy)
+{
+  simplex_tree *tree = h->tree;
+  simplex_tree_accel *accel = simplex_tree_accel_alloc(2);
+  double pt[2];
+  gsl_vector_view point = gsl_vector_view_array(pt, 2);
+  long outside = 0, q;
+  int f;
+  for (q = 0; q < nq; q++)
+    {
+      pt[0] = xq[q];
+      pt[1] = yq[q];
+      if (!contains_point(tree, 0, h->data, &point.vector, accel))
+        {
+          outside++;
+          if (leaf_out) leaf_out[q] = -1;
+          for (f = 0; f < n_fields; f++)
+            {
+              if (dzdx) dzdx[(long)f*nq + q] = NAN;
+              if (dzdy) dzdy[(long)f*nq + q] = NAN;
+            }
+          continue;
+        }
+      simplex_index leaf = find_leaf(tree, h->data, &point.vector, accel);
+      if (leaf_out) leaf_out[q] = leaf;
+      for (f = 0; f < n_fields; f++)
+        {
+          if (dzdx) dzdx[(long)f*nq + q] = deriv_point(tree, leaf, h->data, z + (long)f*h->n, &point.vector, accel, 0);
+          if (dzdy) dzdy[(long)f*nq + q] = deriv_point(tree, leaf, h->data, z + (long)f*h->n, &point.vector, accel, 1);
+        }
+    }
+  simplex_tree_accel_free(accel);
+  return outside;
+}
+
 /* The reference's raster driver shape (scattered_interp_example.c:176-199):
  * x = x0 + dx*i (outer), y = y0 + dy*j (inner), result stored x-major [i][j].
  * Two roundings per coordinate (this file is compiled with -ffp-contract=off). */

@@ -20,6 +20,11 @@ void so_tree_free(so_tree *t);
 long so_eval(const so_tree *t, const double *xq, const double *yq, long nq, const double *z,
              int n_fields, int *leaf, double *val);
 
+/* find_leaf + the gradient of every field (definition: oracle/ref_driver.c:deriv_point);
+ * dzdx / dzdy field-major (n_fields x nq), may be NULL; NaN outside the cage / singular leaf */
+long so_eval_deriv(const so_tree *t, const double *xq, const double *yq, long nq, const double *z,
+                   int n_fields, int *leaf, double *dzdx, double *dzdy);
+
 /* per-query descent statistics: depth[q] = DAG levels, tests[q] = contains_point calls */
 long so_eval_stats(const so_tree *t, const double *xq, const double *yq, long nq, int *depth,
                    int *tests);

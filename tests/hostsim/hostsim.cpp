@@ -115,4 +115,12 @@ hostsim_eval(const hostsim *h, const double *xq, const double *yq, size_t nq, do
   stats[0] = (long long) deferred.size();
   return 0;
 }
+
+/* what k_deriv does on the device: gradient of every field for the leaf ids of a locate pass */
+int
+hostsim_deriv(const hostsim *h, const int *leaf, size_t nq, double *dzdx, double *dzdy)
+{
+  for (size_t q = 0; q < nq; q++) gsi_deriv_one(&h->view, leaf[q], dzdx, dzdy, nq, q);
+  return 0;
+}
 }

@@ -33,6 +33,7 @@ def lib():
         H.hostsim_free.argtypes = [c_void_p]
         H.hostsim_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int,
                                    c_int, c_void_p]
+        H.hostsim_deriv.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
         H.hostsim_n_leaves.restype = c_size_t
         H.hostsim_n_leaves.argtypes = [c_void_p]
         H.hostsim_grid_g.restype = c_size_t
@@ -84,3 +85,10 @@ class HostSim:
         st = (ctypes.c_longlong * 3)()
         self.H.hostsim_eval(self.h, _p(xq), _p(yq), nq, _p(zq), _p(leaf), mode, max_steps, st)
         return leaf, zq, dict(deferred=st[0], steps=st[1], outside=st[2])
+
+    def deriv(self, leaf):
+        leaf = np.ascontiguousarray(leaf, dtype=np.int32)
+        dx = np.zeros((self.F, leaf.size))
+        dy = np.zeros((self.F, leaf.size))
+        self.H.hostsim_deriv(self.h, _p(leaf), leaf.size, _p(dx), _p(dy))
+        return dx, dy

@@ -44,6 +44,10 @@ def _load_ref(path):
     L.ref_eval_raster.argtypes = [c_void_p, c_double, c_double, c_long, c_double, c_double, c_long,
                                   c_void_p, c_int, c_void_p, c_void_p]
     L.ref_weather_data.argtypes = [c_void_p]
+    if hasattr(L, "ref_eval_deriv"):
+        L.ref_eval_deriv.restype = c_long
+        L.ref_eval_deriv.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_void_p]
     return L
 
 
@@ -114,6 +118,19 @@ class RefTree:
         out = self.L.ref_eval(self.h, _p(xq), _p(yq), nq, _p(za), F, _p(leaf), _p(val))
         return leaf, val, int(out)
 
+    def eval_deriv(self, xq, yq, za):
+        """find_leaf + gradient of every field (oracle-side definition on top of the reference's
+        calculate_bary_coords + gsl_linalg_LU_solve).  Returns (leaf, dzdx[F,nq], dzdy[F,nq])."""
+        xq = np.ascontiguousarray(xq, dtype=np.float64)
+        yq = np.ascontiguousarray(yq, dtype=np.float64)
+        za = np.ascontiguousarray(np.atleast_2d(za), dtype=np.float64)
+        F, nq = za.shape[0], xq.size
+        leaf = np.empty(nq, dtype=np.int32)
+        dx = np.empty((F, nq), dtype=np.float64)
+        dy = np.empty((F, nq), dtype=np.float64)
+        self.L.ref_eval_deriv(self.h, _p(xq), _p(yq), nq, _p(za), F, _p(leaf), _p(dx), _p(dy))
+        return leaf, dx, dy
+
     def time_eval(self, xq, yq, za, nproc):
         xq = np.ascontiguousarray(xq, dtype=np.float64)
         yq = np.ascontiguousarray(yq, dtype=np.float64)
@@ -147,6 +164,9 @@ def port_lib():
         L.so_tree_free.argtypes = [c_void_p]
         L.so_eval.restype = c_long
         L.so_eval.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]
+        L.so_eval_deriv.restype = c_long
+        L.so_eval_deriv.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p]
         L.so_eval_stats.restype = c_long
         L.so_eval_stats.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p]
         _PORT = L
@@ -183,6 +203,17 @@ class PortTree:
         val = np.empty((F, nq), dtype=np.float64)
         out = self.L.so_eval(self.h, _p(xq), _p(yq), nq, _p(za), F, _p(leaf), _p(val))
         return leaf, val, int(out)
+
+    def eval_deriv(self, xq, yq, za):
+        xq = np.ascontiguousarray(xq, dtype=np.float64)
+        yq = np.ascontiguousarray(yq, dtype=np.float64)
+        za = np.ascontiguousarray(np.atleast_2d(za), dtype=np.float64)
+        F, nq = za.shape[0], xq.size
+        leaf = np.empty(nq, dtype=np.int32)
+        dx = np.empty((F, nq), dtype=np.float64)
+        dy = np.empty((F, nq), dtype=np.float64)
+        self.L.so_eval_deriv(self.h, _p(xq), _p(yq), nq, _p(za), F, _p(leaf), _p(dx), _p(dy))
+        return leaf, dx, dy
 
     def stats(self, xq, yq):
         xq = np.ascontiguousarray(xq, dtype=np.float64)
