@@ -28,6 +28,26 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 ALG_BYTES_PER_QUERY = 28          # 16 B (x, y) in + 4 B leaf id out + 8 B value out, F = 1
+L2_NOTE = "inputs (16 B/query) and outputs (12 B/query) are far larger than the 126 MB L2"
+
+
+def workload_string(nodes, fields):
+    """identical in both arms (ours / --impl reference): the driver compares config.workload"""
+    return (f"BASELINE.json configs[4]: {nodes} uniform-random nodes, {fields} field(s), uniform-random queries "
+            f"in the unit square; triangulation replicated per GPU, queries sharded (no collective on the data path)")
+
+
+def source_sha16():
+    """hash of the kernel / library sources: ties a committed ncu capture to the code it measured
+    (the GPU box has no .git, so a commit hash cannot be checked there)"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "gsl_scattered_interpolation_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".h", ".cpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def parse():
@@ -48,6 +68,10 @@ def parse():
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--stats", action="store_true", help="extra untimed pass counting walk steps")
     ap.add_argument("--param", action="append", default=[], help="library knob name=value (repeatable)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[1..3] legs (N = 1 only)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1 only)")
+    ap.add_argument("--pageable-queries", type=int, default=20_000_000,
+                    help="queries per GPU per step for the pageable host-buffer leg")
     return ap.parse_args()
 
 
@@ -193,7 +217,21 @@ def cpu_reference_leg(args, steps, warmup, sample_seconds, check=None):
         parity = {"queries": int(xs.size), "leaf": int(np.count_nonzero(rl != gl)),
                   "value_bits": int(np.count_nonzero(np.ascontiguousarray(rv).view(np.uint64)
                                                      != np.ascontiguousarray(gz).view(np.uint64)))}
-    return {"parity": parity, "value": per_step / t, "unit": "queries/s", "cores": cores, "kind": kind,
+    # the thread-safe restatement on `cores` POSIX threads sharing one tree
+    # (the reference itself cannot be threaded: tree->tmp_vec1, linear_simplex.c:644)
+    port_mt = None
+    try:
+        pt = refimpl.PortTree(tree.export(), xa, ya) if kind == "reference" else port
+        nmt = max(20000, per_step // 4)
+        xq, yq = synth.uniform_queries(nmt, first=7 * per_step)
+        t0 = time.perf_counter()
+        pt.eval_mt(xq, yq, za, cores if kind == "reference" else (os.cpu_count() or 1))
+        port_mt = {"value": nmt / (time.perf_counter() - t0), "unit": "queries/s",
+                   "threads": cores if kind == "reference" else (os.cpu_count() or 1), "kind": "port (oracle/simplex_oracle.c, pthreads)",
+                   "sample": f"{nmt} uniform queries, one pass"}
+    except Exception as e:                  # pragma: no cover
+        port_mt = {"error": f"{type(e).__name__}: {e}"}
+    return {"parity": parity, "port_mt": port_mt, "value": per_step / t, "unit": "queries/s", "cores": cores, "kind": kind,
             "sample": f"{per_step} uniform queries per step x {steps} steps on the {args.nodes}-node tree, "
                       f"find_leaf + {args.fields} x interp_point, forked over {cores} cores",
             "single_core_qps": rate1, "build_seconds": build_s, "ms_per_step": 1e3 * t,
@@ -210,16 +248,121 @@ def main_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.nodes} uniform nodes, {args.fields} field(s), uniform random queries "
-                               f"(BASELINE.json configs[4]); CPU arm evaluates a bounded sample of "
-                               f"{cb['per_step']} queries per step",
-                   "nodes": args.nodes, "fields": args.fields},
+        "config": {"workload": workload_string(args.nodes, args.fields), "nodes": args.nodes, "fields": args.fields,
+                   "l2": L2_NOTE},
+        "sample_queries_per_step": cb["per_step"],
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "reference_build_seconds": cb["build_seconds"],
         "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def timed_on_stream(torch, fn, dev, steps, warmup):
+    """ms per call of fn(stream_ptr), CUDA events on the launching stream"""
+    st = torch.cuda.Stream(device=dev)
+    for _ in range(warmup):
+        fn(st.cuda_stream)
+    st.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        fn(st.cuda_stream)
+    e1.record(st)
+    st.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def config_legs(torch, g, synth, dev, peak, tree_1e6, nodes_1e6):
+    """BASELINE.json configs[1..3] (the parity-test configurations) at their stated sizes: a short
+    device-timed leg each, verified in the same run (fast path == exact DAG replay on 100 % of the
+    queries; the stated-size comparison with oracle/_ref is in tests/test_gpu_stated_sizes.py).
+    Not part of the driver-timed region; rank 0 at N = 1 only."""
+    out = {}
+
+    def finish(w, steps, name, units, alg, ms, bad, extra):
+        inf = w.info()
+        out[name] = {"value": units / (ms * 1e-3), "ms_per_step": ms, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                     "achieved_GBps": alg / (ms * 1e-3) / 1e9,
+                     "kernel_ms": 1e3 * inf["locate_seconds"] / steps, "exact_replay_ms": 1e3 * inf["exact_seconds"] / steps,
+                     "deferred_per_step": inf["n_deferred"] / steps, "reordered": inf["n_reordered"] > 0,
+                     "fast_vs_exact_mismatches": {"leaf": bad[0], "value_bits": bad[1]}, **extra}
+
+    def arrays_leg(name, xa, ya, za, xq_t, yq_t, nq, label):
+        n = len(xa)
+        w = g.ScatteredCuda(n, 1)
+        w.set_param("profile", 1)
+        w.init(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n))
+        dz = torch.empty((1, nq), dtype=torch.float64, device=dev)
+        dl = torch.empty(nq, dtype=torch.int32, device=dev)
+        fn = lambda sp: w.eval_device_e(0 if dev.index is None else dev.index, xq_t.data_ptr(), yq_t.data_ptr(), nq,
+                                        dz.data_ptr(), nq, dl.data_ptr(), sp)
+        timed_on_stream(torch, fn, dev, 1, 2)
+        w.reset_counters()
+        steps = 5
+        ms = timed_on_stream(torch, fn, dev, steps, 0)
+        inf_steps = steps
+        vz = torch.empty((1, nq), dtype=torch.float64, device=dev)
+        vl = torch.empty(nq, dtype=torch.int32, device=dev)
+        w.set_param("profile", 0)
+        w.set_param("mode", 1)
+        w.eval_device_e(dev.index or 0, xq_t.data_ptr(), yq_t.data_ptr(), nq, vz.data_ptr(), nq, vl.data_ptr())
+        w.set_param("mode", 0)
+        bad = w.compare_device(dev.index or 0, dl.data_ptr(), vl.data_ptr(), dz.data_ptr(), vz.data_ptr(), nq, nq)
+        finish(w, inf_steps, name, nq, nq * 28, ms, bad, {"unit": "queries/s", "workload": label})
+        w.free()
+
+    # configs[1]: 10^5 uniform nodes, 10^7 uniform queries
+    n, nq = 100_000, 10_000_000
+    xa, ya = synth.uniform_nodes(n)
+    xq, yq = synth.uniform_queries(nq)
+    arrays_leg("configs[1]", xa, ya, synth.values(n, 1), torch.from_numpy(xq).to(dev), torch.from_numpy(yq).to(dev), nq,
+               "1e5 uniform nodes, 1e7 uniform queries, 1 field")
+    # configs[2]: 10^5 clustered nodes, 10^7 mixed queries (needs the leaves for the edge midpoints)
+    xa, ya = synth.clustered_nodes(n)
+    wt = g.ScatteredCuda(n, 1)
+    wt.build(xa, ya, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n))
+    tree = wt.get_tree(wt.n_simplexes(), n)
+    wt.free()
+    lv = tree["pts3"].reshape(-1, 3)[tree["type"] == 0]
+    lv = lv[(lv >= 0).all(axis=1)]
+    xq, yq = synth.mixed_queries(nq, xa, ya, tree["shuffle"][lv].astype(np.int64))
+    arrays_leg("configs[2]", xa, ya, synth.values(n, 1), torch.from_numpy(xq).to(dev), torch.from_numpy(yq).to(dev), nq,
+               "1e5 clustered/anisotropic nodes, 1e7 mixed queries (60% in bbox, 15% inflated bbox, 5% far outside, "
+               "10% on nodes, 10% on edge midpoints), 1 field")
+    del xq, yq
+    # configs[3]: 10^6 nodes (the bench's own triangulation), 8192 x 8192 raster, 16 fields
+    if tree_1e6 is not None:
+        xa, ya = nodes_1e6
+        n, F, nx, ny = len(xa), 16, 8192, 8192
+        za = synth.values(n, F)
+        w = g.ScatteredCuda(n, F)
+        w.set_param("profile", 1)
+        w.init_from_tree(tree_1e6["pts3"], tree_1e6["lnk3"], tree_1e6["type"], tree_1e6["shuffle"], tree_1e6["shift"],
+                         tree_1e6["scale"], tree_1e6["seed_points"], np.stack([xa, ya], axis=1), za)
+        x0, y0 = float(xa.min()), float(ya.min())
+        ddx, ddy = (float(xa.max()) - x0) / nx, (float(ya.max()) - y0) / ny
+        npx = nx * ny
+        dz = torch.empty((F, npx), dtype=torch.float64, device=dev)
+        dl = torch.empty(npx, dtype=torch.int32, device=dev)
+        d = dev.index or 0
+        fn = lambda sp: w.eval_raster_device_e(d, x0, ddx, nx, y0, ddy, ny, dz.data_ptr(), dl.data_ptr(), sp)
+        timed_on_stream(torch, fn, dev, 1, 2)
+        w.reset_counters()
+        steps = 5
+        ms = timed_on_stream(torch, fn, dev, steps, 0)
+        vz = torch.empty((F, npx), dtype=torch.float64, device=dev)
+        vl = torch.empty(npx, dtype=torch.int32, device=dev)
+        w.set_param("profile", 0)
+        w.set_param("mode", 1)
+        w.eval_raster_device_e(d, x0, ddx, nx, y0, ddy, ny, vz.data_ptr(), vl.data_ptr())
+        w.set_param("mode", 0)
+        bad = w.compare_device(d, dl.data_ptr(), vl.data_ptr(), dz.data_ptr(), vz.data_ptr(), npx, F * npx)
+        finish(w, steps, "configs[3]", npx, npx * (4 + 8 * F), ms, bad,
+               {"unit": "pixels/s", "workload": "1e6 uniform nodes, 8192x8192 raster, 16 fields (132 B/pixel algorithmic)"})
+        w.free()
+    return out
 
 
 def main_ours(args):
@@ -257,7 +400,10 @@ def main_ours(args):
         w.set_param(k, float(v))
     build_info = {}
     # --- triangulation: built once on the host by rank 0 (timed separately), uploaded, and
-    #     replicated to the other GPUs as one slab over NCCL/NVLink
+    #     replicated to the other GPUs as one slab over NCCL/NVLink.  Every rank ends up with its slab
+    #     in an allocation of its own made the same way (rank 0's staging copy for the broadcast is
+    #     released before anything is timed).
+    xa = ya = None
     if rank == 0:
         xa, ya, za = workload_nodes(n, F)
         t0 = time.perf_counter()
@@ -281,6 +427,7 @@ def main_ours(args):
         if rank != 0:
             w.init_from_slab_device(slab.data_ptr(), slab.numel())
         del slab
+        torch.cuda.empty_cache()
     # the part of the slab the fast path reads: leaf records, vertex values,
     # seed grid -- not the history DAG / entry table of the exact replay
     inf0 = w.info()
@@ -293,40 +440,45 @@ def main_ours(args):
                               dx.data_ptr(), dy.data_ptr(), sp)
     stream.synchronize()
 
-    def step():
-        w.eval_device_e(local, dx.data_ptr(), dy.data_ptr(), Q, dz.data_ptr(), Q, dl.data_ptr(), sp)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    w.reset_counters()
-    sampler = ClockSampler(local)
-    sampler.start()                      # every rank samples its own GPU
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms_mine = e0.elapsed_time(e1)
-    ms_total = dist_util.max_over_ranks(ms_mine, dev)
-    ms_by_rank = dist_util.gather_over_ranks(ms_mine / args.steps, dev)
-    clocks = sampler.stop()
+    def timed_region(nq, steps, warmup, sample_clocks):
+        """`steps` passes over the first nq queries of this rank's arrays: (max-over-ranks ms of the
+        region, per-rank ms per step, clocks); every pass is one eval_device_e call"""
+        def step():
+            w.eval_device_e(local, dx.data_ptr(), dy.data_ptr(), nq, dz.data_ptr(), Q, dl.data_ptr(), sp)
+        for _ in range(warmup):
+            step()
+        barrier()
+        w.reset_counters()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()                  # every rank samples its own GPU
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms_mine = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        return dist_util.max_over_ranks(ms_mine, dev), dist_util.gather_over_ranks(ms_mine / steps, dev), clocks
+
+    ms_total, ms_by_rank, clocks = timed_region(Q, args.steps, args.warmup, True)
     sm_by_rank = dist_util.gather_over_ranks(clocks["sm_mhz"] or 0.0, dev)
     mem_by_rank = dist_util.gather_over_ranks(clocks.get("mem_mhz") or 0.0, dev)
     pw_by_rank = dist_util.gather_over_ranks(clocks.get("power_w_max") or 0.0, dev)
     clocks["by_rank"] = {"sm_mhz": sm_by_rank, "mem_mhz": mem_by_rank, "power_w_max": pw_by_rank}
     inf = w.info()
     value = world * Q * args.steps / (ms_total * 1e-3)
-    locate_s = inf["locate_seconds"] / max(1, args.steps)          # dominant kernel, per launch
+    locate_s = inf["locate_seconds"] / max(1, args.steps)          # dominant kernel(s), per launch
     exact_s = inf["exact_seconds"] / max(1, args.steps)
     launches = int(inf["n_kernel_launches"])
+    reordered = inf.get("n_reordered", 0) > 0
 
     # --- verification inside the run: checksum, and fast path == exact replay on a prefix
     chk = w.checksum_device(local, dl.data_ptr(), dz.data_ptr(), Q, sp)
@@ -351,15 +503,28 @@ def main_ours(args):
     if args.stats:
         w.set_param("stats", 1)
         w.reset_counters()
-        step()
+        w.eval_device_e(local, dx.data_ptr(), dy.data_ptr(), Q, dz.data_ptr(), Q, dl.data_ptr(), sp)
         torch.cuda.synchronize()
         i2 = w.info()
         stats = {"walk_steps_per_query": i2["n_steps"] / max(1, Q - i2["n_deferred"]),
                  "deferred_fraction": i2["n_deferred"] / Q}
         w.set_param("stats", 0)
 
-    # --- e2e: the same metric through the host-buffer C-ABI call (pinned host memory; H2D of
-    #     the inputs and D2H of leaf ids + values inside the timed region)
+    # --- strong scaling (BASELINE.json configs[4] as written: a FIXED stream of Q queries sharded
+    #     over the N GPUs): rank r re-generates k in [r*Q/N, (r+1)*Q/N) into the front of its arrays
+    strong = None
+    if world > 1 and not args.no_strong:
+        s0, s1 = dist_util.split_range(rank, world, Q)
+        w.generate_uniform_device(local, synth.SEED_QUERIES, s0, s1 - s0, 0.0, 1.0, 0.0, 1.0,
+                                  dx.data_ptr(), dy.data_ptr(), sp)
+        stream.synchronize()
+        ms_s, ms_s_by_rank, _ = timed_region(s1 - s0, args.steps, max(1, args.warmup), False)
+        strong = {"scaling": "strong", "queries_total_per_step": Q, "value": Q * args.steps / (ms_s * 1e-3),
+                  "unit": "queries/s", "ms_per_step": ms_s / args.steps, "ms_per_step_by_rank": ms_s_by_rank}
+
+    # --- e2e: the same metric through the host-buffer C-ABI call (H2D of the inputs and D2H of leaf
+    #     ids + values inside the timed region), from pinned host memory and from pageable (malloc'd)
+    #     arrays such as the reference's gsl_matrix / gsl_vector
     del dx, dy, dz, dl
     torch.cuda.empty_cache()
     Qe = min(args.e2e_queries, Q)
@@ -384,7 +549,35 @@ def main_ours(args):
     for p in (hx, hy, hz, hl):
         if p:
             L.gsl_scattered_cuda_host_free(p)
+    e2e_pageable = None
+    Qp = min(args.pageable_queries, Q)
+    if Qp > 0:
+        px, py = g.generate_uniform_host(synth.SEED_QUERIES, rank * Q, Qp, 0.0, 1.0, 0.0, 1.0)   # numpy = malloc'd
+        pz = np.empty((F, Qp), dtype=np.float64)
+        pl = np.empty(Qp, dtype=np.int32)
+        w.eval_e(px, py, out_z=pz, out_leaf=pl)                 # warm-up (allocates the pinned staging)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            w.eval_e(px, py, out_z=pz, out_leaf=pl)
+        dt = dist_util.max_over_ranks(time.perf_counter() - t0, dev)
+        e2e_pageable = {"value": world * Qp * 2 / dt, "unit": "queries/s", "queries_per_gpu_per_step": Qp,
+                        "host_memory": "pageable (numpy / malloc), staged through the library's pinned buffers by "
+                                       "4 host threads", "h2d_bytes_per_step": Qp * 16, "d2h_bytes_per_step": Qp * (4 + 8 * F)}
+        del px, py, pz, pl
+    tree_1e6 = None
+    if rank == 0 and world == 1 and not args.no_configs and n == 1_000_000:
+        tree_1e6 = w.get_tree(w.n_simplexes(), n)
     w.free()
+
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        peak0, _ = peaks()
+        try:
+            configs = config_legs(torch, g, synth, dev, peak0, tree_1e6, (xa, ya))
+        except Exception as e:                                   # a failed side leg must not lose the main line
+            configs = {"error": f"{type(e).__name__}: {e}"}
+    del tree_1e6
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -392,21 +585,23 @@ def main_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        reordered = inf.get("n_reordered", 0) > 0
-        kernel_name = "k_bin + k_tile_locate + k_unpermute (reorder pipeline)" if reordered else "k_walk"
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per query,
-        # scaled to this launch); only valid for the configuration the capture was taken on
+        kernel_name = "k_bin + k_tile_walk + k_unpermute (reorder pipeline)" if reordered else "k_walk"
+        # DRAM traffic of the dominant kernel(s) from the committed ncu --set full capture (per query,
+        # scaled to this launch).  Only emitted when the capture was taken on exactly these sources and
+        # on this configuration (scripts/ncu_capture.sh writes the source hash into the file).
         traffic, traffic_src, ncu_counters = None, None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1c_k_walk_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 tj = json.load(f)
-            if not reordered and n == 1_000_000 and F == 1:
-                traffic = tj["dram_bytes_per_query"] * Q
-                ncu_counters = {k: tj[k] for k in ("dram_throughput_pct_of_peak", "lts_sector_hit_rate_pct",
-                                                   "branch_targets_threads_uniform_pct", "sm_warps_active_pct",
-                                                   "l1_sectors_per_query") if k in tj}
-                traffic_src = (f"{tj['dram_bytes_per_query']:.1f} B/query x {Q} queries; ncu dram__bytes_read+write.sum "
-                               f"of one {tj['queries_per_launch']}-query launch ({tj['source']})")
+            key = "pipeline" if reordered else "k_walk"
+            if tj.get("source_sha16") == source_sha16() and n == tj.get("nodes") and F == tj.get("fields") and key in tj:
+                traffic = tj[key]["dram_bytes_per_query"] * Q
+                ncu_counters = tj[key].get("counters")
+                traffic_src = (f"{tj[key]['dram_bytes_per_query']:.1f} B/query x {Q} queries; ncu dram__bytes_read+write.sum "
+                               f"of one {tj['queries_per_launch']}-query launch, sources {tj['source_sha16']} "
+                               f"({tj.get('source', 'profiles/')})")
+            else:
+                traffic_src = "no ncu capture of these sources / this configuration (profiles/r2_traffic.json)"
         except Exception:
             pass
         alg = Q * (16 + 4 + 8 * F) + struct_bytes
@@ -417,14 +612,11 @@ def main_ours(args):
             "ms_per_step_by_rank": ms_by_rank,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"BASELINE.json configs[4]: {n} uniform-random nodes, {F} field(s), "
-                                   f"{Q} uniform-random queries per GPU per step, triangulation replicated "
-                                   f"per GPU, queries sharded (no collective on the data path)",
-                       "nodes": n, "fields": F, "queries_per_gpu": Q,
-                       "l2": "inputs (16 B/query) and outputs (12 B/query) are far larger than the 126 MB L2",
-                       **build_info},
+            "config": {"workload": workload_string(n, F), "nodes": n, "fields": F, "l2": L2_NOTE},
+            "setup": {"queries_per_gpu_per_step": Q, "source_sha16": source_sha16(), **build_info},
             "clocks": clocks,
             "e2e": e2e,
+            "e2e_pageable": e2e_pageable,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
@@ -438,9 +630,14 @@ def main_ours(args):
                        "deferred_queries_per_step": inf["n_deferred"] / max(1, args.steps),
                        "outside_cage": inf["n_outside"]},
         }
+        if strong:
+            line["scaling_strong"] = strong
+        if configs is not None:
+            line["configs"] = configs
         if cb:
             line["cpu_reference_detail"] = {"single_core_qps": cb["single_core_qps"],
-                                            "reference_build_seconds": cb["build_seconds"]}
+                                            "reference_build_seconds": cb["build_seconds"],
+                                            "thread_safe_port_multi_thread": cb["port_mt"]}
         if stats:
             line["walk_stats"] = stats
         emit(line)

@@ -50,7 +50,7 @@ def clustered_nodes(n, n_clusters=64, seed=SEED_NODES + 100):
     return cx[c] + sx[c] * rng.standard_normal(n), cy[c] + sy[c] * rng.standard_normal(n)
 
 
-def mixed_queries(nq, xa, ya, leaf_vertices=None, seed=SEED_QUERIES + 100):
+def mixed_queries(nq, xa, ya, leaf_vertices=None, seed=SEED_QUERIES + 100, with_class=False):
     """config 3 query mix: 60 % uniform in the bbox, 15 % in the bbox inflated by 25 % per
     side, 5 % far outside (+-50x extent, still inside the cage), 10 % exact node copies,
     10 % edge midpoints 0.5*(a+b) of leaf edges (or of random node pairs)."""
@@ -74,4 +74,8 @@ def mixed_queries(nq, xa, ya, leaf_vertices=None, seed=SEED_QUERIES + 100):
     xs.append(0.5 * (xa[a] + xa[b])); ys.append(0.5 * (ya[a] + ya[b]))
     xq, yq = np.concatenate(xs), np.concatenate(ys)
     p = rng.permutation(nq)
+    if with_class:
+        # 0 = in bbox, 1 = inflated bbox, 2 = far outside, 3 = on a node, 4 = on an edge midpoint
+        cls = np.repeat(np.arange(5, dtype=np.int8), [n1, n2, n3, n4, n5])
+        return np.ascontiguousarray(xq[p]), np.ascontiguousarray(yq[p]), cls[p]
     return np.ascontiguousarray(xq[p]), np.ascontiguousarray(yq[p])

@@ -25,6 +25,11 @@ long so_eval(const so_tree *t, const double *xq, const double *yq, long nq, cons
 long so_eval_deriv(const so_tree *t, const double *xq, const double *yq, long nq, const double *z,
                    int n_fields, int *leaf, double *dzdx, double *dzdy);
 
+/* so_eval on n_threads POSIX threads sharing the (read-only) tree: thread-safe, unlike the
+ * reference (tree->tmp_vec1, linear_simplex.c:644).  SURVEY.md section 8f.4. */
+long so_eval_mt(const so_tree *t, const double *xq, const double *yq, long nq, const double *z,
+                int n_fields, int *leaf, double *val, int n_threads);
+
 /* per-query descent statistics: depth[q] = DAG levels, tests[q] = contains_point calls */
 long so_eval_stats(const so_tree *t, const double *xq, const double *yq, long nq, int *depth,
                    int *tests);

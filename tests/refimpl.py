@@ -167,6 +167,8 @@ def port_lib():
         L.so_eval_deriv.restype = c_long
         L.so_eval_deriv.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p]
+        L.so_eval_mt.restype = c_long
+        L.so_eval_mt.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p, c_int]
         L.so_eval_stats.restype = c_long
         L.so_eval_stats.argtypes = [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p]
         _PORT = L
@@ -202,6 +204,18 @@ class PortTree:
         leaf = np.empty(nq, dtype=np.int32)
         val = np.empty((F, nq), dtype=np.float64)
         out = self.L.so_eval(self.h, _p(xq), _p(yq), nq, _p(za), F, _p(leaf), _p(val))
+        return leaf, val, int(out)
+
+    def eval_mt(self, xq, yq, za, n_threads):
+        """the thread-safe multi-thread evaluation: n_threads POSIX threads on
+        one shared tree"""
+        xq = np.ascontiguousarray(xq, dtype=np.float64)
+        yq = np.ascontiguousarray(yq, dtype=np.float64)
+        za = np.ascontiguousarray(np.atleast_2d(za), dtype=np.float64)
+        F, nq = za.shape[0], xq.size
+        leaf = np.empty(nq, dtype=np.int32)
+        val = np.empty((F, nq), dtype=np.float64)
+        out = self.L.so_eval_mt(self.h, _p(xq), _p(yq), nq, _p(za), F, _p(leaf), _p(val), int(n_threads))
         return leaf, val, int(out)
 
     def eval_deriv(self, xq, yq, za):

@@ -158,61 +158,6 @@ def test_degenerate_grid_nodes_vs_port():
     w.free()
 
 
-def test_config2_scale_vs_oracle():
-    """10^5 uniform nodes, 10^6 queries against the oracle (real reference on all cores when
-    oracle/_ref is present, else the port), then 10^7 device-generated queries: fast path vs
-    exact replay on 100 % of them."""
-    torch = _torch()
-    n = 100000
-    xa, ya = synth.uniform_nodes(n)
-    za = synth.values(n, 1)
-    order = g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
-    w = make(xa, ya, za, g.DEFAULT, order, stats=1)
-    nq = 1000000
-    xq, yq = synth.uniform_queries(nq)
-    st, zq, leaf = w.eval_e(xq, yq)
-    assert st == g.SUCCESS
-    leaf_host_api = leaf.copy()
-    tree = w.get_tree(w.n_simplexes(), n)
-    if refimpl.have_ref():
-        rt = refimpl.RefTree(xa, ya, g.DEFAULT, synth.SEED_SHUFFLE)
-        assert rt.n_simplexes == tree["type"].size
-        import os
-        rl, rv, _ = rt.eval(xq, yq, za, nproc=max(1, min(32, os.cpu_count() or 1)))
-        rt.close()
-    else:
-        sub = slice(0, 200000)
-        port = refimpl.PortTree(tree, xa, ya)
-        rl, rv, _ = port.eval(xq[sub], yq[sub], za)
-        leaf, zq = leaf[sub], zq[:, sub]
-    assert np.array_equal(leaf, rl)
-    assert refimpl.same_bits(zq, rv)
-    info = w.info()
-    assert info["n_deferred"] < 1e-3 * nq
-    # device API, 10^7 queries generated on the device
-    nq = 10_000_000
-    dev = torch.device("cuda:0")
-    dx = torch.empty(nq, dtype=torch.float64, device=dev)
-    dy = torch.empty(nq, dtype=torch.float64, device=dev)
-    w.generate_uniform_device(0, synth.SEED_QUERIES, 0, nq, 0.0, 1.0, 0.0, 1.0, dx.data_ptr(), dy.data_ptr())
-    hx, hy = synth.uniform_queries(4096)
-    assert np.array_equal(dx[:4096].cpu().numpy(), hx) and np.array_equal(dy[:4096].cpu().numpy(), hy)
-    za_d = torch.empty(nq, dtype=torch.float64, device=dev)
-    la_d = torch.empty(nq, dtype=torch.int32, device=dev)
-    zb_d = torch.empty(nq, dtype=torch.float64, device=dev)
-    lb_d = torch.empty(nq, dtype=torch.int32, device=dev)
-    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, za_d.data_ptr(), nq, la_d.data_ptr()) == 0
-    w.set_param("mode", 1)
-    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, zb_d.data_ptr(), nq, lb_d.data_ptr()) == 0
-    w.set_param("mode", 0)
-    bad_leaf, bad_val = w.compare_device(0, la_d.data_ptr(), lb_d.data_ptr(), za_d.data_ptr(),
-                                         zb_d.data_ptr(), nq, nq)
-    assert bad_leaf == 0 and bad_val == 0
-    # host API (eval_e) and device API agree on the shared prefix of the query stream
-    assert np.array_equal(la_d[:1000000].cpu().numpy(), leaf_host_api)
-    w.free()
-
-
 def test_sixteen_fields_raster_vs_port():
     """config 4 shape at test size: 2*10^4 nodes, 16 fields, 384 x 256 raster"""
     n, F = 20000, 16
@@ -353,55 +298,6 @@ def test_two_devices_if_present(golden):
     x0, dx, nx, y0, dy, ny = golden["cfg1_raster_spec"]
     st, rz, rl = w.eval_raster_e(x0, dx, int(nx), y0, dy, int(ny))
     assert np.array_equal(rl, golden["cfg1_raster_leaf"]) and refimpl.same_bits(rz, golden["cfg1_raster_val"])
-    w.free()
-
-
-def test_million_nodes_properties():
-    """BASELINE.json target size: 10^6 nodes.  CPU oracle on a strided subsample, fast path
-    vs exact replay on 100 % of 5*10^7 device-generated queries, linear precision."""
-    torch = _torch()
-    n = 1_000_000
-    xa, ya = synth.uniform_nodes(n)
-    za = np.stack([synth.values(n, 1)[0], xa + 1000.0 * ya])
-    order = g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
-    w = make(xa, ya, za, g.DEFAULT, order)
-    info = w.info()
-    assert info["n_leaves"] == 2 * n + 1                    # SURVEY.md: T = 2n + 1
-    nq = 50_000_000
-    dev = torch.device("cuda:0")
-    dx = torch.empty(nq, dtype=torch.float64, device=dev)
-    dy = torch.empty(nq, dtype=torch.float64, device=dev)
-    w.generate_uniform_device(0, synth.SEED_QUERIES, 0, nq, 0.0, 1.0, 0.0, 1.0, dx.data_ptr(), dy.data_ptr())
-    za_d = torch.empty((2, nq), dtype=torch.float64, device=dev)
-    la_d = torch.empty(nq, dtype=torch.int32, device=dev)
-    zb_d = torch.empty((2, nq), dtype=torch.float64, device=dev)
-    lb_d = torch.empty(nq, dtype=torch.int32, device=dev)
-    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, za_d.data_ptr(), nq, la_d.data_ptr()) == 0
-    w.set_param("mode", 1)
-    assert w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), nq, zb_d.data_ptr(), nq, lb_d.data_ptr()) == 0
-    w.set_param("mode", 0)
-    bad_leaf, bad_val = w.compare_device(0, la_d.data_ptr(), lb_d.data_ptr(), za_d.data_ptr(),
-                                         zb_d.data_ptr(), nq, 2 * nq)
-    assert bad_leaf == 0 and bad_val == 0
-    assert w.info()["n_deferred"] < 1e-3 * nq
-    # linear precision in non-cage leaves (field 1 = x + 1000 y); cage leaves (a negative
-    # vertex id) return partial sums by design (linear_simplex.c:696-709)
-    tree = w.get_tree(w.n_simplexes(), n)
-    npre = 4_000_000
-    lp = la_d[:npre].cpu().numpy()
-    real = (tree["pts3"].reshape(-1, 3)[lp] >= 0).all(axis=1)
-    assert real.mean() > 0.999
-    want = (dx[:npre] + 1000.0 * dy[:npre]).cpu().numpy()
-    got = za_d[1, :npre].cpu().numpy()
-    rel = np.abs(got - want) / np.abs(want)
-    assert rel[real].max() < REL_TOL
-    # CPU oracle (port) on the strided subsample k = 0 (mod 256)
-    sub = torch.arange(0, nq, 256, device=dev)
-    xs, ys = dx[sub].cpu().numpy(), dy[sub].cpu().numpy()
-    port = refimpl.PortTree(tree, xa, ya)
-    pl, pv, _ = port.eval(xs, ys, za)
-    assert np.array_equal(la_d[sub].cpu().numpy(), pl)
-    assert refimpl.same_bits(za_d[:, sub].cpu().numpy(), pv)
     w.free()
 
 

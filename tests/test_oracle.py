@@ -109,3 +109,20 @@ def test_stub_integrity_tu_is_transparent():
     assert b.check() == 1
     a.close()
     b.close()
+
+
+def test_thread_safe_multi_thread_evaluation_matches_single_thread(golden):
+    """the port evaluates one shared tree from several POSIX threads (the
+    reference cannot: tree->tmp_vec1, linear_simplex.c:644) and returns the golden vectors whatever
+    the thread count, including thread counts that do not divide the batch and exceed it."""
+    xa, ya = synth.uniform_nodes(1000)
+    za = synth.values(1000, 1)
+    tree = {k: golden["cfg1_" + k] for k in ("pts3", "lnk3", "type", "shuffle", "shift", "scale", "seed_points")}
+    port = refimpl.PortTree(tree, xa, ya)
+    xq, yq = synth.uniform_queries(10000)
+    for nt in (1, 2, 7, 16):
+        leaf, val, out = port.eval_mt(xq, yq, za, nt)
+        assert out == 0 and np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(val, golden["cfg1_val"])
+    leaf, val, out = port.eval_mt(np.array([0.5, 1e6, 0.25]), np.array([0.5, 0.0, 0.75]), za, 8)
+    assert out == 1 and leaf[1] == -1 and np.isnan(val[0, 1]) and leaf[0] >= 0 and leaf[2] >= 0
+    port.close()
