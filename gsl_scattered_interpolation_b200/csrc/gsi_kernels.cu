@@ -719,7 +719,7 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
       unsigned cb = range * WPC + warp;
       const unsigned cb_stride = (unsigned) A.ranges * WPC;
       unsigned r_pos0 = 0, r_len = 0, r_excl = 0; /* this lane's run of the current block */
-      unsigned b_total = 0, win_lo = 0, win_n = 0, next = 0;
+      unsigned b_total = 0, win_lo = 0, win_n = 0, next = 0; /* block items, window [win_lo, win_lo + win_n), cursor */
       bool cur_v = false;
       double cur_x = 0, cur_y = 0;
       unsigned cur_pos = 0;
@@ -729,8 +729,9 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
           if (next >= win_n) /* warp-uniform: the dense list is used up */
             {
               bool have = true;
-              if (win_lo + win_n < b_total)
-                win_lo += win_n; /* next window of a block that exceeds the list */
+              win_lo += win_n; /* items of the current block handed out so far */
+              if (win_lo < b_total)
+                ; /* next window of a block that exceeds the list */
               else if (cb < n_blocks)
                 {
                   const unsigned c = (cb << 5) + lane;
