@@ -990,6 +990,9 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
   cudaError_t e = cudaMemcpyAsync(r0->slab, image.data(), image.size(), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = gsi_launch_entry_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_entry), r0->sm_count, st);
   if (e == cudaSuccess) e = gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->sm_count, st);
+  if (e == cudaSuccess)
+    e = gsi_launch_pack_seeds(r0->view, (const int32_t *) (r0->slab + w->hdr.off_seeds), (uint16_t *) (r0->slab + w->hdr.off_seed16),
+                              (int32_t *) (r0->slab + w->hdr.off_seedbase), r0->sm_count, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   for (size_t i = 1; e == cudaSuccess && i < w->reps.size(); i++)
     {
@@ -1043,7 +1046,9 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       || !extent_ok(h.off_z, std::max<uint64_t>(1, h.n_points), (uint64_t) h.n_fields * sizeof(double), bytes)
       || !extent_ok(h.off_seeds, cells, sizeof(int32_t), bytes) || !extent_ok(h.off_entry, cells, sizeof(int32_t), bytes)
       || !extent_ok(h.off_tiles, ((uint64_t) 1 << h.tile_bits) + 1, sizeof(int32_t), bytes)
-      || (h.off_dag | h.off_leaf | h.off_z | h.off_seeds | h.off_entry | h.off_tiles) % 32 != 0
+      || !extent_ok(h.off_seed16, cells, sizeof(uint16_t), bytes)
+      || !extent_ok(h.off_seedbase, (((uint64_t) h.grid_g + 7) >> 3) * (((uint64_t) h.grid_g + 7) >> 3), sizeof(int32_t), bytes)
+      || (h.off_dag | h.off_leaf | h.off_z | h.off_seeds | h.off_entry | h.off_tiles | h.off_seed16 | h.off_seedbase) % 32 != 0
       || !(h.inv_du > 0) || !(h.inv_dv > 0) || !(h.delta > 0))
     GSI_ERROR("slab sections out of range", GSL_SCATTERED_EINVAL);
   device_guard restore;

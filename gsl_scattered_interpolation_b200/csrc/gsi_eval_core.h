@@ -217,6 +217,29 @@ gsi_cell_of(const gsi_view *V, double qx, double qy)
   return (size_t) GSI_FLOOR_INT(fy) * (size_t) V->grid_g + (size_t) GSI_FLOOR_INT(fx);
 }
 
+/* Seed of the fast path for a query: the compact table (two independent loads that stay in L2),
+ * the int32 table only for escaped cells.  Like the cell itself this is a hint: any leaf slot is
+ * a correct starting point of the walk. */
+GSI_HD int
+gsi_seed_of(const gsi_view *V, double qx, double qy)
+{
+  const double u = (qx - V->xf.cx) * V->xf.sx, v = (qy - V->xf.cy) * V->xf.sy;
+  const double gmax = (double) (V->grid_g - 1);
+  const int ix = GSI_FLOOR_INT(fmin(fmax((u - V->u0) * V->inv_du, 0.0), gmax));
+  const int iy = GSI_FLOOR_INT(fmin(fmax((v - V->v0) * V->inv_dv, 0.0), gmax));
+  const size_t cell = (size_t) iy * (size_t) V->grid_g + (size_t) ix;
+#if defined(__CUDA_ARCH__)
+  const unsigned off = __ldg(V->seed16 + cell);
+  const int base = __ldg(V->seedbase + (size_t) (iy >> 3) * (size_t) V->grid_gb + (size_t) (ix >> 3));
+  if (off != GSI_SEED16_ESC) return base + (int) off;
+  return gsi_ld_seed(V->seeds + cell);
+#else
+  const unsigned off = V->seed16[cell];
+  if (off != GSI_SEED16_ESC) return V->seedbase[(size_t) (iy >> 3) * (size_t) V->grid_gb + (size_t) (ix >> 3)] + (int) off;
+  return V->seeds[cell];
+#endif
+}
+
 /* centre of grid cell `cell` in raw coordinates (seeding) */
 GSI_HD void
 gsi_cell_centre(const gsi_view *V, size_t cell, double *qx, double *qy)
@@ -453,7 +476,7 @@ gsi_locate_one(const gsi_view *V, double qx, double qy, int max_steps, double *v
 {
   *steps = 0;
   if (!(isfinite(qx) && isfinite(qy))) return 0;
-  int slot = GSI_LDG(V->seeds + gsi_cell_of(V, qx, qy));
+  int slot = gsi_seed_of(V, qx, qy);
   for (int step = 0; step < max_steps; step++)
     {
       gsi_rec r;

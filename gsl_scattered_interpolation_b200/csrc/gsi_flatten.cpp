@@ -160,6 +160,11 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   h.off_z = off;     off = align256(off + std::max<size_t>(1, n) * n_fields * sizeof(double));
   h.off_seeds = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
   h.off_entry = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
+  h.off_seed16 = off; off = align256(off + (uint64_t) G * G * sizeof(uint16_t));
+  {
+    const uint64_t gb = ((uint64_t) G + 7) >> 3;
+    h.off_seedbase = off; off = align256(off + gb * gb * sizeof(int32_t));
+  }
   /* Morton-prefix tiles of about tile_leaves leaves: P bits, 2 <= P <= 12 */
   uint32_t P = 2;
   while (P < 12 && (double) L / (double) (1u << P) > (double) std::max<uint32_t>(1, prm.tile_leaves) * 1.05) P++;

@@ -19,7 +19,8 @@ struct gsi_flatten_params
 };
 
 /* za: n_fields x n_points, field-major (may be NULL: values left zero).
- * The seeds and entry sections are left zero (entry 0 = root); they are filled on the device. */
+ * The seeds, seed16, seedbase and entry sections are left zero (entry 0 = root); they are filled on
+ * the device (seed16 all zero + seedbase all zero is a valid, if useless, compact table: slot 0). */
 int gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const double *za,
                 size_t n_fields, const gsi_flatten_params &prm, std::vector<char> *image,
                 std::string *err);

@@ -173,6 +173,58 @@ k_seed_cells(const gsi_view V, int32_t *seeds)
     }
 }
 
+/* compact seed table (gsi_layout.h): one thread per block of 8 x 8 cells takes the smallest seed
+ * of the block as its base and stores every cell's 16-bit offset, 0xffff where it does not fit */
+__global__ void __launch_bounds__(128)
+k_pack_seeds(const gsi_view V, const int32_t *seeds, uint16_t *seed16, int32_t *seedbase)
+{
+  const unsigned g = (unsigned) V.grid_g, gb = (unsigned) V.grid_gb;
+  const size_t nblk = (size_t) gb * gb;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t b = (size_t) blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += stride)
+    {
+      const unsigned by = (unsigned) (b / gb), bx = (unsigned) (b - (size_t) by * gb);
+      const unsigned x0 = bx << 3, y0 = by << 3, x1 = min(x0 + 8u, g), y1 = min(y0 + 8u, g);
+      /* base = the smallest seed that still lets most of the block fit: the minimum, unless the
+         block straddles a coarse Morton boundary; then the most common 64K-slot window wins */
+      int lo = 0x7fffffff;
+      for (unsigned y = y0; y < y1; y++)
+        for (unsigned x = x0; x < x1; x++) lo = min(lo, seeds[(size_t) y * g + x]);
+      int best = lo, best_n = -1;
+      for (int pass = 0; pass < 2; pass++)
+        {
+          /* candidate bases: the minimum, and the smallest seed that is more than 64K above it */
+          int cand = lo;
+          if (pass == 1)
+            {
+              cand = 0x7fffffff;
+              for (unsigned y = y0; y < y1; y++)
+                for (unsigned x = x0; x < x1; x++)
+                  {
+                    const int s = seeds[(size_t) y * g + x];
+                    if (s - lo >= (int) GSI_SEED16_ESC) cand = min(cand, s);
+                  }
+              if (cand == 0x7fffffff) break;
+            }
+          int n = 0;
+          for (unsigned y = y0; y < y1; y++)
+            for (unsigned x = x0; x < x1; x++)
+              {
+                const int d = seeds[(size_t) y * g + x] - cand;
+                n += d >= 0 && d < (int) GSI_SEED16_ESC;
+              }
+          if (n > best_n) { best_n = n; best = cand; }
+        }
+      seedbase[b] = best;
+      for (unsigned y = y0; y < y1; y++)
+        for (unsigned x = x0; x < x1; x++)
+          {
+            const int d = seeds[(size_t) y * g + x] - best;
+            seed16[(size_t) y * g + x] = (d >= 0 && d < (int) GSI_SEED16_ESC) ? (uint16_t) d : (uint16_t) GSI_SEED16_ESC;
+          }
+    }
+}
+
 /* entry[cell] = deepest DAG node every query of the cell is certain to pass (gsi_eval_core.h) */
 __global__ void __launch_bounds__(128)
 k_entry_cells(const gsi_view V, int32_t *entry)
@@ -221,7 +273,7 @@ k_locate(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_out,
           status = GSI_STEP_DEFER;
           if (isfinite(qx) && isfinite(qy))
             {
-              slot = gsi_ld_seed(V.seeds + gsi_cell_of(&V, qx, qy));
+              slot = gsi_seed_of(&V, qx, qy);
               for (int step = 0; step < max_steps; step++)
                 {
                   gsi_rec r;
@@ -312,7 +364,7 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
               cur_v = nxt_v; cur_q = nxt_q; cur_x = nxt_x; cur_y = nxt_y;
               cur_slot = nxt_seed; cur_steps = 0;
               nxt_v = nn_v; nxt_q = nn_q; nxt_x = nn_x; nxt_y = nn_y;
-              if (nxt_v) nxt_seed = gsi_ld_seed(V.seeds + gsi_cell_of(&V, nxt_x, nxt_y));
+              if (nxt_v) nxt_seed = gsi_seed_of(&V, nxt_x, nxt_y);
             }
           const unsigned take = __ballot_sync(FULL, need);
           if (need)
@@ -1023,6 +1075,12 @@ k_validate_slab(const gsi_view V, unsigned long long n_points, unsigned long lon
       if (i < cells)
         {
           mine += (unsigned) V.seeds[i] >= (unsigned) V.n_leaves;
+          {
+            const size_t iy = i / (size_t) V.grid_g, ix = i - iy * (size_t) V.grid_g;
+            const unsigned off = V.seed16[i];
+            if (off != GSI_SEED16_ESC)
+              mine += (unsigned) (V.seedbase[(iy >> 3) * (size_t) V.grid_gb + (ix >> 3)] + (int) off) >= (unsigned) V.n_leaves;
+          }
           if (V.entry) mine += (unsigned) V.entry[i] >= (unsigned) V.n_dag;
         }
       if (i < nt1)
@@ -1242,6 +1300,15 @@ gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count, cudaStrea
 {
   const size_t ncell = (size_t) V.grid_g * V.grid_g;
   k_seed_cells<<<grid_for(ncell, 128, sm_count, 16), 128, 0, st>>>(V, seeds);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_pack_seeds(const gsi_view &V, const int32_t *seeds, uint16_t *seed16, int32_t *seedbase, int sm_count,
+                      cudaStream_t st)
+{
+  const size_t nblk = (size_t) V.grid_gb * V.grid_gb;
+  k_pack_seeds<<<grid_for(nblk, 128, sm_count, 16), 128, 0, st>>>(V, seeds, seed16, seedbase);
   return cudaGetLastError();
 }
 

@@ -88,6 +88,10 @@ cudaError_t gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, doub
 cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count,
                                   cudaStream_t st);
 
+/* fill the compact seed table (seed16 + seedbase) from the int32 seeds; run after the seeding */
+cudaError_t gsi_launch_pack_seeds(const gsi_view &V, const int32_t *seeds, uint16_t *seed16, int32_t *seedbase,
+                                  int sm_count, cudaStream_t st);
+
 /* fill the entry section (per-cell start node of the exact replay); run before the seeding */
 cudaError_t gsi_launch_entry_cells(const gsi_view &V, int32_t *entry, int sm_count,
                                    cudaStream_t st);

@@ -17,6 +17,13 @@
  *   seeds    int32[G*G]         uniform grid over the data bounding box in standardised
  *                               coordinates: leaf slot containing the cell centre
  *                               (filled on the device by the exact-replay kernel)
+ *   seed16   uint16[G*G] +      the same table as the fast path reads it: seed = base[block] + seed16[cell]
+ *   seedbase int32[GB*GB]       with one base (the smallest seed) per block of 8 x 8 cells, GB = ceil(G/8).
+ *                               Leaves are in Morton order, so the seeds of a block are a narrow slot
+ *                               range; 0xffff = escape to the int32 table (blocks that straddle a
+ *                               coarse Morton boundary, dense clusters).  2 bytes per cell instead of 4
+ *                               and, above all, a table that stays L2-resident beside ~200 MB of
+ *                               randomly gathered leaf records (16 MB instead of 32 MB at 10^6 nodes)
  *   tiles    int32[2^P + 1]     the leaves are sorted by the Morton key of their centroid, so the
  *                               leaves whose key starts with the P-bit prefix t are the slot
  *                               range [tiles[t], tiles[t+1]): a spatial tile whose records can be
@@ -37,7 +44,8 @@
 #include "gsi_core.h"
 
 #define GSI_SLAB_MAGIC 0x3142414c53495347ull /* "GSISLAB1" */
-#define GSI_SLAB_VERSION 4u
+#define GSI_SLAB_VERSION 5u
+#define GSI_SEED16_ESC 0xffffu
 
 /* One compacted leaf: 96 bytes = three 32-byte sectors, each fetched with one 256-bit load
  * (LDG.E.256 on sm_100a).  A walk step reads r (sectors 0-1); only the accepted leaf's tail
@@ -85,7 +93,9 @@ typedef struct
   double delta; /* absolute safety margin (standardised units) behind the per-leaf tau */
   uint64_t off_dag, off_leaf, off_z, off_seeds;
   uint64_t total_bytes;
-  uint64_t reserved[4]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
+  uint64_t reserved[2]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
+  uint64_t off_seed16;  /* uint16[grid_g^2] */
+  uint64_t off_seedbase; /* int32[ceil(grid_g/8)^2] */
   uint32_t tile_bits;       /* tiles = the 2^tile_bits prefixes of the leaves' 32-bit Morton keys */
   uint32_t tile_max_leaves; /* largest tile */
   uint64_t off_tiles;       /* int32[2^tile_bits + 1]: first leaf slot of every tile */
@@ -101,12 +111,15 @@ typedef struct
   const char *leaf; /* gsi_leaf records, leaf_stride bytes apart */
   const double *z;
   const int32_t *seeds;
+  const uint16_t *seed16;   /* compact seeds: base[block] + seed16[cell], GSI_SEED16_ESC -> seeds[cell] */
+  const int32_t *seedbase;
   const int32_t *entry; /* NULL: exact replay always starts at the root */
   const int32_t *tiles; /* first leaf slot per Morton-prefix tile, 2^tile_bits + 1 entries */
   int32_t tile_bits;
   double u0, v0, inv_du, inv_dv;
   double delta;
   int32_t grid_g;
+  int32_t grid_gb; /* blocks of 8 x 8 cells per side */
   int32_t n_fields;
   int32_t n_dag;
   int32_t n_leaves;
@@ -136,6 +149,9 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   v.leaf_stride = (int32_t) h->leaf_stride;
   v.z = (const double *) (b + h->off_z);
   v.seeds = (const int32_t *) (b + h->off_seeds);
+  v.seed16 = (const uint16_t *) (b + h->off_seed16);
+  v.seedbase = (const int32_t *) (b + h->off_seedbase);
+  v.grid_gb = (int32_t) ((h->grid_g + 7u) >> 3);
   v.entry = (const int32_t *) (b + h->off_entry);
   v.tiles = (const int32_t *) (b + h->off_tiles);
   v.tile_bits = (int32_t) h->tile_bits;

@@ -7,6 +7,7 @@
  * seeding) against the reference before a GPU is available.  It is not linked into
  * libgsl_scattered_cuda.so and is not an evaluation fallback.
  */
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -71,6 +72,27 @@ hostsim_create(const double *xa, const double *ya, const double *za, size_t n, s
       const int slot = gsi_exact_one(&h->view, qx, qy, nullptr, nullptr, 0, c);
       seeds[c] = slot < 0 ? 0 : slot;
     }
+  /* what k_pack_seeds does on the device, with the minimum as the block base (the kernel may pick a later
+     base for a block that straddles a coarse Morton boundary; either is a valid table) */
+  {
+    const size_t g = h->hdr.grid_g, gb = (g + 7) >> 3;
+    uint16_t *s16 = (uint16_t *) (h->image.data() + h->hdr.off_seed16);
+    int32_t *sb = (int32_t *) (h->image.data() + h->hdr.off_seedbase);
+    for (size_t by = 0; by < gb; by++)
+      for (size_t bx = 0; bx < gb; bx++)
+        {
+          int lo = 0x7fffffff;
+          for (size_t y = by * 8; y < std::min(by * 8 + 8, g); y++)
+            for (size_t x = bx * 8; x < std::min(bx * 8 + 8, g); x++) lo = std::min(lo, seeds[y * g + x]);
+          sb[by * gb + bx] = lo;
+          for (size_t y = by * 8; y < std::min(by * 8 + 8, g); y++)
+            for (size_t x = bx * 8; x < std::min(bx * 8 + 8, g); x++)
+              {
+                const int d = seeds[y * g + x] - lo;
+                s16[y * g + x] = d < (int) GSI_SEED16_ESC ? (uint16_t) d : (uint16_t) GSI_SEED16_ESC;
+              }
+        }
+  }
   return h;
 }
 

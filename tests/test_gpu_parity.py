@@ -507,3 +507,74 @@ def test_raster_kernel_vs_exact_replay_on_device(F, nx, ny, kernel):
                                              res[0][0].data_ptr(), res[1][0].data_ptr(), nx * ny, F * nx * ny)
         assert bad_leaf == 0 and bad_val == 0, (x0, x1)
     w.free()
+
+
+def test_eval_is_reentrant_across_host_threads(golden):
+    """eval* may be called concurrently from several host threads on one
+    workspace -- every call in flight gets its own evaluation context (streams, deferred list,
+    counters, staging).  Four threads hammer eval_e / eval_raster_e / eval_deriv_e on one
+    workspace; every result must be the golden one and the outside-cage status must stay with the
+    call that caused it."""
+    import threading
+    xa, ya = synth.uniform_nodes(1000)
+    w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000), host_chunk=1500)
+    xq, yq = synth.uniform_queries(10000)
+    x0, dx, nx, y0, dy, ny = golden["cfg1_raster_spec"]
+    bad_x, bad_y = xq.copy(), yq.copy()
+    bad_x[123] = 1e6                                     # one query outside the cage: this call alone reports EDOM
+    errors = []
+
+    def worker(kind):
+        try:
+            for _ in range(6):
+                if kind == 0:
+                    st, zq, leaf = w.eval_e(xq, yq)
+                    assert st == g.SUCCESS and np.array_equal(leaf, golden["cfg1_leaf"])
+                    assert refimpl.same_bits(zq, golden["cfg1_val"])
+                elif kind == 1:
+                    st, rz, rl = w.eval_raster_e(x0, dx, int(nx), y0, dy, int(ny))
+                    assert st == g.SUCCESS and np.array_equal(rl, golden["cfg1_raster_leaf"])
+                    assert refimpl.same_bits(rz, golden["cfg1_raster_val"])
+                elif kind == 2:
+                    st, zq, leaf = w.eval_e(bad_x, bad_y)
+                    assert st == g.EDOM and leaf[123] == -1 and np.isnan(zq[0, 123])
+                    keep = np.arange(10000) != 123
+                    assert np.array_equal(leaf[keep], golden["cfg1_leaf"][keep])
+                else:
+                    st, ddx, ddy = w.eval_deriv_e(xq, yq)
+                    assert st == g.SUCCESS and np.isfinite(ddx).all()
+        except Exception as e:                            # surfaced in the main thread below
+            errors.append((kind, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in (0, 1, 2, 3, 0)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    info = w.info()
+    assert info["n_contexts"] >= 2                       # the calls really overlapped
+    assert info["n_outside"] == 6                        # counters of all contexts are folded into get_info
+    w.free()
+
+
+def test_pageable_host_arrays_are_staged_through_pinned_buffers(golden):
+    """plain numpy (malloc) arrays above the pageable threshold go through the library's pinned
+    staging in several chunks, 3 fields, ragged last chunk; same bits as the small direct call"""
+    n = 3000
+    xa, ya = synth.clustered_nodes(n)
+    za = synth.values(n, 3)
+    w = make(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), host_chunk=70000, copy_threads=3,
+             pageable_min=100000)
+    xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
+    reps = 16                                            # 320000 queries: 4 full chunks + a ragged one
+    bx, by = np.tile(xq, reps), np.tile(yq, reps)
+    st, zq, leaf = w.eval_e(bx, by)
+    assert st == g.SUCCESS
+    assert np.array_equal(leaf, np.tile(golden["cfg3_leaf"], reps))
+    assert refimpl.same_bits(zq, np.tile(golden["cfg3_val"], (1, reps)))
+    st, _, leaf = w.eval_e(bx, by, want_values=False)    # leaf ids only
+    assert np.array_equal(leaf, np.tile(golden["cfg3_leaf"], reps))
+    st, zq, _ = w.eval_e(bx, by, want_leaf=False)        # values only
+    assert refimpl.same_bits(zq, np.tile(golden["cfg3_val"], (1, reps)))
+    w.free()

@@ -57,6 +57,12 @@ def _worker(rank, world, port, out_dir):
     s0, s1 = dist_util.split_range(rank, world, 1001)
     tot = torch.tensor([s1 - s0]); dist.all_reduce(tot)
     assert int(tot.item()) == 1001
+    # strong scaling (bench.py's scaling_strong leg): a FIXED stream of 5001 queries cut into `world` slices
+    s0, s1 = dist_util.split_range(rank, world, 5001)
+    xq, yq = synth.uniform_queries(s1 - s0, first=s0)
+    leaf, val, _ = port_tree.eval(xq, yq, za)
+    np.save(os.path.join(out_dir, f"sleaf{rank}.npy"), leaf)
+    np.save(os.path.join(out_dir, f"sval{rank}.npy"), val)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,3 +88,8 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     got_val = np.concatenate([np.load(tmp_path / f"val{r}.npy") for r in range(world)], axis=1)
     assert np.array_equal(got_leaf, leaf)
     assert refimpl.same_bits(got_val, val)
+    xq, yq = synth.uniform_queries(5001)
+    leaf, val, _ = refimpl.PortTree(tree, xa, ya).eval(xq, yq, za)
+    got_leaf = np.concatenate([np.load(tmp_path / f"sleaf{r}.npy") for r in range(world)])
+    got_val = np.concatenate([np.load(tmp_path / f"sval{r}.npy") for r in range(world)], axis=1)
+    assert np.array_equal(got_leaf, leaf) and refimpl.same_bits(got_val, val)
