@@ -1748,6 +1748,27 @@ gsl_scattered_cuda_checksum_device(const gsl_scattered_cuda *w, int dev, const i
 }
 
 int
+gsl_scattered_cuda_selftest_division(int dev, gsl_scattered_cuda_u64 seed, size_t n, gsl_scattered_cuda_u64 out[2])
+{
+  if (!out) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  if (gsl_scattered_cuda_device_count() <= 0) GSI_ERROR("no CUDA device available", GSL_SCATTERED_EFAILED);
+  device_guard restore;
+  CU(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  unsigned long long *d = nullptr;
+  CU(cudaMalloc(&d, 2 * sizeof *d));
+  cudaError_t e = gsi_launch_selftest_division(seed, n, d, prop.multiProcessorCount, nullptr);
+  unsigned long long h[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CU(e);
+  out[0] = h[0];
+  out[1] = h[1];
+  return GSL_SCATTERED_SUCCESS;
+}
+
+int
 gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, const int *d_leaf_a,
                                   const int *d_leaf_b, const double *d_val_a,
                                   const double *d_val_b, size_t n, size_t n_val,

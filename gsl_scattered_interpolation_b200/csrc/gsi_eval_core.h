@@ -467,6 +467,42 @@ gsi_walk_step(const gsi_xform *xf, const gsi_rec *r, double qx, double qy, int *
   return GSI_STEP_MOVE;
 }
 
+#if defined(__CUDACC__)
+/* gsi_walk_step for a record whose divisors' reciprocals (r11 for u11, r00 for u00, gsi_div_rcp) are
+ * at hand: the two divisions of the solve cost three operations each.  Same operations otherwise;
+ * when the hoisted division cannot vouch for a quotient the step defers (exact replay decides). */
+__device__ __forceinline__ int
+gsi_walk_step_rcp(const gsi_xform *xf, const gsi_rec *r, double r11, double r00, double qx, double qy, int *slot,
+                  double *c0, double *c1)
+{
+  const double tau = (double) GSI_BITS_TO_FLOAT(r->meta & 0x7fffffffu);
+  double b0 = GSI_MUL(GSI_SUB(qx, r->x0x), xf->sx);
+  double b1 = GSI_MUL(GSI_SUB(qy, r->x0y), xf->sy);
+  if (r->meta >> 31)
+    {
+      const double s = b0; b0 = b1; b1 = s;
+    }
+  unsigned bad = 0;
+  b1 = GSI_SUB(b1, GSI_MUL(r->l10, b0));
+  b1 = gsi_div_by_rcp(b1, r->u11, r11, &bad);
+  b0 = gsi_div_by_rcp(GSI_SUB(b0, GSI_MUL(r->u01, b1)), r->u00, r00, &bad);
+  *c0 = b0;
+  *c1 = b1;
+  if (bad) return GSI_STEP_DEFER;
+  const double c2 = GSI_SUB(1.0, GSI_ADD(GSI_ADD(0.0, b0), b1));
+  if ((b0 >= tau) && (b1 >= tau) && (c2 >= tau)) return GSI_STEP_ACCEPT;
+  int e = 0;
+  double m = b0;
+  if (b1 < m) { m = b1; e = 1; }
+  if (c2 < m) { m = c2; e = 2; }
+  if (!(m <= -tau)) return GSI_STEP_DEFER;
+  const int nb = GSI_LNK(*r, e);
+  if (nb < 0) return GSI_STEP_DEFER;
+  *slot = nb;
+  return GSI_STEP_MOVE;
+}
+#endif
+
 /* Fast path for one query, start to finish (host logic simulator; the device kernel runs
  * the same gsi_walk_step with lanes decoupled from queries).  Returns 1 when the query was
  * resolved (outputs written), 0 when it must be deferred.  *steps = leaves visited. */

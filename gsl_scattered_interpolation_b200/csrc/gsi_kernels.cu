@@ -526,6 +526,17 @@ k_bin(const gsi_tile_map M, const double *__restrict__ xq, const double *__restr
     {
       const size_t q0 = c * (size_t) S;
       const unsigned n = (unsigned) (nq - q0 < (size_t) S ? nq - q0 : (size_t) S);
+      /* the chunk this CTA sorts next: ask the L2 for its coordinates now (TMA bulk prefetch), so that the
+         loads of the next round hit the L2 instead of waiting for HBM between two barriers */
+      if (tid < 2 && c + gridDim.x < n_chunks)
+        {
+          const size_t qn = (c + gridDim.x) * (size_t) S;
+          const size_t nn = nq - qn < (size_t) S ? nq - qn : (size_t) S;
+          const double *src = (tid == 0 ? xq : yq) + qn;
+          const size_t lo = ((size_t) src + 15) & ~(size_t) 15, hi = ((size_t) (src + nn)) & ~(size_t) 15;
+          if (hi > lo)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned) (hi - lo)) : "memory");
+        }
       for (unsigned i = tid; i < (unsigned) nt; i += T) hist[i] = 0;
       __syncthreads();
       unsigned pk[KPT];
@@ -681,6 +692,7 @@ fetch_tail_smem(gsi_leaf_tail *t, const uint4 *p)
 struct gsi_tile_args
 {
   gsi_tile_map M;
+  double cax, cbx, cay, cby; /* grid cell of a query as one fused multiply-add per axis (a hint, like the bin) */
   const double *bx, *by;
   const unsigned short *bi;
   const unsigned *runs; /* [n_bins][n_chunks] */
@@ -700,6 +712,20 @@ struct gsi_tile_args
 
 #define GSI_SEED_FAR 0xffffu /* staged seed cell whose leaf lies outside the staged slot range */
 
+/* shared memory of k_tile_walk: leaf records | reciprocals of their two divisors | seed cells | one
+ * dense position list per warp */
+__host__ __device__ inline size_t
+tile_smem_seeds_at(int leaf_cap)
+{
+  return (size_t) leaf_cap * (96 + 16);
+}
+
+__host__ __device__ inline size_t
+tile_smem_spos_at(int leaf_cap, int seed_rows, int seed_pitch)
+{
+  return (tile_smem_seeds_at(leaf_cap) + (size_t) seed_rows * seed_pitch * 2 + 15) & ~(size_t) 15;
+}
+
 template <bool STATS, bool ONE_FIELD>
 __global__ void __launch_bounds__(GSI_TILE_THREADS, 1)
 k_tile_walk(const gsi_view V, const gsi_tile_args A)
@@ -708,15 +734,15 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
   __shared__ unsigned long long mbar;
   __shared__ unsigned s_item;
   uint4 *sleaf = reinterpret_cast<uint4 *>(smem_raw);
-  unsigned short *sseed = reinterpret_cast<unsigned short *>(sleaf + (size_t) A.leaf_cap * 6);
-  unsigned *spos_all = reinterpret_cast<unsigned *>(smem_raw + (((size_t) A.leaf_cap * 96 + (size_t) A.seed_rows * A.seed_pitch * 2 + 15) & ~(size_t) 15));
+  double2 *srcp = reinterpret_cast<double2 *>(smem_raw + (size_t) A.leaf_cap * 96);
+  unsigned short *sseed = reinterpret_cast<unsigned short *>(smem_raw + tile_smem_seeds_at(A.leaf_cap));
+  unsigned *spos_all = reinterpret_cast<unsigned *>(smem_raw + tile_smem_spos_at(A.leaf_cap, A.seed_rows, A.seed_pitch));
   const unsigned FULL = 0xffffffffu;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, WPC = blockDim.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned *spos = spos_all + (size_t) warp * GSI_TILE_SPOS;
   const unsigned n_blocks = (A.n_chunks + 31u) >> 5;
   const unsigned n_items = (unsigned) A.nt * (unsigned) A.ranges;
-  const double gmax = (double) (V.grid_g - 1);
   unsigned long long steps_acc = 0;
   unsigned parity = 0;
   if (tid == 0) mbar_init(&mbar, 1);
@@ -759,12 +785,28 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
               sseed[i] = rel < (unsigned) n_staged && rel < GSI_SEED_FAR ? (unsigned short) rel : (unsigned short) GSI_SEED_FAR;
             }
         }
-      __syncthreads(); /* seeds (and the fallback copy of the records) are visible */
       if (packed && n_staged > 0)
         {
           while (!mbar_try_wait(&mbar, parity)) {}
           parity ^= 1u;
         }
+      else
+        __syncthreads(); /* the fallback copy of the records is visible */
+      /* reciprocals of the two divisors of every staged record (gsi_div_rcp): the walk then divides
+         with three operations per quotient.  A divisor the hoisted division cannot serve makes the
+         leaf defer always (tau = +inf), like a singular leaf. */
+      for (int i = tid; i < n_staged; i += blockDim.x)
+        {
+          const uint4 b = sleaf[(size_t) i * 6 + 1], c = sleaf[(size_t) i * 6 + 2];
+          const double u00 = __hiloint2double((int) b.y, (int) b.x), u11 = __hiloint2double((int) c.y, (int) c.x);
+          srcp[i] = make_double2(gsi_div_rcp(u11), gsi_div_rcp(u00));
+          if (!(gsi_div_rcp_usable(u00) && gsi_div_rcp_usable(u11)))
+            {
+              unsigned *meta = reinterpret_cast<unsigned *>(sleaf + (size_t) i * 6 + 3) + 3;
+              *meta = (*meta & 0x80000000u) | 0x7f800000u;
+            }
+        }
+      __syncthreads(); /* seeds, records and reciprocals are visible */
 
       /* ---- walk the tile's queries ---- */
       const unsigned *runs_row = A.runs + (size_t) bin * A.n_chunks;
@@ -772,9 +814,11 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
       const unsigned cb_stride = (unsigned) A.ranges * WPC;
       unsigned r_pos0 = 0, r_len = 0, r_excl = 0; /* this lane's run of the current block */
       unsigned b_total = 0, win_lo = 0, win_n = 0, next = 0; /* block items, window [win_lo, win_lo + win_n), cursor */
-      bool cur_v = false;
-      double cur_x = 0, cur_y = 0;
-      unsigned cur_pos = 0;
+      /* a lane holds three queries: cur (walking), nxt and nn (coordinates on their way from HBM), so the
+         streaming loads of the binned coordinates are two refills ahead of their use */
+      bool cur_v = false, nxt_v = false, nn_v = false;
+      double cur_x = 0, cur_y = 0, nxt_x = 0, nxt_y = 0, nn_x = 0, nn_y = 0;
+      unsigned cur_pos = 0, nxt_pos = 0, nn_pos = 0;
       int cur_slot = 0, cur_steps = 0;
       for (;;)
         {
@@ -817,36 +861,38 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                   __syncwarp();
                   if (win_n == 0) continue; /* empty block */
                 }
-              else if (!__any_sync(FULL, cur_v))
+              else if (!__any_sync(FULL, cur_v || nxt_v || nn_v))
                 break;
             }
-          /* refill: a lane without a query takes the next position of the list */
+          /* refill: a lane without a query shifts its pipeline and takes the next position of the list */
           bool defer = false;
           const bool need = !cur_v;
           const unsigned take = __ballot_sync(FULL, need);
           if (need)
             {
+              cur_v = nxt_v; cur_pos = nxt_pos; cur_x = nxt_x; cur_y = nxt_y;
+              cur_steps = 0;
+              nxt_v = nn_v; nxt_pos = nn_pos; nxt_x = nn_x; nxt_y = nn_y;
               const unsigned off = next + __popc(take & lt_mask);
-              if (off < win_n)
+              nn_v = off < win_n;
+              if (nn_v)
                 {
-                  cur_pos = spos[off];
-                  cur_x = __ldcs(A.bx + cur_pos);
-                  cur_y = __ldcs(A.by + cur_pos);
-                  cur_steps = 0;
-                  cur_v = true;
-                  if (isfinite(cur_x) && isfinite(cur_y))
-                    {
-                      /* the cell of gsi_cell_of; its seed from the staged block when it is inside */
-                      const double u = (cur_x - V.xf.cx) * V.xf.sx, v = (cur_y - V.xf.cy) * V.xf.sy;
-                      const int ix = __double2int_rd(fmin(fmax((u - V.u0) * V.inv_du, 0.0), gmax));
-                      const int iy = __double2int_rd(fmin(fmax((v - V.v0) * V.inv_dv, 0.0), gmax));
-                      const unsigned rx = (unsigned) (ix - cx0), ry = (unsigned) (iy - cy0);
-                      unsigned rel = GSI_SEED_FAR;
-                      if (rx < (unsigned) ncx && ry < (unsigned) ncy) rel = sseed[ry * A.seed_pitch + rx];
-                      cur_slot = rel != GSI_SEED_FAR ? slot0 + (int) rel
-                                                     : gsi_ld_seed(V.seeds + (size_t) iy * (size_t) V.grid_g + (size_t) ix);
-                    }
-                  else
+                  nn_pos = spos[off];
+                  nn_x = __ldcs(A.bx + nn_pos);
+                  nn_y = __ldcs(A.by + nn_pos);
+                }
+              if (cur_v)
+                {
+                  /* grid cell (one fused multiply-add per axis; NaN -> 0, +-inf saturate) and its seed from
+                     the staged block when it is inside */
+                  const int ix = min(max(__double2int_rd(__fma_rn(cur_x, A.cax, A.cbx)), 0), V.grid_g - 1);
+                  const int iy = min(max(__double2int_rd(__fma_rn(cur_y, A.cay, A.cby)), 0), V.grid_g - 1);
+                  const unsigned rx = (unsigned) (ix - cx0), ry = (unsigned) (iy - cy0);
+                  unsigned rel = GSI_SEED_FAR;
+                  if (rx < (unsigned) ncx && ry < (unsigned) ncy) rel = sseed[ry * A.seed_pitch + rx];
+                  cur_slot = rel != GSI_SEED_FAR ? slot0 + (int) rel
+                                                 : gsi_ld_seed(V.seeds + (size_t) iy * (size_t) V.grid_g + (size_t) ix);
+                  if (!(isfinite(cur_x) && isfinite(cur_y)))
                     {
                       defer = true;
                       cur_v = false;
@@ -861,12 +907,19 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
               const int at = cur_slot;
               const unsigned rel = (unsigned) (at - slot0);
               const bool staged = rel < (unsigned) n_staged;
-              if (staged)
-                fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
-              else
-                gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
               double c0, c1;
-              const int st = gsi_walk_step(&V.xf, &rec, cur_x, cur_y, &cur_slot, &c0, &c1);
+              int st;
+              if (staged)
+                {
+                  fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
+                  const double2 rc = srcp[rel];
+                  st = gsi_walk_step_rcp(&V.xf, &rec, rc.x, rc.y, cur_x, cur_y, &cur_slot, &c0, &c1);
+                }
+              else
+                {
+                  gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
+                  st = gsi_walk_step(&V.xf, &rec, cur_x, cur_y, &cur_slot, &c0, &c1);
+                }
               ++cur_steps;
               if (st == GSI_STEP_ACCEPT)
                 {
@@ -1092,6 +1145,57 @@ k_validate_slab(const gsi_view V, unsigned long long n_points, unsigned long lon
   if (mine) atomicAdd(bad, mine);
 }
 
+/* self-test of the hoisted-reciprocal division (gsi_core.h): operand pairs from four families
+ * (data-like magnitudes, raw random bit patterns, mixed, scaled over the whole exponent range);
+ * out[0] = pairs the fast path vouched for, out[1] = of those, quotients that differ from __ddiv_rn */
+__global__ void __launch_bounds__(256)
+k_selftest_division(uint64_t seed, size_t n, unsigned long long *out)
+{
+  unsigned long long ok = 0, bad = 0;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+      uint64_t z[3];
+      for (int k = 0; k < 3; k++)
+        {
+          uint64_t v = seed + (3 * i + k + 1) * 0x9E3779B97F4A7C15ull;
+          v ^= v >> 30; v *= 0xBF58476D1CE4E5B9ull;
+          v ^= v >> 27; v *= 0x94D049BB133111EBull;
+          v ^= v >> 31;
+          z[k] = v;
+        }
+      const double ua = ((double) (z[0] >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 8.0;
+      const double ub = ((double) (z[1] >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 8.0;
+      double a, b;
+      switch (i & 3)
+        {
+        case 0: a = ua; b = ub; break;
+        case 1: a = __longlong_as_double((long long) z[0]); b = __longlong_as_double((long long) z[1]); break;
+        case 2: a = __longlong_as_double((long long) z[0]); b = ub; break;
+        default:
+          a = scalbn(ua, (int) (z[2] % 2200u) - 1100);
+          b = scalbn(ub, (int) ((z[2] >> 32) % 2200u) - 1100);
+          break;
+        }
+      if (!gsi_div_rcp_usable(b)) continue;
+      unsigned flag = 0;
+      const double q = gsi_div_by_rcp(a, b, gsi_div_rcp(b), &flag);
+      if (flag) continue;
+      ok++;
+      bad += __double_as_longlong(q) != __double_as_longlong(__ddiv_rn(a, b));
+    }
+  for (int o = 16; o > 0; o >>= 1)
+    {
+      ok += __shfl_xor_sync(0xffffffffu, ok, o);
+      bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+  if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd(out, ok);
+      if (bad) atomicAdd(out + 1, bad);
+    }
+}
+
 __global__ void
 k_accumulate_deferred(unsigned *counters)
 {
@@ -1168,11 +1272,16 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
       seed_bytes = 0;
     }
   int leaf_cap = R->tile_max_leaves < 1 ? 1 : R->tile_max_leaves;
-  const size_t room = (budget - seed_bytes - spos_bytes - 16) / 96;
+  const size_t room = (budget - seed_bytes - spos_bytes - 16) / (96 + 16);
   if ((size_t) leaf_cap > room) leaf_cap = (int) room;
   if (leaf_cap > 65000) leaf_cap = 65000; /* 16-bit relative seeds */
   A.leaf_cap = leaf_cap;
-  const size_t smem_tile = (((size_t) leaf_cap * 96 + seed_bytes + 15) & ~(size_t) 15) + spos_bytes;
+  const size_t smem_tile = tile_smem_spos_at(leaf_cap, A.seed_rows, A.seed_pitch) + spos_bytes;
+  /* cell = floor(((q - c) * s - u0) * inv_du) as one fused multiply-add per axis */
+  A.cax = V.xf.sx * V.inv_du;
+  A.cbx = (-V.xf.cx * V.xf.sx - V.u0) * V.inv_du;
+  A.cay = V.xf.sy * V.inv_dv;
+  A.cby = (-V.xf.cy * V.xf.sy - V.v0) * V.inv_dv;
   /* work items per tile: a few dozen items per CTA for balance, at least two 32-chunk blocks per warp */
   const size_t n_blocks = (n_chunks + 31) / 32;
   int ranges = R->ranges;
@@ -1370,5 +1479,14 @@ gsi_launch_deriv(const gsi_view &V, const int *leaf, size_t nq, double *dzdx, do
 {
   if (nq == 0) return cudaSuccess;
   k_deriv<<<grid_for(nq, 256, sm_count, 8), 256, 0, st>>>(V, leaf, nq, dzdx, dzdy, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_selftest_division(uint64_t seed, size_t n, unsigned long long *out2, int sm_count, cudaStream_t st)
+{
+  cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(unsigned long long), st);
+  if (e != cudaSuccess || n == 0) return e;
+  k_selftest_division<<<grid_for(n, 256, sm_count, 8), 256, 0, st>>>(seed, n, out2);
   return cudaGetLastError();
 }

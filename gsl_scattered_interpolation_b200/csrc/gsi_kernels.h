@@ -104,6 +104,10 @@ cudaError_t gsi_launch_deriv(const gsi_view &V, const int *leaf, size_t nq, doub
 /* count out-of-range indices in an adopted slab image (*bad, device memory) */
 cudaError_t gsi_launch_validate_slab(const gsi_view &V, unsigned long long *bad, int sm_count, cudaStream_t st);
 
+/* hoisted-reciprocal division against __ddiv_rn on n operand pairs: out2[0] = pairs vouched for,
+ * out2[1] = mismatches among them (device memory) */
+cudaError_t gsi_launch_selftest_division(uint64_t seed, size_t n, unsigned long long *out2, int sm_count, cudaStream_t st);
+
 cudaError_t gsi_launch_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo,
                                    double xhi, double ylo, double yhi, double *xq, double *yq,
                                    int sm_count, cudaStream_t st);

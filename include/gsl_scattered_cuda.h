@@ -306,6 +306,14 @@ int gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, cons
                                       const double *d_val_b, size_t n, size_t n_val,
                                       gsl_scattered_cuda_u64 out[2], void *stream);
 
+/* Diagnostic: the tile kernel of the reorder pipeline divides by per-leaf constants with the
+ * divisor's reciprocal hoisted out (csrc/gsi_core.h: the operations of nvcc's own binary64 division,
+ * split at the point where they stop depending on the divisor only).  This runs n operand pairs
+ * (data-like, raw bit patterns, the whole exponent range) on device `dev`: out[0] = pairs the
+ * hoisted form vouched for, out[1] = quotients among them that differ from __ddiv_rn (must be 0). */
+int gsl_scattered_cuda_selftest_division(int dev, gsl_scattered_cuda_u64 seed, size_t n,
+                                         gsl_scattered_cuda_u64 out[2]);
+
 const char *gsl_scattered_cuda_version(void);
 
 #ifdef __cplusplus

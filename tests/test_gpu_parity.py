@@ -578,3 +578,19 @@ def test_pageable_host_arrays_are_staged_through_pinned_buffers(golden):
     st, zq, _ = w.eval_e(bx, by, want_leaf=False)        # values only
     assert refimpl.same_bits(zq, np.tile(golden["cfg3_val"], (1, reps)))
     w.free()
+
+
+def test_division_by_hoisted_reciprocal():
+    """csrc/gsi_core.h: gsi_div_rcp / gsi_div_by_rcp are nvcc's own binary64 division split where it
+    stops depending on the divisor only.  On 10^9 operand pairs -- data-like magnitudes, raw random
+    bit patterns (NaN, inf, denormals), mixed, and the whole exponent range -- every quotient the
+    hoisted form vouches for must be bit-identical to __ddiv_rn; the rest is deferred by design."""
+    import ctypes
+    from gsl_scattered_interpolation_b200 import _lib
+    L = _lib.load()
+    out = (ctypes.c_ulonglong * 2)()
+    n = 1_000_000_000
+    assert L.gsl_scattered_cuda_selftest_division(0, 20260004, n, out) == g.SUCCESS
+    vouched, mismatches = int(out[0]), int(out[1])
+    assert mismatches == 0
+    assert vouched > 0.3 * n                    # the data-like family is never deferred, the wild ones mostly are

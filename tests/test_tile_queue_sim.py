@@ -21,6 +21,8 @@ def simulate(runs, S, ranges, rng_id, wpc, warp, rng, p_accept=0.75, p_defer=0.0
     r_pos0 = np.zeros(32, dtype=np.int64); r_len = np.zeros(32, dtype=np.int64); r_excl = np.zeros(32, dtype=np.int64)
     b_total = win_lo = win_n = nxt = 0
     cur_v = np.zeros(32, dtype=bool); cur_pos = np.zeros(32, dtype=np.int64); cur_steps = np.zeros(32, dtype=np.int64)
+    nxt_v = np.zeros(32, dtype=bool); nxt_pos = np.zeros(32, dtype=np.int64)      # coordinates on their way (one refill ahead)
+    nn_v = np.zeros(32, dtype=bool); nn_pos = np.zeros(32, dtype=np.int64)        # ... two refills ahead
     spos = np.full(SPOS, -1, dtype=np.int64)
     done = []
     it = 0
@@ -58,18 +60,19 @@ def simulate(runs, S, ranges, rng_id, wpc, warp, rng, p_accept=0.75, p_defer=0.0
                         spos[r_excl[l] + k - win_lo] = r_pos0[l] + k
                 if win_n == 0:
                     continue
-            elif not cur_v.any():
+            elif not (cur_v | nxt_v | nn_v).any():
                 break
         need = ~cur_v
         rank = np.cumsum(need) - need
         for l in range(32):
             if need[l]:
+                cur_v[l], cur_pos[l], cur_steps[l] = nxt_v[l], nxt_pos[l], 0
+                nxt_v[l], nxt_pos[l] = nn_v[l], nn_pos[l]
                 off = nxt + rank[l]
-                if off < win_n:
+                nn_v[l] = off < win_n
+                if nn_v[l]:
                     assert spos[off] >= 0
-                    cur_pos[l] = spos[off]
-                    cur_steps[l] = 0
-                    cur_v[l] = True
+                    nn_pos[l] = spos[off]
         nxt = min(nxt + int(need.sum()), win_n)
         for l in range(32):
             if cur_v[l]:
