@@ -711,9 +711,10 @@ struct gsi_tile_args
 };
 
 #define GSI_SEED_FAR 0xffffu /* staged seed cell whose leaf lies outside the staged slot range */
+#define GSI_TILE_RING 64     /* per-warp ring of queries whose walk left the staged tile */
 
-/* shared memory of k_tile_walk: leaf records | reciprocals of their two divisors | seed cells | one
- * dense position list per warp */
+/* shared memory of k_tile_walk: leaf records | reciprocals of their two divisors | seed cells | per
+ * warp: a dense position list and a ring of stragglers (position, leaf slot) */
 __host__ __device__ inline size_t
 tile_smem_seeds_at(int leaf_cap)
 {
@@ -721,9 +722,32 @@ tile_smem_seeds_at(int leaf_cap)
 }
 
 __host__ __device__ inline size_t
-tile_smem_spos_at(int leaf_cap, int seed_rows, int seed_pitch)
+tile_smem_warp_at(int leaf_cap, int seed_rows, int seed_pitch)
 {
   return (tile_smem_seeds_at(leaf_cap) + (size_t) seed_rows * seed_pitch * 2 + 15) & ~(size_t) 15;
+}
+
+#define GSI_TILE_WARP_WORDS (GSI_TILE_SPOS + 2 * GSI_TILE_RING)
+
+/* Predicated streaming loads INTO an existing register: no temporary and no move, so nothing
+ * touches the value before its consumer one loop iteration later (a compiler-placed move right
+ * behind a plain load makes the warp wait for HBM at once -- measured: 19 % of all stall samples). */
+__device__ __forceinline__ void
+ld_stream_if(bool p, double &dst, const double *src)
+{
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.cs.f64 %0, [%1];\n\t}"
+               : "+d"(dst)
+               : "l"(src), "r"((unsigned) p)
+               : "memory");
+}
+
+__device__ __forceinline__ void
+ld_nc_if(bool p, unsigned &dst, const unsigned *src)
+{
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+               : "+r"(dst)
+               : "l"(src), "r"((unsigned) p)
+               : "memory");
 }
 
 template <bool STATS, bool ONE_FIELD>
@@ -732,20 +756,53 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ unsigned long long mbar;
-  __shared__ unsigned s_item;
+  __shared__ unsigned s_item, s_next_block;
   uint4 *sleaf = reinterpret_cast<uint4 *>(smem_raw);
   double2 *srcp = reinterpret_cast<double2 *>(smem_raw + (size_t) A.leaf_cap * 96);
   unsigned short *sseed = reinterpret_cast<unsigned short *>(smem_raw + tile_smem_seeds_at(A.leaf_cap));
-  unsigned *spos_all = reinterpret_cast<unsigned *>(smem_raw + tile_smem_spos_at(A.leaf_cap, A.seed_rows, A.seed_pitch));
   const unsigned FULL = 0xffffffffu;
-  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, WPC = blockDim.x >> 5;
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned *spos = spos_all + (size_t) warp * GSI_TILE_SPOS;
+  unsigned *spos = reinterpret_cast<unsigned *>(smem_raw + tile_smem_warp_at(A.leaf_cap, A.seed_rows, A.seed_pitch))
+                   + (size_t) warp * GSI_TILE_WARP_WORDS;
+  unsigned *sg_pos = spos + GSI_TILE_SPOS;
+  int *sg_slot = reinterpret_cast<int *>(sg_pos + GSI_TILE_RING);
   const unsigned n_blocks = (A.n_chunks + 31u) >> 5;
   const unsigned n_items = (unsigned) A.nt * (unsigned) A.ranges;
   unsigned long long steps_acc = 0;
   unsigned parity = 0;
   if (tid == 0) mbar_init(&mbar, 1);
+
+  /* warp-aggregated append to the deferred list (original query index of binned position pos) */
+  auto append_deferred = [&](bool defer, unsigned pos) {
+    const unsigned dm = __ballot_sync(FULL, defer);
+    if (!dm) return;
+    const int leader = __ffs(dm) - 1;
+    unsigned at0 = 0;
+    if (lane == (unsigned) leader) at0 = atomicAdd(A.counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+    at0 = __shfl_sync(FULL, at0, leader);
+    if (defer)
+      {
+        const size_t q = (size_t) (pos / (unsigned) A.S) * (size_t) A.S + A.bi[pos];
+        const unsigned at = at0 + __popc(dm & lt_mask);
+        if (at < A.list_cap)
+          A.list[at] = (unsigned) q;
+        else
+          mark_overflow(A.ovf_mask, q, A.counters);
+      }
+  };
+  /* result of an accepted query */
+  auto store_result = [&](unsigned pos, const gsi_leaf_tail &tl, double c0, double c1) {
+    if (A.lb) __stcs(A.lb + pos, tl.g.node);
+    if (A.zb)
+      {
+        if (ONE_FIELD)
+          __stcs(A.zb + pos, gsi_blend(c0, c1, (int) (tl.s.vflags & 1u), tl.s.z[0], (int) (tl.s.vflags & 2u), tl.s.z[1],
+                                       (int) (tl.s.vflags & 4u), tl.s.z[2]));
+        else
+          gsi_blend_store(&V, &tl, c0, c1, A.zb, A.ldb, pos);
+      }
+  };
 
   for (;;)
     {
@@ -759,14 +816,18 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
       const int n_staged = min(V.tiles[prefix + 1] - slot0, A.leaf_cap);
       const bool packed = V.leaf_stride == (int) sizeof(gsi_leaf);
       /* ---- stage the tile: leaf records by TMA bulk copy, seed cells by the threads ---- */
-      if (packed && n_staged > 0 && tid == 0)
+      if (tid == 0)
         {
-          const unsigned bytes = (unsigned) n_staged * 96u;
-          const char *src = V.leaf + (size_t) slot0 * sizeof(gsi_leaf);
-          fence_proxy_async();
-          mbar_arrive_expect_tx(&mbar, bytes);
-          for (unsigned o = 0; o < bytes; o += 32768u)
-            bulk_load(reinterpret_cast<char *>(sleaf) + o, src + o, min(32768u, bytes - o), &mbar);
+          s_next_block = 0;
+          if (packed && n_staged > 0)
+            {
+              const unsigned bytes = (unsigned) n_staged * 96u;
+              const char *src = V.leaf + (size_t) slot0 * sizeof(gsi_leaf);
+              fence_proxy_async();
+              mbar_arrive_expect_tx(&mbar, bytes);
+              for (unsigned o = 0; o < bytes; o += 32768u)
+                bulk_load(reinterpret_cast<char *>(sleaf) + o, src + o, min(32768u, bytes - o), &mbar);
+            }
         }
       if (!packed)
         for (int i = tid; i < n_staged * 6; i += blockDim.x)
@@ -806,20 +867,87 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
               *meta = (*meta & 0x80000000u) | 0x7f800000u;
             }
         }
-      __syncthreads(); /* seeds, records and reciprocals are visible */
+      __syncthreads(); /* seeds, records, reciprocals and the block counter are visible */
 
-      /* ---- walk the tile's queries ---- */
+      /* ---- walk the tile's queries ----
+       * The item's 32-chunk blocks (block k of this item = chunks of block range + k * ranges) are
+       * handed to the warps by a shared counter; the run word of a warp's next block is loaded while
+       * it still works on the current one. */
       const unsigned *runs_row = A.runs + (size_t) bin * A.n_chunks;
-      unsigned cb = range * WPC + warp;
-      const unsigned cb_stride = (unsigned) A.ranges * WPC;
+      unsigned cb_nxt = 0, run_nxt = 0;
+      auto grab_block = [&]() {
+        unsigned k = 0;
+        if (lane == 0) k = atomicAdd(&s_next_block, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        cb_nxt = range + k * (unsigned) A.ranges;
+        const unsigned c = (cb_nxt << 5) + lane;
+        run_nxt = 0;
+        ld_nc_if(cb_nxt < n_blocks && c < A.n_chunks, run_nxt, runs_row + c);
+      };
+      grab_block();
       unsigned r_pos0 = 0, r_len = 0, r_excl = 0; /* this lane's run of the current block */
       unsigned b_total = 0, win_lo = 0, win_n = 0, next = 0; /* block items, window [win_lo, win_lo + win_n), cursor */
-      /* a lane holds three queries: cur (walking), nxt and nn (coordinates on their way from HBM), so the
-         streaming loads of the binned coordinates are two refills ahead of their use */
-      bool cur_v = false, nxt_v = false, nn_v = false;
-      double cur_x = 0, cur_y = 0, nxt_x = 0, nxt_y = 0, nn_x = 0, nn_y = 0;
-      unsigned cur_pos = 0, nxt_pos = 0, nn_pos = 0;
+      unsigned sg_head = 0, sg_count = 0;                     /* ring of stragglers (warp-uniform) */
+      /* a lane holds two queries: cur (walking) and nxt (coordinates on their way from HBM, requested one
+         loop iteration -- longer than the HBM latency -- before they are needed) */
+      bool cur_v = false, nxt_v = false;
+      double cur_x = 0, cur_y = 0, nxt_x = 0, nxt_y = 0;
+      unsigned cur_pos = 0, nxt_pos = 0;
       int cur_slot = 0, cur_steps = 0;
+
+      /* Queries whose walk left the staged slot range (seed or neighbour in another tile; ~6 %) wait
+         in the ring until a full batch can take the global-memory path together: one lane fetching
+         from HBM while 31 wait was 13 % of the kernel. */
+      auto run_stragglers = [&](unsigned n) {
+        bool act = lane < n, dfr = false;
+        unsigned pos = 0;
+        int slot = 0, steps = 0;
+        double x = 0, y = 0;
+        if (act)
+          {
+            const unsigned e = (sg_head + lane) & (GSI_TILE_RING - 1);
+            pos = sg_pos[e];
+            slot = sg_slot[e];
+            x = __ldcs(A.bx + pos);
+            y = __ldcs(A.by + pos);
+            if (slot < 0)
+              {
+                const int ix = min(max(__double2int_rd(__fma_rn(x, A.cax, A.cbx)), 0), V.grid_g - 1);
+                const int iy = min(max(__double2int_rd(__fma_rn(y, A.cay, A.cby)), 0), V.grid_g - 1);
+                slot = gsi_ld_seed(V.seeds + (size_t) iy * (size_t) V.grid_g + (size_t) ix);
+              }
+          }
+        sg_head = (sg_head + n) & (GSI_TILE_RING - 1);
+        sg_count -= n;
+        while (__any_sync(FULL, act))
+          {
+            if (act)
+              {
+                gsi_rec rec;
+                const int at = slot;
+                double c0, c1;
+                gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
+                const int st = gsi_walk_step(&V.xf, &rec, x, y, &slot, &c0, &c1);
+                ++steps;
+                if (st == GSI_STEP_ACCEPT)
+                  {
+                    gsi_leaf_tail tl;
+                    gsi_fetch_tail(&tl, gsi_leaf_at(&V, at));
+                    store_result(pos, tl, c0, c1);
+                    if (STATS) steps_acc += (unsigned) steps;
+                    act = false;
+                  }
+                else if (st == GSI_STEP_DEFER || steps >= A.max_steps)
+                  {
+                    dfr = true;
+                    act = false;
+                  }
+              }
+          }
+        append_deferred(dfr, pos);
+        __syncwarp();
+      };
+
       for (;;)
         {
           if (next >= win_n) /* warp-uniform: the dense list is used up */
@@ -828,12 +956,11 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
               win_lo += win_n; /* items of the current block handed out so far */
               if (win_lo < b_total)
                 ; /* next window of a block that exceeds the list */
-              else if (cb < n_blocks)
+              else if (cb_nxt < n_blocks)
                 {
-                  const unsigned c = (cb << 5) + lane;
-                  const unsigned run = c < A.n_chunks ? __ldg(runs_row + c) : 0u;
-                  const unsigned start = run & 0xffffu;
-                  r_len = (run >> 16) - start;
+                  const unsigned c = (cb_nxt << 5) + lane;
+                  const unsigned start = run_nxt & 0xffffu;
+                  r_len = (run_nxt >> 16) - start;
                   r_pos0 = c * (unsigned) A.S + start;
                   unsigned incl = r_len;
 #pragma unroll
@@ -845,7 +972,7 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                   r_excl = incl - r_len;
                   b_total = __shfl_sync(FULL, incl, 31);
                   win_lo = 0;
-                  cb += cb_stride;
+                  grab_block();
                 }
               else
                 have = false;
@@ -861,10 +988,10 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                   __syncwarp();
                   if (win_n == 0) continue; /* empty block */
                 }
-              else if (!__any_sync(FULL, cur_v || nxt_v || nn_v))
+              else if (!__any_sync(FULL, cur_v || nxt_v))
                 break;
             }
-          /* refill: a lane without a query shifts its pipeline and takes the next position of the list */
+          /* refill: a lane without a query takes over its prefetched one and requests the next position of the list */
           bool defer = false;
           const bool need = !cur_v;
           const unsigned take = __ballot_sync(FULL, need);
@@ -872,15 +999,11 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
             {
               cur_v = nxt_v; cur_pos = nxt_pos; cur_x = nxt_x; cur_y = nxt_y;
               cur_steps = 0;
-              nxt_v = nn_v; nxt_pos = nn_pos; nxt_x = nn_x; nxt_y = nn_y;
               const unsigned off = next + __popc(take & lt_mask);
-              nn_v = off < win_n;
-              if (nn_v)
-                {
-                  nn_pos = spos[off];
-                  nn_x = __ldcs(A.bx + nn_pos);
-                  nn_y = __ldcs(A.by + nn_pos);
-                }
+              nxt_v = off < win_n;
+              if (nxt_v) nxt_pos = spos[off];
+              ld_stream_if(nxt_v, nxt_x, A.bx + nxt_pos);
+              ld_stream_if(nxt_v, nxt_y, A.by + nxt_pos);
               if (cur_v)
                 {
                   /* grid cell (one fused multiply-add per axis; NaN -> 0, +-inf saturate) and its seed from
@@ -890,8 +1013,8 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                   const unsigned rx = (unsigned) (ix - cx0), ry = (unsigned) (iy - cy0);
                   unsigned rel = GSI_SEED_FAR;
                   if (rx < (unsigned) ncx && ry < (unsigned) ncy) rel = sseed[ry * A.seed_pitch + rx];
-                  cur_slot = rel != GSI_SEED_FAR ? slot0 + (int) rel
-                                                 : gsi_ld_seed(V.seeds + (size_t) iy * (size_t) V.grid_g + (size_t) ix);
+                  /* a seed outside the staged range is looked up by the straggler path (slot -1) */
+                  cur_slot = rel != GSI_SEED_FAR ? slot0 + (int) rel : -1;
                   if (!(isfinite(cur_x) && isfinite(cur_y)))
                     {
                       defer = true;
@@ -900,43 +1023,22 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                 }
             }
           next = min(next + (unsigned) __popc(take), win_n);
-          /* one walk step for every lane that holds a query */
-          if (cur_v)
+          /* one walk step out of shared memory for every lane that holds a query inside the staged tile */
+          const unsigned rel = (unsigned) (cur_slot - slot0);
+          const bool staged = rel < (unsigned) n_staged;
+          if (cur_v && staged)
             {
               gsi_rec rec;
-              const int at = cur_slot;
-              const unsigned rel = (unsigned) (at - slot0);
-              const bool staged = rel < (unsigned) n_staged;
               double c0, c1;
-              int st;
-              if (staged)
-                {
-                  fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
-                  const double2 rc = srcp[rel];
-                  st = gsi_walk_step_rcp(&V.xf, &rec, rc.x, rc.y, cur_x, cur_y, &cur_slot, &c0, &c1);
-                }
-              else
-                {
-                  gsi_fetch_rec(&rec, gsi_leaf_at(&V, at));
-                  st = gsi_walk_step(&V.xf, &rec, cur_x, cur_y, &cur_slot, &c0, &c1);
-                }
+              fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
+              const double2 rc = srcp[rel];
+              const int st = gsi_walk_step_rcp(&V.xf, &rec, rc.x, rc.y, cur_x, cur_y, &cur_slot, &c0, &c1);
               ++cur_steps;
               if (st == GSI_STEP_ACCEPT)
                 {
                   gsi_leaf_tail tl;
-                  if (staged)
-                    fetch_tail_smem(&tl, sleaf + (size_t) rel * 6);
-                  else
-                    gsi_fetch_tail(&tl, gsi_leaf_at(&V, at));
-                  if (A.lb) __stcs(A.lb + cur_pos, tl.g.node);
-                  if (A.zb)
-                    {
-                      if (ONE_FIELD)
-                        __stcs(A.zb + cur_pos, gsi_blend(c0, c1, (int) (tl.s.vflags & 1u), tl.s.z[0], (int) (tl.s.vflags & 2u),
-                                                         tl.s.z[1], (int) (tl.s.vflags & 4u), tl.s.z[2]));
-                      else
-                        gsi_blend_store(&V, &tl, c0, c1, A.zb, A.ldb, cur_pos);
-                    }
+                  fetch_tail_smem(&tl, sleaf + (size_t) rel * 6);
+                  store_result(cur_pos, tl, c0, c1);
                   if (STATS) steps_acc += (unsigned) cur_steps;
                   cur_v = false;
                 }
@@ -946,25 +1048,25 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                   cur_v = false;
                 }
             }
-          /* warp-aggregated append to the deferred list (original query index) */
-          const unsigned dm = __ballot_sync(FULL, defer);
-          if (dm)
+          /* lanes whose leaf is not staged hand their query to the ring */
+          const bool push = cur_v && !staged;
+          const unsigned pm = __ballot_sync(FULL, push);
+          if (pm)
             {
-              const int leader = __ffs(dm) - 1;
-              unsigned at0 = 0;
-              if (lane == (unsigned) leader) at0 = atomicAdd(A.counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
-              at0 = __shfl_sync(FULL, at0, leader);
-              if (defer)
+              if (push)
                 {
-                  const size_t q = (size_t) (cur_pos / (unsigned) A.S) * (size_t) A.S + A.bi[cur_pos];
-                  const unsigned at = at0 + __popc(dm & lt_mask);
-                  if (at < A.list_cap)
-                    A.list[at] = (unsigned) q;
-                  else
-                    mark_overflow(A.ovf_mask, q, A.counters);
+                  const unsigned e = (sg_head + sg_count + __popc(pm & lt_mask)) & (GSI_TILE_RING - 1);
+                  sg_pos[e] = cur_pos;
+                  sg_slot[e] = cur_slot;
+                  cur_v = false;
                 }
+              sg_count += __popc(pm);
+              __syncwarp();
             }
+          append_deferred(defer, cur_pos);
+          if (sg_count >= 32) run_stragglers(32);
         }
+      while (sg_count > 0) run_stragglers(min(sg_count, 32u));
     }
   if (STATS && steps_acc)
     atomicAdd(reinterpret_cast<unsigned long long *>(A.counters + GSI_CNT_STEPS), steps_acc);
@@ -1263,7 +1365,7 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
   A.seed_pitch = (V.grid_g >> M.bx_bits) + 4;
   A.seed_rows = (V.grid_g >> M.by_bits) + 4;
   const size_t budget = 227 * 1024 - 512;
-  const size_t spos_bytes = (size_t) wpc * GSI_TILE_SPOS * 4;
+  const size_t spos_bytes = (size_t) wpc * GSI_TILE_WARP_WORDS * 4; /* dense list + straggler ring per warp */
   size_t seed_bytes = (size_t) A.seed_pitch * A.seed_rows * 2;
   if (seed_bytes + spos_bytes + 4096 > budget)
     {
@@ -1276,7 +1378,7 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
   if ((size_t) leaf_cap > room) leaf_cap = (int) room;
   if (leaf_cap > 65000) leaf_cap = 65000; /* 16-bit relative seeds */
   A.leaf_cap = leaf_cap;
-  const size_t smem_tile = tile_smem_spos_at(leaf_cap, A.seed_rows, A.seed_pitch) + spos_bytes;
+  const size_t smem_tile = tile_smem_warp_at(leaf_cap, A.seed_rows, A.seed_pitch) + spos_bytes;
   /* cell = floor(((q - c) * s - u0) * inv_du) as one fused multiply-add per axis */
   A.cax = V.xf.sx * V.inv_du;
   A.cbx = (-V.xf.cx * V.xf.sx - V.u0) * V.inv_du;
