@@ -713,15 +713,12 @@ struct gsi_tile_args
 #define GSI_SEED_FAR 0xffffu /* staged seed cell whose leaf lies outside the staged slot range */
 #define GSI_TILE_RING 64     /* per-warp ring of queries whose walk left the staged tile */
 
-/* shared memory of k_tile_walk: leaf records, 112 bytes apart (the 96-byte record + the
- * reciprocals of its two divisors; 7 x 16 bytes, an ODD number of 16-byte bank groups, so that the
- * 128-bit reads of random records spread over all eight groups -- at the packed 96-byte stride they
- * fall on four) | seed cells | per warp: a dense position list and a ring of stragglers */
-#define GSI_TILE_REC16 7 /* 16-byte units per staged record */
+/* shared memory of k_tile_walk: leaf records | reciprocals of their two divisors | seed cells | per
+ * warp: a dense position list and a ring of stragglers (position, leaf slot) */
 __host__ __device__ inline size_t
 tile_smem_seeds_at(int leaf_cap)
 {
-  return (size_t) leaf_cap * (GSI_TILE_REC16 * 16);
+  return (size_t) leaf_cap * (96 + 16);
 }
 
 __host__ __device__ inline size_t
@@ -732,6 +729,27 @@ tile_smem_warp_at(int leaf_cap, int seed_rows, int seed_pitch)
 
 #define GSI_TILE_WARP_WORDS (GSI_TILE_SPOS + 2 * GSI_TILE_RING)
 
+/* Predicated streaming loads INTO an existing register: no temporary and no move, so nothing
+ * touches the value before its consumer one loop iteration later (a compiler-placed move right
+ * behind a plain load makes the warp wait for HBM at once -- measured: 19 % of all stall samples). */
+__device__ __forceinline__ void
+ld_stream_if(bool p, double &dst, const double *src)
+{
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.cs.f64 %0, [%1];\n\t}"
+               : "+d"(dst)
+               : "l"(src), "r"((unsigned) p)
+               : "memory");
+}
+
+__device__ __forceinline__ void
+ld_nc_if(bool p, unsigned &dst, const unsigned *src)
+{
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}"
+               : "+r"(dst)
+               : "l"(src), "r"((unsigned) p)
+               : "memory");
+}
+
 template <bool STATS, bool ONE_FIELD>
 __global__ void __launch_bounds__(GSI_TILE_THREADS, 1)
 k_tile_walk(const gsi_view V, const gsi_tile_args A)
@@ -740,6 +758,7 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
   __shared__ unsigned long long mbar;
   __shared__ unsigned s_item, s_next_block;
   uint4 *sleaf = reinterpret_cast<uint4 *>(smem_raw);
+  double2 *srcp = reinterpret_cast<double2 *>(smem_raw + (size_t) A.leaf_cap * 96);
   unsigned short *sseed = reinterpret_cast<unsigned short *>(smem_raw + tile_smem_seeds_at(A.leaf_cap));
   const unsigned FULL = 0xffffffffu;
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -796,25 +815,23 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
       const int slot0 = V.tiles[prefix];
       const int n_staged = min(V.tiles[prefix + 1] - slot0, A.leaf_cap);
       const bool packed = V.leaf_stride == (int) sizeof(gsi_leaf);
-      /* ---- stage the tile: one TMA bulk copy per leaf record (96 bytes to a 112-byte pitch), issued by
-         the lanes of warp 0 and all signalling one mbarrier; seed cells by the other threads ---- */
-      if (tid == 0) s_next_block = 0;
-      if (warp == 0 && packed && n_staged > 0)
+      /* ---- stage the tile: leaf records by TMA bulk copy, seed cells by the threads ---- */
+      if (tid == 0)
         {
-          if (lane == 0)
+          s_next_block = 0;
+          if (packed && n_staged > 0)
             {
+              const unsigned bytes = (unsigned) n_staged * 96u;
+              const char *src = V.leaf + (size_t) slot0 * sizeof(gsi_leaf);
               fence_proxy_async();
-              mbar_arrive_expect_tx(&mbar, (unsigned) n_staged * 96u);
+              mbar_arrive_expect_tx(&mbar, bytes);
+              for (unsigned o = 0; o < bytes; o += 32768u)
+                bulk_load(reinterpret_cast<char *>(sleaf) + o, src + o, min(32768u, bytes - o), &mbar);
             }
-          __syncwarp();
-          const char *src = V.leaf + (size_t) slot0 * sizeof(gsi_leaf);
-          for (int i = lane; i < n_staged; i += 32)
-            bulk_load(sleaf + (size_t) i * GSI_TILE_REC16, src + (size_t) i * 96, 96u, &mbar);
         }
       if (!packed)
         for (int i = tid; i < n_staged * 6; i += blockDim.x)
-          sleaf[(size_t) (i / 6) * GSI_TILE_REC16 + i % 6] =
-              __ldg(reinterpret_cast<const uint4 *>(V.leaf + (size_t) (slot0 + i / 6) * (size_t) V.leaf_stride) + i % 6);
+          sleaf[i] = __ldg(reinterpret_cast<const uint4 *>(V.leaf + (size_t) (slot0 + i / 6) * (size_t) V.leaf_stride) + i % 6);
       /* the tile's rectangle of grid cells, one cell of margin */
       const unsigned tx = bin & ((1u << A.M.bx_bits) - 1u), ty = bin >> A.M.bx_bits;
       const int cx0 = max(0, (int) (((unsigned long long) tx * (unsigned) V.grid_g) >> A.M.bx_bits) - 1);
@@ -841,13 +858,12 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
          leaf defer always (tau = +inf), like a singular leaf. */
       for (int i = tid; i < n_staged; i += blockDim.x)
         {
-          uint4 *rec = sleaf + (size_t) i * GSI_TILE_REC16;
-          const uint4 b = rec[1], c = rec[2];
+          const uint4 b = sleaf[(size_t) i * 6 + 1], c = sleaf[(size_t) i * 6 + 2];
           const double u00 = __hiloint2double((int) b.y, (int) b.x), u11 = __hiloint2double((int) c.y, (int) c.x);
-          *reinterpret_cast<double2 *>(rec + 6) = make_double2(gsi_div_rcp(u11), gsi_div_rcp(u00));
+          srcp[i] = make_double2(gsi_div_rcp(u11), gsi_div_rcp(u00));
           if (!(gsi_div_rcp_usable(u00) && gsi_div_rcp_usable(u11)))
             {
-              unsigned *meta = reinterpret_cast<unsigned *>(rec + 3) + 3;
+              unsigned *meta = reinterpret_cast<unsigned *>(sleaf + (size_t) i * 6 + 3) + 3;
               *meta = (*meta & 0x80000000u) | 0x7f800000u;
             }
         }
@@ -864,8 +880,9 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
         if (lane == 0) k = atomicAdd(&s_next_block, 1u);
         k = __shfl_sync(FULL, k, 0);
         cb_nxt = range + k * (unsigned) A.ranges;
-        /* unconditional load (index clamped), validity decided where the word is used */
-        run_nxt = __ldg(runs_row + min((cb_nxt << 5) + lane, A.n_chunks - 1u));
+        const unsigned c = (cb_nxt << 5) + lane;
+        run_nxt = 0;
+        ld_nc_if(cb_nxt < n_blocks && c < A.n_chunks, run_nxt, runs_row + c);
       };
       grab_block();
       unsigned r_pos0 = 0, r_len = 0, r_excl = 0; /* this lane's run of the current block */
@@ -943,7 +960,7 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                 {
                   const unsigned c = (cb_nxt << 5) + lane;
                   const unsigned start = run_nxt & 0xffffu;
-                  r_len = c < A.n_chunks ? (run_nxt >> 16) - start : 0u;
+                  r_len = (run_nxt >> 16) - start;
                   r_pos0 = c * (unsigned) A.S + start;
                   unsigned incl = r_len;
 #pragma unroll
@@ -985,6 +1002,8 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
               const unsigned off = next + __popc(take & lt_mask);
               nxt_v = off < win_n;
               if (nxt_v) nxt_pos = spos[off];
+              ld_stream_if(nxt_v, nxt_x, A.bx + nxt_pos);
+              ld_stream_if(nxt_v, nxt_y, A.by + nxt_pos);
               if (cur_v)
                 {
                   /* grid cell (one fused multiply-add per axis; NaN -> 0, +-inf saturate) and its seed from
@@ -1004,12 +1023,6 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
                 }
             }
           next = min(next + (unsigned) __popc(take), win_n);
-          /* the prefetch itself: EVERY lane (re)loads the coordinates of its nxt position in every iteration,
-             straight into the loop-carried registers -- unconditional, so there is no merge point behind the
-             load where the compiler could park a move that waits for HBM (nxt_pos is always a valid
-             position; a lane that kept its nxt re-reads the same line from L1/L2) */
-          nxt_x = __ldcs(A.bx + nxt_pos);
-          nxt_y = __ldcs(A.by + nxt_pos);
           /* one walk step out of shared memory for every lane that holds a query inside the staged tile */
           const unsigned rel = (unsigned) (cur_slot - slot0);
           const bool staged = rel < (unsigned) n_staged;
@@ -1017,15 +1030,14 @@ k_tile_walk(const gsi_view V, const gsi_tile_args A)
             {
               gsi_rec rec;
               double c0, c1;
-              const uint4 *srec = sleaf + (size_t) rel * GSI_TILE_REC16;
-              fetch_rec_smem(&rec, srec);
-              const double2 rc = *reinterpret_cast<const double2 *>(srec + 6);
+              fetch_rec_smem(&rec, sleaf + (size_t) rel * 6);
+              const double2 rc = srcp[rel];
               const int st = gsi_walk_step_rcp(&V.xf, &rec, rc.x, rc.y, cur_x, cur_y, &cur_slot, &c0, &c1);
               ++cur_steps;
               if (st == GSI_STEP_ACCEPT)
                 {
                   gsi_leaf_tail tl;
-                  fetch_tail_smem(&tl, srec);
+                  fetch_tail_smem(&tl, sleaf + (size_t) rel * 6);
                   store_result(cur_pos, tl, c0, c1);
                   if (STATS) steps_acc += (unsigned) cur_steps;
                   cur_v = false;
@@ -1362,7 +1374,7 @@ launch_reordered(const gsi_view &V, const src_arrays &src, size_t nq, double *va
       seed_bytes = 0;
     }
   int leaf_cap = R->tile_max_leaves < 1 ? 1 : R->tile_max_leaves;
-  const size_t room = (budget - seed_bytes - spos_bytes - 16) / (GSI_TILE_REC16 * 16);
+  const size_t room = (budget - seed_bytes - spos_bytes - 16) / (96 + 16);
   if ((size_t) leaf_cap > room) leaf_cap = (int) room;
   if (leaf_cap > 65000) leaf_cap = 65000; /* 16-bit relative seeds */
   A.leaf_cap = leaf_cap;
