@@ -179,7 +179,7 @@ struct gsl_scattered_cuda
   bool built = false, uploaded = false;
   gsi_flatten_params fprm;
   int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
-  int kernel = GSI_KERNEL_AUTO, walk_ctas_per_sm = 4, walk2 = 1;
+  int kernel = GSI_KERNEL_AUTO, walk_ctas_per_sm = 4;
   int l2_fetch = 0; /* cudaLimitMaxL2FetchGranularity, device-wide: 0 = leave the host application's setting
                        alone (measured without effect on B200: an L2 miss fills the whole 128-byte line) */
   /* reorder pipeline (gsi_kernels.cu): 0 = off, 1 = always for query arrays, 2 = auto (default):
@@ -554,7 +554,6 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r, const eval_ctx *c)
   g.locate_ctas_per_sm = w->ctas_per_sm;
   g.kernel = w->kernel;
   g.walk_ctas_per_sm = w->walk_ctas_per_sm;
-  g.walk2 = w->walk2;
   g.walk_chunk = w->walk_chunk;
   g.list = c->list;
   g.list_capacity = c->list_cap;
@@ -1183,8 +1182,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "host_chunk" && value >= 1) w->host_chunk = (size_t) value;
   else if (k == "ctas_per_sm" && value >= 1) w->ctas_per_sm = (int) value;
   else if (k == "profile") w->profile = value != 0;
-  else if (k == "kernel" && (value == 0 || value == 1 || value == 2 || value == 3)) w->kernel = (int) value;
-  else if (k == "walk2" && (value == 0 || value == 1)) w->walk2 = (int) value;
+  else if (k == "kernel" && (value == 0 || value == 1 || value == 2)) w->kernel = (int) value;
   else if (k == "l2_fetch" && (value == 0 || value == 32 || value == 64 || value == 128)) w->l2_fetch = (int) value;
   else if (k == "walk_ctas_per_sm" && value >= 1) w->walk_ctas_per_sm = (int) value;
   else if (k == "walk_chunk" && value >= 0) w->walk_chunk = ((size_t) value + 31) & ~(size_t) 31;

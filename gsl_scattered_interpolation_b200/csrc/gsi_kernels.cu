@@ -442,218 +442,6 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
     atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
 }
 
-/* ---- fast path, two walkers per lane ---------------------------------------------------------------
- * k_walk keeps one leaf fetch in flight per lane, and at 10^6 nodes that fetch is an HBM access of
- * 1-2 microseconds: the kernel is bound by latency x (16 warps x 32 lanes), not by bytes (ncu: 26 % issue
- * slots, 4.5 TB/s of DRAM traffic).  Here every lane runs TWO walkers, A and B, in alternating half
- * iterations: a half consumes the walker's leaf record (requested a whole half iteration earlier),
- * takes one walk step, refills the walker from the lane's prefetch pipeline when its query is done,
- * and at once requests the record of the walker's next leaf -- which then has the other walker's
- * half to arrive.  The records travel by asynchronous copies straight from global to shared
- * memory (cp.async / LDGSTS, one commit group per walker, lane-private slots laid out
- * [walker][16-byte chunk][thread] so the reads back are conflict-free): no registers are tied up
- * by loads in flight and the compiler has nothing to "tidy up" behind them (with plain loads it
- * parks register moves right after the LDG and the warp waits for HBM at once).
- * Twice the leaf fetches in flight per warp, the same queue and the same arithmetic
- * (gsi_walk_step), so accepted results are bit-identical to k_walk's. */
-__device__ __forceinline__ unsigned smem_u32(const void *p);
-
-struct walker_t
-{
-  bool v;
-  unsigned q;
-  double x, y;
-  int slot, steps;
-};
-
-__device__ __forceinline__ void
-cp_async16(void *smem_dst, const void *gsrc)
-{
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-
-__device__ __forceinline__ void
-cp_async_commit()
-{
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-/* wait until at most one commit group of this thread (the other walker's) is still in flight */
-__device__ __forceinline__ void
-cp_async_wait_but_one()
-{
-  asm volatile("cp.async.wait_group 1;" ::: "memory");
-}
-
-/* request the record of the walker's leaf (nothing for an idle walker: an empty group) */
-__device__ __forceinline__ void
-walker_request(const walker_t &w, const gsi_view &V, uint4 *slots)
-{
-  if (w.v)
-    {
-      const char *p = reinterpret_cast<const char *>(gsi_leaf_at(&V, w.slot));
-#pragma unroll
-      for (int j = 0; j < 6; j++) cp_async16(slots + (size_t) j * blockDim.x, p + 16 * j);
-    }
-  cp_async_commit();
-}
-
-/* a leaf record stored as six 16-byte chunks `stride` uint4 apart (lane-private slots) */
-__device__ __forceinline__ void
-fetch_rec_smem_strided(gsi_rec *r, const uint4 *p, unsigned stride)
-{
-  const uint4 a = p[0], b = p[stride], c = p[2 * stride], d = p[3 * stride];
-  r->x0x = __hiloint2double((int) a.y, (int) a.x);
-  r->x0y = __hiloint2double((int) a.w, (int) a.z);
-  r->u00 = __hiloint2double((int) b.y, (int) b.x);
-  r->u01 = __hiloint2double((int) b.w, (int) b.z);
-  r->u11 = __hiloint2double((int) c.y, (int) c.x);
-  r->l10 = __hiloint2double((int) c.w, (int) c.z);
-  r->lnk[0] = (int32_t) d.x;
-  r->lnk[1] = (int32_t) d.y;
-  r->lnk[2] = (int32_t) d.z;
-  r->meta = d.w;
-}
-
-__device__ __forceinline__ void
-fetch_tail_smem_strided(gsi_leaf_tail *t, const uint4 *p, unsigned stride)
-{
-  const uint4 e = p[4 * stride], f = p[5 * stride];
-  t->s.node = (int32_t) e.x;
-  t->s.vflags = e.y;
-  t->s.z[0] = __hiloint2double((int) e.w, (int) e.z);
-  t->s.z[1] = __hiloint2double((int) f.y, (int) f.x);
-  t->s.z[2] = __hiloint2double((int) f.w, (int) f.z);
-}
-
-template <class SRC, bool STATS, bool ONE_FIELD>
-__global__ void __launch_bounds__(GSI_WALK_THREADS, 4)
-k_walk2(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
-        size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
-        int max_steps)
-{
-  const unsigned FULL = 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const size_t warp_id = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t n_warps = ((size_t) gridDim.x * blockDim.x) >> 5;
-  const size_t n_chunks = (nq + chunk - 1) / chunk;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint4 *wsm = reinterpret_cast<uint4 *>(smem_raw); /* [2 walkers][6 chunks][blockDim.x] */
-  unsigned long long steps_acc = 0;
-  for (size_t ch = warp_id; ch < n_chunks; ch += n_warps)
-    {
-      const size_t q0 = ch * (size_t) chunk;
-      const unsigned total = (unsigned) (nq - q0 < (size_t) chunk ? nq - q0 : (size_t) chunk);
-      unsigned next = 0; /* warp-uniform: queries of this chunk handed out so far */
-      walker_t A, B;
-      A.v = B.v = false;
-      A.q = B.q = 0;
-      A.x = A.y = B.x = B.y = 0;
-      A.slot = B.slot = A.steps = B.steps = 0;
-      uint4 *slots_a = wsm + threadIdx.x, *slots_b = wsm + (size_t) 6 * blockDim.x + threadIdx.x;
-      bool nxt_v = false, nn_v = false;
-      unsigned nxt_q = 0, nn_q = 0;
-      double nxt_x = 0, nxt_y = 0, nn_x = 0, nn_y = 0;
-      int nxt_seed = 0;
-      walker_request(A, V, slots_a);
-      walker_request(B, V, slots_b);
-      auto half = [&](walker_t &W, uint4 *slots) {
-        /* 1. one walk step on the record requested a half iteration ago */
-        bool defer = false;
-        const unsigned dq = W.q;
-        cp_async_wait_but_one();
-        if (W.v)
-          {
-            if (!(isfinite(W.x) && isfinite(W.y)))
-              {
-                defer = true;
-                W.v = false;
-              }
-            else
-              {
-                gsi_rec r;
-                fetch_rec_smem_strided(&r, slots, blockDim.x);
-                double c0, c1;
-                const int st = gsi_walk_step(&V.xf, &r, W.x, W.y, &W.slot, &c0, &c1);
-                ++W.steps;
-                if (st == GSI_STEP_ACCEPT)
-                  {
-                    gsi_leaf_tail t;
-                    fetch_tail_smem_strided(&t, slots, blockDim.x);
-                    const size_t q = q0 + W.q;
-                    if (leaf_out) GSI_ST_RESULT(leaf_out + q, t.g.node);
-                    if (val)
-                      {
-                        if (ONE_FIELD)
-                          GSI_ST_RESULT(val + q, gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0], (int) (t.s.vflags & 2u),
-                                                           t.s.z[1], (int) (t.s.vflags & 4u), t.s.z[2]));
-                        else
-                          gsi_blend_store(&V, &t, c0, c1, val, ld, q);
-                      }
-                    if (STATS) steps_acc += (unsigned) W.steps;
-                    W.v = false;
-                  }
-                else if (st == GSI_STEP_DEFER || W.steps >= max_steps)
-                  {
-                    defer = true;
-                    W.v = false;
-                  }
-              }
-          }
-        /* 2. refill the walker from the lane's pipeline: nxt (seed loaded) -> walker, nn (coordinates
-              loaded) -> nxt and its seed lookup, a new nn from the warp's queue */
-        const bool need = !W.v;
-        const unsigned take = __ballot_sync(FULL, need);
-        if (need)
-          {
-            W.v = nxt_v; W.q = nxt_q; W.x = nxt_x; W.y = nxt_y;
-            W.slot = nxt_seed; W.steps = 0;
-            nxt_v = nn_v; nxt_q = nn_q; nxt_x = nn_x; nxt_y = nn_y;
-            if (nxt_v) nxt_seed = gsi_seed_of(&V, nxt_x, nxt_y);
-            const unsigned off = next + __popc(take & lt_mask);
-            nn_v = off < total;
-            if (nn_v)
-              {
-                nn_q = off;
-                src.get_linear(q0 + off, nn_x, nn_y);
-              }
-          }
-        next += __popc(take);
-        if (next > total) next = total;
-        /* 3. request the record of the walker's next leaf: consumed one half iteration later */
-        walker_request(W, V, slots);
-        /* 4. warp-aggregated append to the deferred list */
-        const unsigned dm = __ballot_sync(FULL, defer);
-        if (dm)
-          {
-            const int leader = __ffs(dm) - 1;
-            unsigned pos = 0;
-            if (lane == (unsigned) leader) pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
-            pos = __shfl_sync(FULL, pos, leader);
-            if (defer)
-              {
-                const size_t q = q0 + dq;
-                const unsigned at = pos + __popc(dm & lt_mask);
-                if (at < list_cap)
-                  list[at] = (unsigned) q;
-                else
-                  mark_overflow(ovf_mask, q, counters);
-              }
-          }
-      };
-      for (;;)
-        {
-          half(A, slots_a);
-          half(B, slots_b);
-          if (!__any_sync(FULL, A.v || B.v || nxt_v || nn_v)) break;
-        }
-      asm volatile("cp.async.wait_all;" ::: "memory");
-    }
-  if (STATS && steps_acc)
-    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
-}
-
 /* ---- reorder pipeline: k_bin -> k_tile_walk -> k_unpermute -----------------------------------
  * Uniformly random queries make every leaf fetch an isolated L2/DRAM line fill: at 10^6 nodes the
  * direct walk moves ~220 bytes per query through HBM for 28 algorithmic bytes.  The pipeline
@@ -1651,7 +1439,7 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   if (cfg.ev_locate0) cudaEventRecord(cfg.ev_locate0, st);
   if (launch_reordered(V, src, nq, val, leaf_out, ld, cfg, list_cap, st))
     ;
-  else if (cfg.kernel == GSI_KERNEL_WALK || cfg.kernel == GSI_KERNEL_WALK2 || (cfg.kernel == GSI_KERNEL_AUTO && !SRC::coherent))
+  else if (cfg.kernel == GSI_KERNEL_WALK || (cfg.kernel == GSI_KERNEL_AUTO && !SRC::coherent))
     {
       const int ctas = cfg.sm_count * cfg.walk_ctas_per_sm;
       const size_t n_warps = (size_t) ctas * (GSI_WALK_THREADS / 32);
@@ -1665,18 +1453,9 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
                                ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
                                : (size_t) ctas);
 #define GSI_LAUNCH_WALK(STATS, ONE)                                                             \
-  do                                                                                            \
-    {                                                                                           \
-      if (cfg.kernel == GSI_KERNEL_WALK2 || (cfg.kernel == GSI_KERNEL_AUTO && cfg.walk2))       \
-        k_walk2<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 2 * 6 * GSI_WALK_THREADS * 16, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out, \
-                                                                 ld, cfg.list, list_cap, cfg.ovf_mask, \
-                                                                 cfg.counters, cfg.max_steps);   \
-      else                                                                                      \
-        k_walk<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out, \
-                                                                ld, cfg.list, list_cap, cfg.ovf_mask, \
-                                                                cfg.counters, cfg.max_steps);    \
-    }                                                                                           \
-  while (0)
+  k_walk<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out,  \
+                                                          ld, cfg.list, list_cap, cfg.ovf_mask,      \
+                                                          cfg.counters, cfg.max_steps)
       if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALK(true, true);
       else if (cfg.stats) GSI_LAUNCH_WALK(true, false);
       else if (V.n_fields == 1) GSI_LAUNCH_WALK(false, true);

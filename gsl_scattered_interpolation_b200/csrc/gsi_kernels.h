@@ -29,8 +29,7 @@
 
 #define GSI_KERNEL_WALK 0   /* k_walk: lanes decoupled from queries (default) */
 #define GSI_KERNEL_SIMPLE 1 /* k_locate: one thread per query, two-phase (coherent query sets) */
-#define GSI_KERNEL_AUTO 2   /* k_walk2 / k_walk for query arrays, k_locate for rasters (default) */
-#define GSI_KERNEL_WALK2 3  /* k_walk2: two walkers per lane (twice the leaf fetches in flight) */
+#define GSI_KERNEL_AUTO 2   /* k_walk for query arrays, k_locate for rasters (default) */
 
 /* Scratch of the reorder pipeline (k_bin -> k_tile_walk -> k_unpermute), one per evaluation
  * context.  Queries are processed in windows of `cap` queries; a window is cut into chunks of
@@ -63,7 +62,6 @@ struct gsi_launch_cfg
   int locate_ctas_per_sm = 8;
   int kernel = GSI_KERNEL_AUTO;
   int walk_ctas_per_sm = 5;
-  int walk2 = 1; /* GSI_KERNEL_AUTO: query arrays go to k_walk2 (1) or k_walk (0) */
   size_t walk_chunk = 0; /* 0 = derive from the launch size */
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
   size_t list_capacity = 0;     /* deferred-list entries; overflow goes to the bitmask */

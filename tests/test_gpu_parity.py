@@ -183,9 +183,9 @@ def test_sixteen_fields_raster_vs_port():
     w.free()
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 3])
+@pytest.mark.parametrize("kernel", [0, 1])
 def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel):
-    """k_walk (0), k_locate (1) and k_walk2 (3) on config 1 (1 field) and the config-3 mix (3 fields)"""
+    """k_walk (0) and k_locate (1) on config 1 (1 field) and the config-3 mix (3 fields)"""
     xa, ya = synth.uniform_nodes(1000)
     w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
              kernel=kernel)
@@ -210,7 +210,7 @@ def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel):
     w.free()
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_raster_odd_shapes_and_chunking(golden, kernel):
     """rasters whose sides are not multiples of the 8 x 32 launch tile, evaluated in several
     device launches and several host pipeline stages, with every kernel variant"""
