@@ -179,12 +179,13 @@ struct gsl_scattered_cuda
   bool built = false, uploaded = false;
   gsi_flatten_params fprm;
   int mode = GSI_MODE_FAST, stats = 0, max_steps = 256, ctas_per_sm = 8, profile = 0;
-  int kernel = GSI_KERNEL_AUTO, walk_ctas_per_sm = 4;
+  int kernel = GSI_KERNEL_AUTO, walk_ctas_per_sm = 5;
   int l2_fetch = 0; /* cudaLimitMaxL2FetchGranularity, device-wide: 0 = leave the host application's setting
                        alone (measured without effect on B200: an L2 miss fills the whole 128-byte line) */
-  /* reorder pipeline (gsi_kernels.cu): 0 = off, 1 = always for query arrays, 2 = auto (default):
-     large batches of few fields on a triangulation whose fast-path structure exceeds the L2 */
-  int reorder = 2;
+  /* reorder pipeline (gsi_kernels.cu): 0 = off (default: measured no faster than the direct walk on B200,
+     DESIGN.md section 4.3), 1 = always for query arrays, 2 = auto: large batches of few fields on a
+     triangulation whose fast-path structure exceeds the L2 */
+  int reorder = 0;
   size_t reorder_window = (size_t) 1 << 27, reorder_min = (size_t) 1 << 24;
   size_t reorder_min_leaves = 600000; /* ~58 MB of leaf records: about half the L2 */
   int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_ranges = 0, tile_threads = GSI_TILE_THREADS;

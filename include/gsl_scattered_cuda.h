@@ -91,7 +91,7 @@ int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_
  * 0 = at the root; may be changed at any time).
  * Reorder pipeline for incoherent query arrays (chunk-local counting sort by spatial tile ->
  * tile-major walk out of TMA-staged shared memory -> inverse permutation): "reorder" (0 = off,
- * 1 = always, 2 = auto, default: batches of at least "reorder_min" queries (2^24) with at most
+ * default; 1 = always; 2 = auto: batches of at least "reorder_min" queries (2^24) with at most
  * "reorder_max_fields" fields (2) on triangulations of at least "reorder_min_leaves" leaves
  * (600000: leaf records beyond the reach of the L2)), "reorder_window" (queries per window,
  * default 2^27), "reorder_chunk" (queries per sorted chunk, <= 8192), "tile_leaves" (target
