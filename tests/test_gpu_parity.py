@@ -520,6 +520,8 @@ def test_eval_is_reentrant_across_host_threads(golden):
     w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000), host_chunk=1500)
     xq, yq = synth.uniform_queries(10000)
     x0, dx, nx, y0, dy, ny = golden["cfg1_raster_spec"]
+    # the NpzFile reads lazily and is not thread-safe: take the arrays out before the threads start
+    golden = {k: np.array(golden[k]) for k in ("cfg1_leaf", "cfg1_val", "cfg1_raster_leaf", "cfg1_raster_val")}
     bad_x, bad_y = xq.copy(), yq.copy()
     bad_x[123] = 1e6                                     # one query outside the cage: this call alone reports EDOM
     errors = []
