@@ -427,7 +427,8 @@ def main_ours(args):
         if rank != 0:
             w.init_from_slab_device(slab.data_ptr(), slab.numel())
         del slab
-        torch.cuda.empty_cache()
+        if not os.environ.get("GSI_BENCH_KEEP_CACHE"):
+            torch.cuda.empty_cache()
     # the part of the slab the fast path reads: leaf records, vertex values,
     # seed grid -- not the history DAG / entry table of the exact replay
     inf0 = w.info()

@@ -191,6 +191,7 @@ struct gsl_scattered_cuda
   int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_ranges = 0, tile_threads = GSI_TILE_THREADS;
   size_t reorder_max_fields = 2;
   int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
+  int exact_coop = 1;  /* deferred queries are replayed by four lanes each (0: one thread each) */
   int vmm = 1;         /* slab through cuMemCreate/cuMemMap with the recommended granularity (0: cudaMalloc) */
   size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
@@ -555,6 +556,7 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r, const eval_ctx *c)
   g.locate_ctas_per_sm = w->ctas_per_sm;
   g.kernel = w->kernel;
   g.walk_ctas_per_sm = w->walk_ctas_per_sm;
+  g.exact_coop = w->exact_coop;
   g.walk_chunk = w->walk_chunk;
   g.list = c->list;
   g.list_capacity = c->list_cap;
@@ -1198,6 +1200,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "tile_threads" && value >= 32 && value <= GSI_TILE_THREADS) w->tile_threads = (int) value;
   else if (k == "tile_leaves" && value >= 1) w->fprm.tile_leaves = (uint32_t) value;
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
+  else if (k == "exact_coop" && (value == 0 || value == 1)) w->exact_coop = (int) value;
   else if (k == "copy_threads" && value >= 1 && value <= 64) w->copy_threads = (int) value;
   else if (k == "pageable_min" && value >= 0) w->pageable_min = (size_t) value;
   else if (k == "exact_entry" && (value == 0 || value == 1))

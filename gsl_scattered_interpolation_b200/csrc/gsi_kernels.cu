@@ -157,6 +157,186 @@ k_exact_overflow(const gsi_view V, const SRC src, size_t nq, unsigned *mask, dou
     }
 }
 
+/* ---- exact replay, four lanes per query ---------------------------------------------------------------
+ * gsi_descend (one thread per query) keeps the current record and up to three child records in
+ * registers (128 registers, spills, 16 warps per SM) and tests the children one after the other:
+ * the deferred queries of a mixed workload (BASELINE.json configs[2]: 20 % on nodes and on edge
+ * midpoints) spend ~50 dependent levels like that.  Here a group of four lanes replays ONE query:
+ * lane j fetches and solves child j (lane 3 idles), a ballot finds the first passing child in link
+ * order, and only when no child passes are the coordinates gathered to replay the reference's
+ * best-worst fallback with its stale-coordinate rule.  One record per lane, the three solves of a
+ * level side by side, twice the warps per SM.  The semantics are those of GSI_DEFINE_DESCEND
+ * (gsi_core.h), statement for statement; k_exact_all keeps the one-thread form, and the tests
+ * compare the two on 100 % of their queries.
+ *
+ * All four lanes of a group hold the same state (node, accel->coords, last) and take the same
+ * branches, so the group-masked shuffles below are always converged. */
+__device__ __forceinline__ double
+shfl_f64(unsigned mask, double v, int src)
+{
+  const int lo = __shfl_sync(mask, __double2loint(v), src), hi = __shfl_sync(mask, __double2hiint(v), src);
+  return __hiloint2double(hi, lo);
+}
+
+/* Returns the leaf node id (>= 0), GSI_DESCEND_OUTSIDE or GSI_DESCEND_LOOP; *slot = the leaf's compact
+ * slot, (*c0, *c1) = accel->coords as interp_point will use them (recomputed at the leaf unless the
+ * leaf is singular or was the last simplex solved, linear_simplex.c:641-642,687). */
+__device__ __forceinline__ int
+descend4(const gsi_view &V, unsigned gmask, int gbase, int sub, int start, double qx, double qy, double *c0, double *c1,
+         int *slot)
+{
+  const gsi_rec *dag = V.dag;
+  const gsi_xform *t = &V.xf;
+  gsi_rec r; /* the record this lane fetched last: the current node's in lane `holder` (in every lane at the start) */
+  GSI_FETCH_DAG(r, start);
+  if (r.meta & GSI_META_SINGULAR) return GSI_DESCEND_OUTSIDE;
+  gsi_solve(t, &r, (int) (r.meta & GSI_META_SWAP), qx, qy, c0, c1);
+  int last = start, node = start, guard = 0, holder = sub; /* every lane holds the start record */
+  if (start == 0 && !gsi_inside(*c0, *c1)) return GSI_DESCEND_OUTSIDE;
+  int k0 = r.lnk[0], k1 = r.lnk[1], k2 = r.lnk[2];
+  uint32_t meta = r.meta;
+  for (;;)
+    {
+      const uint32_t type = meta & GSI_META_TYPE_MASK;
+      if (type == GSI_LEAF)
+        {
+          *slot = k0;
+          /* interp_point solves the leaf again unless it is singular or was solved last */
+          if (!(meta & GSI_META_SINGULAR) && last != node)
+            {
+              double a, b;
+              gsi_solve(t, &r, (int) (r.meta & GSI_META_SWAP), qx, qy, &a, &b); /* meaningful in lane `holder` */
+              *c0 = shfl_f64(gmask, a, gbase + (holder & 3));
+              *c1 = shfl_f64(gmask, b, gbase + (holder & 3));
+            }
+          return node;
+        }
+      if (++guard > GSI_MAX_DESCENT) return GSI_DESCEND_LOOP;
+      const int nch = (type == GSI_SUB_DPLUS1) ? 3 : 2;
+      if (nch == 2) k2 = 0;
+      const int k = sub == 0 ? k0 : (sub == 1 ? k1 : k2);
+      const bool active = sub < nch && k != 0;
+      bool valid = false;
+      double a = 0, b = 0;
+      int pass = 0;
+      if (active)
+        {
+          GSI_FETCH_DAG(r, k);
+          valid = !(r.meta & GSI_META_SINGULAR);
+          if (valid)
+            {
+              gsi_solve(t, &r, (int) (r.meta & GSI_META_SWAP), qx, qy, &a, &b);
+              pass = gsi_inside(a, b);
+            }
+        }
+      const unsigned pm = (__ballot_sync(gmask, pass) >> gbase) & 0xfu;
+      int chosen;
+      if (pm)
+        {
+          /* first passing child in link order; the children behind it are never evaluated, so
+             accel->coords and `last` are this child's */
+          chosen = __ffs(pm) - 1;
+          *c0 = shfl_f64(gmask, a, gbase + chosen);
+          *c1 = shfl_f64(gmask, b, gbase + chosen);
+          node = chosen == 0 ? k0 : (chosen == 1 ? k1 : k2);
+          last = node;
+        }
+      else
+        {
+          /* no child passes: every child was evaluated in order; a child with link 0 or a singular
+             matrix leaves accel->coords as they were (linear_simplex.c:375-395 after :641-642) */
+          const unsigned vm = (__ballot_sync(gmask, valid) >> gbase) & 0xfu;
+          int best_match = 0;
+          double best_worst = -1;
+          double e0 = *c0, e1 = *c1;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+            {
+              const double ai = shfl_f64(gmask, a, gbase + i), bi = shfl_f64(gmask, b, gbase + i);
+              if (i < nch)
+                {
+                  if (vm & (1u << i))
+                    {
+                      e0 = ai;
+                      e1 = bi;
+                      last = i == 0 ? k0 : (i == 1 ? k1 : k2);
+                    }
+                  const double worst = gsi_worst(e0, e1);
+                  if ((best_worst < 0) || (worst < best_worst))
+                    {
+                      best_worst = worst;
+                      best_match = i;
+                    }
+                }
+            }
+          *c0 = e0;
+          *c1 = e1;
+          chosen = best_match;
+          node = chosen == 0 ? k0 : (chosen == 1 ? k1 : k2);
+        }
+      if (node == 0)
+        {
+          /* link 0: the reference would re-enter the root */
+          GSI_FETCH_DAG(r, 0);
+          holder = sub;
+          k0 = r.lnk[0]; k1 = r.lnk[1]; k2 = r.lnk[2];
+          meta = r.meta;
+        }
+      else
+        {
+          /* the chosen child's record sits in lane `chosen`: its links and meta word to everyone */
+          holder = chosen;
+          k0 = __shfl_sync(gmask, r.lnk[0], gbase + chosen);
+          k1 = __shfl_sync(gmask, r.lnk[1], gbase + chosen);
+          k2 = __shfl_sync(gmask, r.lnk[2], gbase + chosen);
+          meta = (uint32_t) __shfl_sync(gmask, (int) r.meta, gbase + chosen);
+        }
+    }
+}
+
+/* one deferred query per group of four lanes; lane 0 of the group writes the result */
+template <class SRC>
+__device__ __forceinline__ void
+exact_one4(const gsi_view &V, const SRC &src, size_t q, double *val, int *leaf_out, size_t ld, unsigned *counters,
+           unsigned gmask, int gbase, int sub)
+{
+  double qx, qy, c0 = 0, c1 = 0;
+  src.get_linear(q, qx, qy);
+  int slot = 0;
+  const int start = V.entry ? GSI_LDG(V.entry + gsi_cell_of(&V, qx, qy)) : 0;
+  const int node = descend4(V, gmask, gbase, sub, start, qx, qy, &c0, &c1, &slot);
+  if (sub != 0) return;
+  if (node < 0)
+    {
+      if (leaf_out) leaf_out[q] = -1;
+      if (val)
+        for (int f = 0; f < V.n_fields; f++) val[(size_t) f * ld + q] = GSI_NAN;
+      atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+      return;
+    }
+  if (leaf_out) leaf_out[q] = node;
+  if (val)
+    {
+      gsi_leaf_tail tl;
+      gsi_fetch_tail(&tl, gsi_leaf_at(&V, slot));
+      gsi_blend_store(&V, &tl, c0, c1, val, ld, q);
+    }
+}
+
+template <class SRC>
+__global__ void __launch_bounds__(128, 8)
+k_exact_list4(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, double *val, int *leaf_out,
+              size_t ld, unsigned *counters)
+{
+  const unsigned count = min(counters[GSI_CNT_DEFERRED], list_cap);
+  const unsigned lane = threadIdx.x & 31u;
+  const int sub = (int) (lane & 3u), gbase = (int) (lane & ~3u);
+  const unsigned gmask = 0xfu << gbase;
+  const unsigned n_groups = (gridDim.x * blockDim.x) >> 2;
+  for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; g < count; g += n_groups)
+    exact_one4(V, src, (size_t) list[g], val, leaf_out, ld, counters, gmask, gbase, sub);
+}
+
 /* seeds[cell] = leaf slot containing the cell centre (exact replay of the centre) */
 __global__ void __launch_bounds__(128)
 k_seed_cells(const gsi_view V, int32_t *seeds)
@@ -1475,8 +1655,11 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (cfg.ev_exact0) cudaEventRecord(cfg.ev_exact0, st);
-  k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld,
-                                                      cfg.counters);
+  if (cfg.exact_coop)
+    k_exact_list4<SRC><<<cfg.sm_count * 8, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld, cfg.counters);
+  else
+    k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld,
+                                                        cfg.counters);
   k_exact_overflow<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, nq, cfg.ovf_mask, val, leaf_out, ld,
                                                           cfg.counters);
   if (cfg.ev_exact1) cudaEventRecord(cfg.ev_exact1, st);

@@ -62,6 +62,7 @@ struct gsi_launch_cfg
   int locate_ctas_per_sm = 8;
   int kernel = GSI_KERNEL_AUTO;
   int walk_ctas_per_sm = 5;
+  int exact_coop = 1; /* deferred list: four lanes per query (k_exact_list4) instead of one thread (k_exact_list) */
   size_t walk_chunk = 0; /* 0 = derive from the launch size */
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
   size_t list_capacity = 0;     /* deferred-list entries; overflow goes to the bitmask */
