@@ -308,23 +308,14 @@ gsi_cell_vs_rec(const gsi_xform *xf, const gsi_rec *r, double delta, const doubl
   return (out0 | out1 | out2) ? -1 : 0;
 }
 
+/* deepest DAG node every point of the box with corners (cx[k], cy[k]) is certain to pass; *depth
+ * (may be NULL) = levels descended */
 GSI_HD int
-gsi_entry_of_cell(const gsi_view *V, size_t cell)
+gsi_entry_of_box(const gsi_view *V, const double cx[4], const double cy[4], int *depth)
 {
-  const size_t g = (size_t) V->grid_g;
-  const size_t iy = cell / g, ix = cell - iy * g;
-  if (ix == 0 || iy == 0 || ix + 1 >= g || iy + 1 >= g) return 0;
-  const double pad = 1.0 / 1024; /* of a cell: covers the rounding of gsi_cell_of by far */
-  double cx[4], cy[4];
-  for (int k = 0; k < 4; k++)
-    {
-      const double u = V->u0 + ((double) ix + ((k & 1) ? 1.0 + pad : -pad)) / V->inv_du;
-      const double v = V->v0 + ((double) iy + ((k & 2) ? 1.0 + pad : -pad)) / V->inv_dv;
-      cx[k] = V->xf.cx + u / V->xf.sx;
-      cy[k] = V->xf.cy + v / V->xf.sy;
-    }
   const gsi_rec *dag = V->dag;
   gsi_rec cur;
+  if (depth) *depth = 0;
   GSI_FETCH_DAG(cur, 0);
   if (cur.meta & GSI_META_SINGULAR) return 0;
   if (gsi_cell_vs_rec(&V->xf, &cur, V->delta, cx, cy) != 1) return 0;
@@ -349,8 +340,51 @@ gsi_entry_of_cell(const gsi_view *V, size_t cell)
       if (!chosen) break;
       node = chosen;
       cur = rc;
+      if (depth) ++*depth;
     }
   return node;
+}
+
+GSI_HD int
+gsi_entry_of_cell(const gsi_view *V, size_t cell)
+{
+  const size_t g = (size_t) V->grid_g;
+  const size_t iy = cell / g, ix = cell - iy * g;
+  if (ix == 0 || iy == 0 || ix + 1 >= g || iy + 1 >= g) return 0;
+  const double pad = 1.0 / 1024; /* of a cell: covers the rounding of gsi_cell_of by far */
+  double cx[4], cy[4];
+  for (int k = 0; k < 4; k++)
+    {
+      const double u = V->u0 + ((double) ix + ((k & 1) ? 1.0 + pad : -pad)) / V->inv_du;
+      const double v = V->v0 + ((double) iy + ((k & 2) ? 1.0 + pad : -pad)) / V->inv_dv;
+      cx[k] = V->xf.cx + u / V->xf.sx;
+      cy[k] = V->xf.cy + v / V->xf.sy;
+    }
+  return gsi_entry_of_box(V, cx, cy, (int *) 0);
+}
+
+/* The bounding box, in raw coordinates, of the leaf whose record is r (vertices x0, x0 + column 0,
+ * x0 + column 1 of the edge matrix M = L U, rows un-swapped), inflated by `grow` of its size plus
+ * twice the absolute margin delta: every point the fast path can defer AT this leaf -- all three
+ * weights above -tau, i.e. at most delta outside an edge -- lies inside. */
+GSI_HD void
+gsi_leaf_box(const gsi_view *V, const gsi_rec *r, int swap, double grow, double cx[4], double cy[4])
+{
+  const double m00 = r->u00, m01 = r->u01;
+  const double m10 = r->l10 * r->u00, m11 = r->u11 + r->l10 * r->u01;
+  /* standardised edge vectors a - x0, b - x0 (row 0 = x unless the rows were swapped) */
+  const double ax = swap ? m10 : m00, ay = swap ? m00 : m10;
+  const double bx = swap ? m11 : m01, by = swap ? m01 : m11;
+  const double u0 = (r->x0x - V->xf.cx) * V->xf.sx, v0 = (r->x0y - V->xf.cy) * V->xf.sy;
+  double ulo = fmin(u0, fmin(u0 + ax, u0 + bx)), uhi = fmax(u0, fmax(u0 + ax, u0 + bx));
+  double vlo = fmin(v0, fmin(v0 + ay, v0 + by)), vhi = fmax(v0, fmax(v0 + ay, v0 + by));
+  const double pu = grow * (uhi - ulo) + 4.0 * V->delta, pv = grow * (vhi - vlo) + 4.0 * V->delta;
+  ulo -= pu; uhi += pu; vlo -= pv; vhi += pv;
+  for (int k = 0; k < 4; k++)
+    {
+      cx[k] = V->xf.cx + ((k & 1) ? uhi : ulo) / V->xf.sx;
+      cy[k] = V->xf.cy + ((k & 2) ? vhi : vlo) / V->xf.sy;
+    }
 }
 
 #define GSI_EXACT_OUTSIDE (-1)

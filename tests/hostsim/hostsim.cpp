@@ -145,4 +145,26 @@ hostsim_deriv(const hostsim *h, const int *leaf, size_t nq, double *dzdx, double
   for (size_t q = 0; q < nq; q++) gsi_deriv_one(&h->view, leaf[q], dzdx, dzdy, nq, q);
   return 0;
 }
+
+/* experiment: how deep is the certified entry node of a LEAF's inflated bounding box, compared with the
+ * depth of the leaf itself (certified descent of a degenerate box at the centroid)? */
+int
+hostsim_leaf_entry_depths(const hostsim *h, double grow, int *depth_entry, int *depth_leaf, int *entry_node)
+{
+  const gsi_view *V = &h->view;
+  for (int s = 0; s < V->n_leaves; s++)
+    {
+      const gsi_leaf *lf = gsi_leaf_at(V, s);
+      gsi_rec r = lf->r;
+      double cx[4], cy[4];
+      if (!(r.u00 != 0 && r.u11 != 0)) { depth_entry[s] = depth_leaf[s] = -1; entry_node[s] = 0; continue; }
+      gsi_leaf_box(V, &r, (int) (r.meta >> 31), grow, cx, cy);
+      entry_node[s] = gsi_entry_of_box(V, cx, cy, &depth_entry[s]);
+      /* centroid */
+      double mx = 0.25 * (cx[0] + cx[1] + cx[2] + cx[3]), my = 0.25 * (cy[0] + cy[1] + cy[2] + cy[3]);
+      double px[4] = {mx, mx, mx, mx}, py[4] = {my, my, my, my};
+      gsi_entry_of_box(V, px, py, &depth_leaf[s]);
+    }
+  return 0;
+}
 }
