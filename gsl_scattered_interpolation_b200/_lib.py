@@ -111,6 +111,8 @@ _PROTOS = {
     "gsl_scattered_cuda_checksum_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t,
                                                    c_void_p, c_void_p]),
     "gsl_scattered_cuda_selftest_division": (c_int, [c_int, c_ulonglong, c_size_t, c_void_p]),
+    "gsl_scattered_cuda_build_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gsl_scattered_cuda_debug_walk_trace": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "gsl_scattered_cuda_compare_device": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_size_t, c_size_t, c_void_p,
                                                   c_void_p]),

@@ -271,6 +271,23 @@ class ScatteredCuda:
                                                                stream), "checksum_device")
         return int(out[0]), int(out[1])
 
+    def build_stats(self):
+        """how much of the last build() went through the batched device locate"""
+        sec, pts, rounds = ctypes.c_double(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+        self._check(self._L.gsl_scattered_cuda_build_stats(self._w, ctypes.byref(sec), ctypes.byref(pts),
+                                                           ctypes.byref(rounds)), "build_stats")
+        return {"batched_seconds": sec.value, "batched_points": pts.value, "rounds": rounds.value}
+
+    def walk_trace(self, dev):
+        """(n_ctas, 4) uint64 array {smid, start ns, end ns, queries} of the last fast-path launch
+        (set_param("walk_trace", 1) first)"""
+        import numpy as np
+        out = np.zeros(4 * 16 * 1024, dtype=np.uint64)
+        n = ctypes.c_size_t(0)
+        self._check(self._L.gsl_scattered_cuda_debug_walk_trace(
+            self._w, dev, out.ctypes.data_as(ctypes.c_void_p), out.size, ctypes.byref(n)), "walk_trace")
+        return out[:n.value].reshape(-1, 4)
+
     def compare_device(self, dev, d_leaf_a, d_leaf_b, d_val_a, d_val_b, n, n_val, stream=None):
         out = (ctypes.c_ulonglong * 2)()
         self._check(self._L.gsl_scattered_cuda_compare_device(

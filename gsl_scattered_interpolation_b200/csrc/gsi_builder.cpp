@@ -5,6 +5,7 @@
  */
 #include "gsi_builder.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -171,7 +172,8 @@ class builder
 {
 public:
   builder(gsi_host_tree &t, std::string *err) : T(t), err_(err) {}
-  int run(const double *xa, const double *ya, size_t n, int flags, const int64_t *order);
+  int run(const double *xa, const double *ya, size_t n, int flags, const int64_t *order,
+          gsi_build_locator *locator);
 
 private:
   gsi_host_tree &T;
@@ -543,7 +545,8 @@ builder::insert_point(int leaf)
 
 /* simplex_tree_init, linear_simplex.c:134-296 (min == max == NULL) */
 int
-builder::run(const double *xa, const double *ya, size_t n, int flags, const int64_t *order)
+builder::run(const double *xa, const double *ya, size_t n, int flags, const int64_t *order,
+             gsi_build_locator *locator)
 {
   double mn[2], mx[2];
   if (flags & GSI_FLAG_NOSTANDARDIZE || n == 0)
@@ -633,17 +636,103 @@ builder::run(const double *xa, const double *ya, size_t n, int flags, const int6
     }
 
   tree_view view{&rec_, &T.lnk, &T.type};
-  for (size_t i = 0; i < n; i++)
+  T.batched_points = T.batched_rounds = 0;
+  T.batched_seconds = 0;
+  /* Rounds of the batched locate: the first kFirstBatch points are located on the host (the tree
+     is small and hot in cache); afterwards every round covers as many points as are already in
+     the tree (the snapshot doubles), so the descent that is left for the host is the few levels
+     the tree grew by during the round. */
+  const size_t kFirstBatch = 4096;
+  size_t n_prev_nodes = 0;
+  std::vector<int32_t> b_node, b_last;
+  std::vector<double> b_c0, b_c1;
+  if (locator && n > kFirstBatch)
     {
-      int last = -1;
-      gsi_rec leaf_rec;
-      const int leaf = descend_view(&view, &T.xf, 0, px_[i], py_[i], &c0_, &c1_, &last, &leaf_rec);
-      if (leaf < 0) return fail("given point outside the domain");
-      const int st = insert_point(leaf);
-      if (st) return st;
+      const int st = locator->begin(T.xf, px_.data(), py_.data(), n, 9 * n + 16);
+      if (st) locator = nullptr; /* no device: plain host build */
+    }
+  size_t i = 0;
+  while (i < n)
+    {
+      if (!locator || i < kFirstBatch)
+        {
+          int last = -1;
+          gsi_rec leaf_rec;
+          const int leaf = descend_view(&view, &T.xf, 0, px_[i], py_[i], &c0_, &c1_, &last, &leaf_rec, 0);
+          if (leaf < 0) return fail("given point outside the domain");
+          const int st = insert_point(leaf);
+          if (st) return st;
+          i++;
+          continue;
+        }
+      const size_t count = std::min(n - i, i);
+      b_node.resize(count); b_last.resize(count); b_c0.resize(count); b_c1.resize(count);
+      const auto t0 = std::chrono::steady_clock::now();
+      const size_t n_nodes = T.type.size();
+      const int ls = locator->locate(rec_.data(), T.lnk.data(), T.type.data(), n_nodes, n_prev_nodes, i, count,
+                                     b_node.data(), b_c0.data(), b_c1.data(), b_last.data());
+      T.batched_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (ls) return fail("batched locate failed");
+      n_prev_nodes = n_nodes;
+      T.batched_rounds++;
+      T.batched_points += count;
+      for (size_t k = 0; k < count; k++)
+        {
+          int leaf = b_node[k];
+          if (leaf < 0 || (size_t) leaf >= n_nodes) return fail("given point outside the domain");
+          c0_ = b_c0[k];
+          c1_ = b_c1[k];
+          if (!LEAF(leaf))
+            {
+              /* the snapshot's leaf has been subdivided since: finish the descent on the live tree */
+              int last = b_last[k];
+              gsi_rec leaf_rec;
+              leaf = descend_view(&view, &T.xf, leaf, px_[i + k], py_[i + k], &c0_, &c1_, &last, &leaf_rec, 1);
+              if (leaf < 0) return fail("given point outside the domain");
+            }
+          const int st = insert_point(leaf);
+          if (st) return st;
+        }
+      i += count;
     }
   return 0;
 }
+
+/* the batched protocol on the host: descends on a private copy of the snapshot */
+class host_snapshot_locator : public gsi_build_locator
+{
+public:
+  int begin(const gsi_xform &xf, const double *px, const double *py, size_t, size_t) override
+  {
+    xf_ = xf; px_ = px; py_ = py;
+    rec_.clear(); lnk_.clear(); type_.clear();
+    return 0;
+  }
+  int locate(const gsi_rec *rec, const int32_t *lnk, const uint8_t *type, size_t n_nodes, size_t n_prev, size_t first,
+             size_t count, int32_t *node, double *c0, double *c1, int32_t *last) override
+  {
+    rec_.insert(rec_.end(), rec + n_prev, rec + n_nodes); /* records are immutable: only the new ones */
+    lnk_.assign(lnk, lnk + 3 * n_nodes);
+    type_.assign(type, type + n_nodes);
+    tree_view view{&rec_, &lnk_, &type_};
+    for (size_t k = 0; k < count; k++)
+      {
+        double a = 0, b = 0;
+        int l = -1;
+        gsi_rec leaf_rec;
+        node[k] = descend_view(&view, &xf_, 0, px_[first + k], py_[first + k], &a, &b, &l, &leaf_rec, 0);
+        c0[k] = a; c1[k] = b; last[k] = l;
+      }
+    return 0;
+  }
+
+private:
+  gsi_xform xf_;
+  const double *px_ = nullptr, *py_ = nullptr;
+  std::vector<gsi_rec> rec_;
+  std::vector<int32_t> lnk_;
+  std::vector<uint8_t> type_;
+};
 
 } // namespace
 
@@ -662,15 +751,21 @@ gsi_shuffle_mt19937(unsigned long seed, size_t n, int64_t *order)
 
 int
 gsi_build_tree(const double *xa, const double *ya, size_t n, int flags, const int64_t *order,
-               gsi_host_tree *out, std::string *err)
+               gsi_host_tree *out, std::string *err, gsi_build_locator *locator)
 {
   if (n > 0 && (!xa || !ya)) return 4; /* GSL_EINVAL */
   if (n > (size_t) 200000000) return 4; /* node ids are int32: 9n must fit */
   const auto t0 = std::chrono::steady_clock::now();
   builder b(*out, err);
-  const int st = b.run(xa, ya, n, flags, order);
+  const int st = b.run(xa, ya, n, flags, order, locator);
   out->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return st;
+}
+
+gsi_build_locator *
+gsi_make_host_snapshot_locator()
+{
+  return new host_snapshot_locator();
 }
 
 void

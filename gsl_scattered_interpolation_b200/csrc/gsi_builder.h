@@ -36,8 +36,38 @@ struct gsi_host_tree
   gsi_xform xf;                 /* scale / shift */
   double seed[6];               /* tree->seed_points, row-major 3x2, raw coordinates */
   double build_seconds = 0;
+  /* batched locate (gsi_build_locator): points located through it, rounds, seconds inside it */
+  size_t batched_points = 0, batched_rounds = 0;
+  double batched_seconds = 0;
 
   size_t n_nodes() const { return type.size(); }
+};
+
+/* Batched point location for the builder.
+ *
+ * insert_point's caller locates every new point with the same descent the evaluation path uses
+ * (linear_simplex.c:283-293 -> find_leaf, :331-402), one point after the other, and that descent
+ * is about half of the build.  A node's children never change once it has them, so the descent
+ * of point i through the nodes that existed when point s <= i was inserted is the same whenever it
+ * is run: the builder hands the points [s, e) to a locator together with the tree as of point s,
+ * gets back for each the node where that descent leaves the snapshot (a leaf of the snapshot) and
+ * the state it arrived with (accel->coords, the node they belong to), and finishes each descent
+ * on the live tree from there (GSI_DEFINE_DESCEND, resume = 1) right before inserting the point --
+ * a few levels instead of ~45 at 10^6 nodes.  The result is the reference's tree node for node.
+ * The CUDA implementation lives in gsi_capi.cu / gsi_kernels.cu (k_build_locate). */
+struct gsi_build_locator
+{
+  virtual ~gsi_build_locator() {}
+  /* called once before the first round: the points in insertion order, the transform, and an
+     upper bound of the number of nodes the tree will have */
+  virtual int begin(const gsi_xform &xf, const double *px, const double *py, size_t n, size_t max_nodes) = 0;
+  /* The tree now has n_nodes nodes, n_prev of which were there at the previous call (0 at the
+     first).  rec[i] = LU half + swap/singular bits of node i (immutable once made), lnk / type as
+     in gsi_host_tree (a node's links are final once its type is not GSI_LEAF).  Locate the points
+     [first, first + count): node[k] = leaf of this snapshot reached by point first + k (< 0:
+     GSI_DESCEND_OUTSIDE / GSI_DESCEND_LOOP), c0/c1/last = the state on arrival. */
+  virtual int locate(const gsi_rec *rec, const int32_t *lnk, const uint8_t *type, size_t n_nodes, size_t n_prev,
+                     size_t first, size_t count, int32_t *node, double *c0, double *c1, int32_t *last) = 0;
 };
 
 /* Fill `order` with gsl_ran_shuffle(gsl_rng_mt19937 seeded `seed`) applied to the identity. */
@@ -46,7 +76,12 @@ void gsi_shuffle_mt19937(unsigned long seed, size_t n, int64_t *order);
 /* Build the tree of the points (xa[i], ya[i]).  order == NULL: data order.
  * Returns 0 on success; on failure returns a GSL error code and sets *err. */
 int gsi_build_tree(const double *xa, const double *ya, size_t n, int flags,
-                   const int64_t *order, gsi_host_tree *out, std::string *err);
+                   const int64_t *order, gsi_host_tree *out, std::string *err,
+                   gsi_build_locator *locator = nullptr);
+
+/* a locator that runs the descent on the host over a COPY of the snapshot (tests of the batched
+ * protocol without a GPU; never used by the library itself) */
+gsi_build_locator *gsi_make_host_snapshot_locator();
 
 /* Raw coordinates of vertex id `p` (negative = seed), DATA_POINT of linear_simplex.h:82-93. */
 static inline void

@@ -137,6 +137,8 @@ struct eval_ctx
   size_t ovf_words = 0;
   unsigned *counters = nullptr;
   unsigned long long *scratch2 = nullptr; /* 2 x u64 for checksum / compare */
+  unsigned long long *trace = nullptr;    /* param "walk_trace": 4 x u64 per CTA of the last k_walkp launch */
+  size_t trace_ctas = 0;
   stage_buf st[2];
   size_t st_cap = 0, st_fields = 0;
   host_stage hs[2];
@@ -168,6 +170,85 @@ struct replica
   std::vector<eval_ctx *> ctxs;
 };
 
+/* the builder's batched locate on a CUDA device (gsi_builder.h, k_build_locate) */
+class cuda_build_locator : public gsi_build_locator
+{
+public:
+  explicit cuda_build_locator(int dev) : dev_(dev) {}
+  ~cuda_build_locator() override
+  {
+    device_guard restore;
+    if (cudaSetDevice(dev_) != cudaSuccess) return;
+    for (void *p : {(void *) d_rec_, (void *) d_lnk_, (void *) d_type_, (void *) d_px_, (void *) d_py_, (void *) d_node_,
+                    (void *) d_c0_, (void *) d_c1_, (void *) d_last_})
+      if (p) cudaFree(p);
+    cudaGetLastError();
+  }
+  int begin(const gsi_xform &xf, const double *px, const double *py, size_t n, size_t max_nodes) override
+  {
+    device_guard restore;
+    if (cudaSetDevice(dev_) != cudaSuccess) return fail();
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev_) != cudaSuccess) return fail();
+    sm_count_ = prop.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    const size_t per_round = n / 2 + 1;
+    const size_t need = max_nodes * (sizeof(gsi_rec) + 13) + n * 16 + per_round * 24;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need + ((size_t) 1 << 30) > free_b) return fail();
+    xf_ = xf;
+    max_nodes_ = max_nodes;
+    cap_ = per_round;
+    if (cudaMalloc(&d_rec_, max_nodes * sizeof(gsi_rec)) != cudaSuccess || cudaMalloc(&d_lnk_, max_nodes * 12) != cudaSuccess
+        || cudaMalloc(&d_type_, max_nodes) != cudaSuccess || cudaMalloc(&d_px_, n * 8) != cudaSuccess
+        || cudaMalloc(&d_py_, n * 8) != cudaSuccess || cudaMalloc(&d_node_, per_round * 4) != cudaSuccess
+        || cudaMalloc(&d_c0_, per_round * 8) != cudaSuccess || cudaMalloc(&d_c1_, per_round * 8) != cudaSuccess
+        || cudaMalloc(&d_last_, per_round * 4) != cudaSuccess)
+      return fail();
+    if (cudaMemcpy(d_px_, px, n * 8, cudaMemcpyHostToDevice) != cudaSuccess
+        || cudaMemcpy(d_py_, py, n * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail();
+    return 0;
+  }
+  int locate(const gsi_rec *rec, const int32_t *lnk, const uint8_t *type, size_t n_nodes, size_t n_prev, size_t first,
+             size_t count, int32_t *node, double *c0, double *c1, int32_t *last) override
+  {
+    if (n_nodes > max_nodes_ || count > cap_ || n_prev > n_nodes) return 1;
+    device_guard restore;
+    if (cudaSetDevice(dev_) != cudaSuccess) return fail();
+    /* LU records never change: only the new ones travel; links and types of old nodes do change */
+    if (cudaMemcpyAsync(d_rec_ + n_prev, rec + n_prev, (n_nodes - n_prev) * sizeof(gsi_rec), cudaMemcpyHostToDevice, 0)
+            != cudaSuccess
+        || cudaMemcpyAsync(d_lnk_, lnk, n_nodes * 12, cudaMemcpyHostToDevice, 0) != cudaSuccess
+        || cudaMemcpyAsync(d_type_, type, n_nodes, cudaMemcpyHostToDevice, 0) != cudaSuccess)
+      return fail();
+    if (gsi_launch_build_locate(d_rec_, d_lnk_, d_type_, xf_, d_px_, d_py_, first, count, d_node_, d_c0_, d_c1_, d_last_,
+                                sm_count_, 0)
+        != cudaSuccess)
+      return fail();
+    if (cudaMemcpyAsync(node, d_node_, count * 4, cudaMemcpyDeviceToHost, 0) != cudaSuccess
+        || cudaMemcpyAsync(c0, d_c0_, count * 8, cudaMemcpyDeviceToHost, 0) != cudaSuccess
+        || cudaMemcpyAsync(c1, d_c1_, count * 8, cudaMemcpyDeviceToHost, 0) != cudaSuccess
+        || cudaMemcpyAsync(last, d_last_, count * 4, cudaMemcpyDeviceToHost, 0) != cudaSuccess
+        || cudaStreamSynchronize(0) != cudaSuccess)
+      return fail();
+    return 0;
+  }
+
+private:
+  int fail()
+  {
+    cudaGetLastError();
+    return 1;
+  }
+  int dev_, sm_count_ = 148;
+  gsi_xform xf_;
+  size_t max_nodes_ = 0, cap_ = 0;
+  gsi_rec *d_rec_ = nullptr;
+  int32_t *d_lnk_ = nullptr, *d_node_ = nullptr, *d_last_ = nullptr;
+  uint8_t *d_type_ = nullptr;
+  double *d_px_ = nullptr, *d_py_ = nullptr, *d_c0_ = nullptr, *d_c1_ = nullptr;
+};
+
 } // namespace
 
 struct gsl_scattered_cuda
@@ -192,6 +273,11 @@ struct gsl_scattered_cuda
   size_t reorder_max_fields = 2;
   int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
   int exact_coop = 1;  /* deferred queries are replayed by four lanes each (0: one thread each) */
+  int walk_variant = 0; /* 1: k_walkp (two walks per lane in rotation behind L2 prefetches), 0: k_walk */
+  int walk_dynamic = 1; /* k_walkp draws its chunks from a device counter (0: round-robin) */
+  int walk_pf = 1;      /* k_walkp: 0 no prefetch, 1..4 = flavours of gsi_prefetch_leaf_l2 */
+  int walk_trace = 0;   /* diagnostic: per-CTA {smid, start, end, queries} of the last k_walkp launch */
+  int build_device = 1; /* the builder locates its points in batches on the GPU when there is one (0: host only) */
   int vmm = 1;         /* slab through cuMemCreate/cuMemMap with the recommended granularity (0: cudaMalloc) */
   size_t walk_chunk = 0;
   size_t chunk = (size_t) 0xfffffff0u;
@@ -362,6 +448,7 @@ free_ctx(eval_ctx *c)
   if (c->ovf_mask) cudaFree(c->ovf_mask);
   if (c->counters) cudaFree(c->counters);
   if (c->scratch2) cudaFree(c->scratch2);
+  if (c->trace) cudaFree(c->trace);
   free_reorder(c);
   free_host_stage(c);
   for (int b = 0; b < 2; b++)
@@ -558,6 +645,10 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r, const eval_ctx *c)
   g.walk_ctas_per_sm = w->walk_ctas_per_sm;
   g.exact_coop = w->exact_coop;
   g.walk_chunk = w->walk_chunk;
+  g.walk_variant = w->walk_variant;
+  g.walk_dynamic = w->walk_dynamic;
+  g.walk_pf = w->walk_pf;
+  g.walk_trace = (w->walk_trace && c->trace_ctas >= (size_t) r->sm_count * (size_t) w->walk_ctas_per_sm) ? c->trace : nullptr;
   g.list = c->list;
   g.list_capacity = c->list_cap;
   g.ovf_mask = c->ovf_mask;
@@ -680,6 +771,16 @@ eval_on_device(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, const
                                            (size_t) (w->list_fraction * (double) per_launch));
       const int s = ensure_list(c, want, per_launch);
       if (s) return s;
+      const size_t ctas = (size_t) r->sm_count * (size_t) w->walk_ctas_per_sm;
+      if (w->walk_trace && c->trace_ctas < ctas)
+        {
+          if (c->trace) cudaFree(c->trace);
+          c->trace = nullptr;
+          c->trace_ctas = 0;
+          CU(cudaMalloc(&c->trace, ctas * 4 * sizeof(unsigned long long)));
+          CU(cudaMemset(c->trace, 0, ctas * 4 * sizeof(unsigned long long)));
+          c->trace_ctas = ctas;
+        }
     }
   for (size_t off = 0; off < nq; off += chunk)
     {
@@ -1200,7 +1301,12 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "tile_threads" && value >= 32 && value <= GSI_TILE_THREADS) w->tile_threads = (int) value;
   else if (k == "tile_leaves" && value >= 1) w->fprm.tile_leaves = (uint32_t) value;
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
+  else if (k == "build_device" && (value == 0 || value == 1)) w->build_device = (int) value;
   else if (k == "exact_coop" && (value == 0 || value == 1)) w->exact_coop = (int) value;
+  else if (k == "walk_variant" && (value == 0 || value == 1)) w->walk_variant = (int) value;
+  else if (k == "walk_dynamic" && (value == 0 || value == 1)) w->walk_dynamic = (int) value;
+  else if (k == "walk_pf" && value >= 0 && value <= 4) w->walk_pf = (int) value;
+  else if (k == "walk_trace" && (value == 0 || value == 1)) w->walk_trace = (int) value;
   else if (k == "copy_threads" && value >= 1 && value <= 64) w->copy_threads = (int) value;
   else if (k == "pageable_min" && value >= 0) w->pageable_min = (size_t) value;
   else if (k == "exact_entry" && (value == 0 || value == 1))
@@ -1249,8 +1355,32 @@ gsl_scattered_cuda_build(gsl_scattered_cuda *w, const double xa[], const double 
       for (size_t i = 0; i < n_nodes; i++) ord[i] = (int64_t) order[i];
     }
   std::string err;
-  const int s = gsi_build_tree(w->xa.data(), w->ya.data(), n_nodes, init_flags,
-                               order ? ord.data() : nullptr, &w->tree, &err);
+  /* with a CUDA device the builder's own point locations run there in
+     batches (same tree, node for node); without one, or when it cannot be set up, on the host */
+  cuda_build_locator *loc = nullptr;
+  if (w->build_device && n_nodes > 4096)
+    {
+      int ndev = 0;
+      if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0)
+        {
+          int dev = 0;
+          if (!w->devs.empty()) dev = w->devs[0];
+          else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+          loc = new (std::nothrow) cuda_build_locator(dev);
+        }
+      cudaGetLastError();
+    }
+  int s;
+  try
+    {
+      s = gsi_build_tree(w->xa.data(), w->ya.data(), n_nodes, init_flags, order ? ord.data() : nullptr, &w->tree, &err, loc);
+    }
+  catch (...)
+    {
+      delete loc;
+      throw;
+    }
+  delete loc;
   if (s) GSI_ERROR(err.empty() ? "triangulation build failed" : err.c_str(), s);
   w->built = true;
   return GSL_SCATTERED_SUCCESS;
@@ -1789,6 +1919,44 @@ gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, const in
   CU(gsi_launch_compare(d_leaf_a, d_leaf_b, d_val_a, d_val_b, n, n_val, lease.c->scratch2, r->sm_count, lease.st));
   CU(cudaMemcpyAsync(out, lease.c->scratch2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, lease.st));
   CU(cudaStreamSynchronize(lease.st));
+  return GSL_SCATTERED_SUCCESS;
+  GSI_GUARD_END
+}
+
+/* how much of the last build went through the batched device locate */
+int
+gsl_scattered_cuda_build_stats(const gsl_scattered_cuda *w, double *batched_seconds, size_t *batched_points, size_t *rounds)
+{
+  if (!w) GSI_ERROR("null argument", GSL_SCATTERED_EINVAL);
+  if (batched_seconds) *batched_seconds = w->tree.batched_seconds;
+  if (batched_points) *batched_points = w->tree.batched_points;
+  if (rounds) *rounds = w->tree.batched_rounds;
+  return GSL_SCATTERED_SUCCESS;
+}
+
+/* diagnostic (param "walk_trace"): per-CTA {smid, start ns, end ns, queries handed out} of the most
+ * recent k_walkp launch of the replica's first evaluation context; *n_words = words written */
+int
+gsl_scattered_cuda_debug_walk_trace(const gsl_scattered_cuda *w, int dev, unsigned long long *out, size_t cap_words,
+                                    size_t *n_words)
+{
+  if (!w || !w->uploaded || !out || !n_words) GSI_ERROR("bad argument", GSL_SCATTERED_EINVAL);
+  replica *r = find_replica(w, dev);
+  if (!r) GSI_ERROR("device holds no replica", GSL_SCATTERED_EINVAL);
+  GSI_GUARD_BEGIN
+  device_guard restore;
+  CU(cudaSetDevice(dev));
+  CU(cudaDeviceSynchronize());
+  *n_words = 0;
+  std::lock_guard<std::mutex> lock(r->mu);
+  for (eval_ctx *c : r->ctxs)
+    if (c->trace && c->trace_ctas)
+      {
+        const size_t n = std::min(cap_words, c->trace_ctas * 4);
+        CU(cudaMemcpy(out, c->trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        *n_words = n;
+        break;
+      }
   return GSL_SCATTERED_SUCCESS;
   GSI_GUARD_END
 }

@@ -399,7 +399,7 @@ gsi_exact_one(const gsi_view *V, double qx, double qy, double *val, int *leaf_ou
   int last = -1;
   gsi_rec lr;
   const int start = V->entry ? GSI_LDG(V->entry + gsi_cell_of(V, qx, qy)) : 0;
-  const int node = gsi_descend(V->dag, &V->xf, start, qx, qy, &c0, &c1, &last, &lr);
+  const int node = gsi_descend(V->dag, &V->xf, start, qx, qy, &c0, &c1, &last, &lr, 0);
   if (node < 0)
     {
       if (leaf_out) leaf_out[q] = -1;

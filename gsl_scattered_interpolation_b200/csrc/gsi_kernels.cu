@@ -622,6 +622,230 @@ k_walk(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, 
     atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
 }
 
+/* ---- fast path, two walks per lane in rotation behind L2 prefetches ----------------------------
+ * k_walk exposes one full DRAM latency per loop iteration: the leaf a lane needs next (its
+ * seed, or the neighbour it just moved to) is only requested when the lane gets there.  Here
+ * every lane owns TWO ready queries, P and Q, and alternates between them: one iteration is a
+ * walk step of P; when it ends the lane knows which leaf P needs next (the neighbour it moved
+ * to, or the seed of the query that replaces it) and asks the L2 for that line
+ * (prefetch.global.L2 -- no destination register, nothing to wait for), then turns to Q, whose
+ * line was requested one iteration ago.  The record loads themselves then hit the L2, and the
+ * HBM fill of one query overlaps the arithmetic of the other.  Behind P and Q sit the two feeder
+ * stages of k_walk (N: seed cell being loaded, M: coordinates being loaded).
+ *
+ * The queue is continuous: a warp draws chunks of `chunk` consecutive queries from a device
+ * counter (the id of the chunk after the current one is always in flight) and moves on to the
+ * next chunk in the middle of a refill, so there is no drain/fill bubble per chunk and a CTA that
+ * starts late or runs on a slower SM simply takes fewer chunks.  `trace` (optional, zeroed by the
+ * caller) receives {smid, start, end in globaltimer ns, queries handed out} per CTA. */
+/* how the line(s) of a leaf record are requested ahead of time (experiment knob "walk_pf"):
+ *   0 nothing; 1 prefetch.global.L2 on the first byte (+ the last sector when the record ends in the
+ *   next line); 2 prefetch.global.L2 on each of the three sectors; 3 one TMA bulk prefetch of the 96
+ *   bytes; 4 a 4-byte demand load per line (returned in *sink so that it stays in flight) */
+__device__ __forceinline__ void
+gsi_prefetch_leaf_l2(const gsi_view &V, int slot, int how, unsigned *sink)
+{
+  const char *p = reinterpret_cast<const char *>(gsi_leaf_at(&V, slot));
+  const bool straddles = (((unsigned) (size_t) p) & 127u) > 128u - (unsigned) sizeof(gsi_leaf);
+  if (how == 1)
+    {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      if (straddles) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + sizeof(gsi_leaf) - 32));
+    }
+  else if (how == 2)
+    {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 64));
+    }
+  else if (how == 3)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((unsigned) sizeof(gsi_leaf)) : "memory");
+  else if (how == 4)
+    {
+      unsigned a, b = 0;
+      asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(a) : "l"(p));
+      if (straddles) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(b) : "l"(p + sizeof(gsi_leaf) - 32));
+      *sink = a ^ b;
+    }
+}
+
+template <class SRC, bool STATS, bool ONE_FIELD>
+__global__ void __launch_bounds__(GSI_WALK_THREADS, 5)
+k_walkp(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
+        size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
+        int max_steps, int dynamic, int pf, unsigned long long *trace)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned n_chunks = (unsigned) ((nq + chunk - 1) / chunk);
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned *work = counters + GSI_CNT_WORK;
+  unsigned long long steps_acc = 0, t_start = 0;
+  unsigned handed = 0;
+  if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+
+  /* warp-uniform queue state: queries [base + next, base + total) of the current chunk are still
+     to be handed out; lane 0 keeps the id of the following chunk in `ahead` (atomic in flight) */
+  unsigned base = 0, next = 0, total = 0, ahead = 0;
+  bool dry = false; /* the counter ran past the last chunk */
+  /* dynamic = 0 deals the chunks round-robin instead (warp w: w, w + n_warps, ...) */
+  if (lane == 0) ahead = dynamic ? atomicAdd(work, 1u) : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+  bool p_v = false, q_v = false, n_v = false, m_v = false;
+  unsigned p_q = 0, q_q = 0, n_q = 0, m_q = 0;
+  double p_x = 0, p_y = 0, q_x = 0, q_y = 0, n_x = 0, n_y = 0, m_x = 0, m_y = 0;
+  int p_slot = 0, q_slot = 0, n_seed = 0, p_steps = 0, q_steps = 0;
+  unsigned p_sink = 0, q_sink = 0, sink_acc = 0;
+  for (;;)
+    {
+      /* ---- one walk step of P (its leaf line was requested an iteration ago) */
+      bool defer = false;
+      if (pf == 4) sink_acc ^= p_sink;
+      if (p_v)
+        {
+          if (!(isfinite(p_x) && isfinite(p_y)))
+            defer = true;
+          else
+            {
+              const gsi_leaf *lf = gsi_leaf_at(&V, p_slot);
+              gsi_rec r;
+              gsi_leaf_tail t;
+              gsi_fetch_rec(&r, lf);
+              gsi_fetch_tail(&t, lf); /* speculative: only used when this leaf is accepted */
+              double c0, c1;
+              const int st = gsi_walk_step(&V.xf, &r, p_x, p_y, &p_slot, &c0, &c1);
+              ++p_steps;
+              if (st == GSI_STEP_ACCEPT)
+                {
+                  const size_t q = p_q;
+                  if (leaf_out) GSI_ST_RESULT(leaf_out + q, t.g.node);
+                  if (val)
+                    {
+                      if (ONE_FIELD)
+                        GSI_ST_RESULT(val + q, gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0],
+                                           (int) (t.s.vflags & 2u), t.s.z[1],
+                                           (int) (t.s.vflags & 4u), t.s.z[2]));
+                      else
+                        gsi_blend_store(&V, &t, c0, c1, val, ld, q);
+                    }
+                  if (STATS) steps_acc += (unsigned) p_steps;
+                  p_v = false;
+                }
+              else if (st == GSI_STEP_DEFER || p_steps >= max_steps)
+                defer = true;
+            }
+          if (defer) p_v = false;
+        }
+      /* warp-aggregated append to the deferred list */
+      const unsigned dm = __ballot_sync(FULL, defer);
+      if (dm)
+        {
+          const int leader = __ffs(dm) - 1;
+          unsigned pos = 0;
+          if (lane == (unsigned) leader)
+            pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+          pos = __shfl_sync(FULL, pos, leader);
+          if (defer)
+            {
+              const unsigned at = pos + __popc(dm & lt_mask);
+              if (at < list_cap)
+                list[at] = p_q;
+              else
+                mark_overflow(ovf_mask, (size_t) p_q, counters);
+            }
+        }
+
+      /* ---- refill: P <- N (seed known by now), N <- M (issue its seed load), M <- queue */
+      const bool need = !p_v;
+      if (need)
+        {
+          p_v = n_v; p_q = n_q; p_x = n_x; p_y = n_y; p_slot = n_seed; p_steps = 0;
+          n_v = m_v; n_q = m_q; n_x = m_x; n_y = m_y;
+          if (n_v && isfinite(n_x) && isfinite(n_y)) n_seed = gsi_seed_of(&V, n_x, n_y);
+          m_v = false;
+        }
+      const unsigned take = __ballot_sync(FULL, need);
+      if (take && !dry)
+        {
+          const unsigned cnt = (unsigned) __popc(take), rank = (unsigned) __popc(take & lt_mask);
+          unsigned rem = total - next;
+          if (cnt > rem)
+            {
+              /* the lanes ranked below `rem` finish the current chunk, the others start the next */
+              const unsigned ch = __shfl_sync(FULL, ahead, 0);
+              if (need && rank < rem)
+                {
+                  m_v = true;
+                  m_q = base + next + rank;
+                }
+              if (ch < n_chunks)
+                {
+                  if (lane == 0) ahead = dynamic ? atomicAdd(work, 1u) : ch + n_warps;
+                  base = ch * chunk;
+                  total = (unsigned) (nq - (size_t) base < (size_t) chunk ? nq - (size_t) base : (size_t) chunk);
+                  const unsigned want = cnt - rem;
+                  if (need && rank >= rem && rank - rem < total)
+                    {
+                      m_v = true;
+                      m_q = base + (rank - rem);
+                    }
+                  next = want < total ? want : total;
+                }
+              else
+                {
+                  dry = true;
+                  next = total;
+                }
+            }
+          else
+            {
+              if (need)
+                {
+                  m_v = true;
+                  m_q = base + next + rank;
+                }
+              next += cnt;
+            }
+          if (need && m_v) src.get_linear((size_t) m_q, m_x, m_y);
+          if (trace) handed += (unsigned) __popc(__ballot_sync(FULL, need && m_v));
+        }
+      /* ask the L2 for the line P needs two iterations from now (moved: the neighbour; refilled:
+         the seed leaf) */
+      if (pf && p_v && isfinite(p_x) && isfinite(p_y)) gsi_prefetch_leaf_l2(V, p_slot, pf, &p_sink);
+      if (!__any_sync(FULL, p_v || q_v || n_v || m_v)) break;
+
+      /* ---- rotate: Q is processed next */
+      {
+        const bool tv = p_v; p_v = q_v; q_v = tv;
+        const unsigned tq = p_q; p_q = q_q; q_q = tq;
+        double td = p_x; p_x = q_x; q_x = td;
+        td = p_y; p_y = q_y; q_y = td;
+        int ti = p_slot; p_slot = q_slot; q_slot = ti;
+        ti = p_steps; p_steps = q_steps; q_steps = ti;
+        const unsigned ts = p_sink; p_sink = q_sink; q_sink = ts;
+      }
+    }
+  if (STATS && steps_acc)
+    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
+  if (pf == 4 && sink_acc == 0x9e3779b9u && nq == 0) counters[GSI_CNT_WORDS - 1] = sink_acc; /* keeps the loads alive */
+  if (trace)
+    {
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          unsigned long long t_end;
+          unsigned smid;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          trace[4 * (size_t) blockIdx.x + 0] = smid;
+          trace[4 * (size_t) blockIdx.x + 1] = t_start;
+          trace[4 * (size_t) blockIdx.x + 2] = t_end;
+        }
+      if (lane == 0) atomicAdd(trace + 4 * (size_t) blockIdx.x + 3, (unsigned long long) handed);
+    }
+}
+
 /* ---- reorder pipeline: k_bin -> k_tile_walk -> k_unpermute -----------------------------------
  * Uniformly random queries make every leaf fetch an isolated L2/DRAM line fill: at 10^6 nodes the
  * direct walk moves ~220 bytes per query through HBM for 28 algorithmic bytes.  The pipeline
@@ -1478,6 +1702,52 @@ k_selftest_division(uint64_t seed, size_t n, unsigned long long *out)
     }
 }
 
+/* ---- batched point location for the host builder -----------------------
+ * The builder (gsi_builder.cpp) locates every point it inserts with find_leaf's descent.  A node's
+ * children are final once it has them, so the descent of point i through a SNAPSHOT of the growing
+ * tree is the prefix of its real descent: one thread per point replays it on the snapshot (the
+ * same GSI_DEFINE_DESCEND as the evaluation replay and the host builder: identical operations,
+ * identical results) and returns the snapshot leaf it ends in plus the state it arrived with; the
+ * host finishes the few levels the tree has grown since.  The snapshot lives in three arrays as on
+ * the host: LU records (written once per node), links and types (re-uploaded every round). */
+struct gsi_build_view
+{
+  const gsi_rec *rec;
+  const int32_t *lnk;
+  const uint8_t *type;
+};
+
+#define GSI_FETCH_BUILD(dst, idx)                                                              \
+  do                                                                                           \
+    {                                                                                          \
+      const size_t i_ = (size_t) (idx);                                                        \
+      gsi_fetch_rec(&(dst), dag->rec + i_);                                                    \
+      (dst).lnk[0] = __ldg(dag->lnk + 3 * i_);                                                 \
+      (dst).lnk[1] = __ldg(dag->lnk + 3 * i_ + 1);                                             \
+      (dst).lnk[2] = __ldg(dag->lnk + 3 * i_ + 2);                                             \
+      (dst).meta = ((dst).meta & (GSI_META_SWAP | GSI_META_SINGULAR)) | (uint32_t) __ldg(dag->type + i_); \
+    }                                                                                          \
+  while (0)
+GSI_DEFINE_DESCEND(descend_build, __device__ __forceinline__, const gsi_build_view *, GSI_FETCH_BUILD)
+
+__global__ void __launch_bounds__(128, 4)
+k_build_locate(const gsi_build_view B, const gsi_xform xf, const double *__restrict__ px,
+               const double *__restrict__ py, size_t first, size_t count, int32_t *node, double *c0,
+               double *c1, int32_t *last)
+{
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride)
+    {
+      double a = 0, b = 0;
+      int l = -1;
+      gsi_rec leaf_rec;
+      node[k] = descend_build(&B, &xf, 0, __ldg(px + first + k), __ldg(py + first + k), &a, &b, &l, &leaf_rec, 0);
+      c0[k] = a;
+      c1[k] = b;
+      last[k] = l;
+    }
+}
+
 __global__ void
 k_accumulate_deferred(unsigned *counters)
 {
@@ -1485,6 +1755,7 @@ k_accumulate_deferred(unsigned *counters)
   unsigned long long *tot = reinterpret_cast<unsigned long long *>(counters + GSI_CNT_DEFERRED_TOTAL);
   *tot += c;
   counters[GSI_CNT_OVERFLOW] = 0;
+  counters[GSI_CNT_WORK] = 0;
 }
 
 inline int
@@ -1623,15 +1894,31 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
     {
       const int ctas = cfg.sm_count * cfg.walk_ctas_per_sm;
       const size_t n_warps = (size_t) ctas * (GSI_WALK_THREADS / 32);
-      /* per-warp chunk: ~8 chunks per warp for balance, 256..8192 queries, multiple of 32 */
+      /* per-warp chunk: ~8 chunks per warp for balance, 256..8192 queries, multiple of 32; the
+         continuous queue of k_walkp pays nothing per chunk, so its chunks stay small */
       size_t chunk = (nq / (n_warps * 8) + 31) & ~(size_t) 31;
       if (chunk < 256) chunk = 256;
-      if (chunk > 8192) chunk = 8192;
+      if (chunk > (cfg.walk_variant ? 2048u : 8192u)) chunk = cfg.walk_variant ? 2048 : 8192;
       if (cfg.walk_chunk) chunk = cfg.walk_chunk;
       const size_t n_chunks = (nq + chunk - 1) / chunk;
       const int g = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas
                                ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
                                : (size_t) ctas);
+      if (cfg.walk_variant)
+        {
+          if (cfg.walk_trace) cudaMemsetAsync(cfg.walk_trace, 0, (size_t) ctas * 4 * sizeof(unsigned long long), st);
+#define GSI_LAUNCH_WALKP(STATS, ONE)                                                            \
+  k_walkp<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out, \
+                                                           ld, cfg.list, list_cap, cfg.ovf_mask,      \
+                                                           cfg.counters, cfg.max_steps, cfg.walk_dynamic, cfg.walk_pf, cfg.walk_trace)
+          if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKP(true, true);
+          else if (cfg.stats) GSI_LAUNCH_WALKP(true, false);
+          else if (V.n_fields == 1) GSI_LAUNCH_WALKP(false, true);
+          else GSI_LAUNCH_WALKP(false, false);
+#undef GSI_LAUNCH_WALKP
+        }
+      else
+        {
 #define GSI_LAUNCH_WALK(STATS, ONE)                                                             \
   k_walk<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out,  \
                                                           ld, cfg.list, list_cap, cfg.ovf_mask,      \
@@ -1641,6 +1928,7 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
       else if (V.n_fields == 1) GSI_LAUNCH_WALK(false, true);
       else GSI_LAUNCH_WALK(false, false);
 #undef GSI_LAUNCH_WALK
+        }
     }
   else if (cfg.stats)
     k_locate<SRC, true><<<grid_for(src.n_launch(nq), GSI_LOCATE_THREADS, cfg.sm_count, cfg.locate_ctas_per_sm),
@@ -1764,6 +2052,17 @@ gsi_launch_deriv(const gsi_view &V, const int *leaf, size_t nq, double *dzdx, do
 {
   if (nq == 0) return cudaSuccess;
   k_deriv<<<grid_for(nq, 256, sm_count, 8), 256, 0, st>>>(V, leaf, nq, dzdx, dzdy, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_build_locate(const gsi_rec *rec, const int32_t *lnk, const uint8_t *type, const gsi_xform &xf,
+                        const double *px, const double *py, size_t first, size_t count, int32_t *node, double *c0,
+                        double *c1, int32_t *last, int sm_count, cudaStream_t st)
+{
+  if (count == 0) return cudaSuccess;
+  const gsi_build_view B{rec, lnk, type};
+  k_build_locate<<<grid_for(count, 128, sm_count, 16), 128, 0, st>>>(B, xf, px, py, first, count, node, c0, c1, last);
   return cudaGetLastError();
 }
 

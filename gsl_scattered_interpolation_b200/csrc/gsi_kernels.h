@@ -22,6 +22,7 @@
 #define GSI_CNT_DEFERRED_TOTAL 2 /* u64: deferred queries since the last reset */
 #define GSI_CNT_STEPS 4          /* u64: walk steps of accepted queries (stats launches only) */
 #define GSI_CNT_OVERFLOW 8       /* u32: deferred queries of the current launch that did not fit the list */
+#define GSI_CNT_WORK 9           /* u32: chunk counter of k_walkp (zero between launches) */
 #define GSI_CNT_WORDS 16
 
 #define GSI_MODE_FAST 0  /* grid-seeded walk + exact replay of the deferred queries */
@@ -64,6 +65,10 @@ struct gsi_launch_cfg
   int walk_ctas_per_sm = 5;
   int exact_coop = 1; /* deferred list: four lanes per query (k_exact_list4) instead of one thread (k_exact_list) */
   size_t walk_chunk = 0; /* 0 = derive from the launch size */
+  int walk_variant = 0;  /* 1 = k_walkp (two walks per lane in rotation behind L2 prefetches), 0 = k_walk */
+  int walk_dynamic = 1;  /* k_walkp: chunks dealt by a device counter (0: round-robin) */
+  int walk_pf = 1;       /* k_walkp: how the next leaf line is requested ahead (gsi_prefetch_leaf_l2) */
+  unsigned long long *walk_trace = nullptr; /* k_walkp: 4 words per CTA {smid, start ns, end ns, queries}, zeroed here */
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
   size_t list_capacity = 0;     /* deferred-list entries; overflow goes to the bitmask */
   unsigned *ovf_mask = nullptr; /* one bit per query of a launch (zero between launches) */
@@ -108,6 +113,12 @@ cudaError_t gsi_launch_validate_slab(const gsi_view &V, unsigned long long *bad,
 /* hoisted-reciprocal division against __ddiv_rn on n operand pairs: out2[0] = pairs vouched for,
  * out2[1] = mismatches among them (device memory) */
 cudaError_t gsi_launch_selftest_division(uint64_t seed, size_t n, unsigned long long *out2, int sm_count, cudaStream_t st);
+
+/* batched locate of the builder's points [first, first + count) on a snapshot of the growing tree
+ * (device arrays as in gsi_host_tree + the LU records); outputs are device arrays of `count` */
+cudaError_t gsi_launch_build_locate(const gsi_rec *rec, const int32_t *lnk, const uint8_t *type, const gsi_xform &xf,
+                                    const double *px, const double *py, size_t first, size_t count, int32_t *node,
+                                    double *c0, double *c1, int32_t *last, int sm_count, cudaStream_t st);
 
 cudaError_t gsi_launch_gen_uniform(uint64_t seed, uint64_t first, size_t nq, double xlo,
                                    double xhi, double ylo, double yhi, double *xq, double *yq,

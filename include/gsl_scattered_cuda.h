@@ -314,6 +314,20 @@ int gsl_scattered_cuda_compare_device(const gsl_scattered_cuda *w, int dev, cons
 int gsl_scattered_cuda_selftest_division(int dev, gsl_scattered_cuda_u64 seed, size_t n,
                                          gsl_scattered_cuda_u64 out[2]);
 
+/* The builder locates every point it inserts with the evaluation path's own descent
+ * (linear_simplex.c:283-293 -> find_leaf); with a CUDA device those locations run there in batches
+ * against snapshots of the growing tree (set_param "build_device" = 0: host only).  The tree is the
+ * same node for node.  Reports how much of the last build went that way. */
+int gsl_scattered_cuda_build_stats(const gsl_scattered_cuda *w, double *batched_seconds, size_t *batched_points,
+                                   size_t *rounds);
+
+/* Diagnostic (set_param "walk_trace" = 1 before evaluating): four words per thread block of the most
+ * recent fast-path launch on device `dev` -- {SM id, start, end (globaltimer ns), queries handed
+ * out}.  Shows whether a slow launch is slow everywhere or on some SMs only.  *n_words = words
+ * written (<= cap_words). */
+int gsl_scattered_cuda_debug_walk_trace(const gsl_scattered_cuda *w, int dev, gsl_scattered_cuda_u64 *out,
+                                        size_t cap_words, size_t *n_words);
+
 const char *gsl_scattered_cuda_version(void);
 
 #ifdef __cplusplus

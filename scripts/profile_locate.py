@@ -18,6 +18,7 @@ za = synth.values(n, F)
 w = g.ScatteredCuda(n, F)
 for k, v in kv:
     w.set_param(k, float(v))
+w.set_param("profile", 1)
 w.init(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n))
 dev = torch.device("cuda:0")
 dx = torch.empty(Q, dtype=torch.float64, device=dev); dy = torch.empty_like(dx)
@@ -26,5 +27,7 @@ w.generate_uniform_device(0, synth.SEED_QUERIES, 0, Q, 0.0, 1.0, 0.0, 1.0, dx.da
 for _ in range(passes):
     w.eval_device_e(0, dx.data_ptr(), dy.data_ptr(), Q, dz.data_ptr(), Q, dl.data_ptr())
 torch.cuda.synchronize()
-print("ok", w.info()["n_deferred"], w.info()["n_reordered"])
+inf = w.info()
+print("ok", inf["n_deferred"], inf["n_reordered"], "locate %.3f ms exact %.3f ms per pass of %d queries" % (
+    1e3 * inf["locate_seconds"] / passes, 1e3 * inf["exact_seconds"] / passes, Q))
 w.free()

@@ -167,4 +167,29 @@ hostsim_leaf_entry_depths(const hostsim *h, double grow, int *depth_entry, int *
     }
   return 0;
 }
+
+/* The builder's batched-locate protocol (gsi_build_locator) with the locator
+ * running on the host over a copy of each snapshot: must give the tree of the plain build node for
+ * node.  Returns 1 = identical, 0 = different, < 0 = a build failed. */
+int
+hostsim_build_batched_equal(const double *xa, const double *ya, size_t n, int flags, const size_t *order,
+                            size_t *batched_points, size_t *rounds)
+{
+  std::vector<int64_t> ord;
+  if (order)
+    {
+      ord.resize(n);
+      for (size_t i = 0; i < n; i++) ord[i] = (int64_t) order[i];
+    }
+  gsi_host_tree a, b;
+  std::string err;
+  if (gsi_build_tree(xa, ya, n, flags, order ? ord.data() : nullptr, &a, &err)) return -1;
+  gsi_build_locator *loc = gsi_make_host_snapshot_locator();
+  const int st = gsi_build_tree(xa, ya, n, flags, order ? ord.data() : nullptr, &b, &err, loc);
+  delete loc;
+  if (st) return -2;
+  if (batched_points) *batched_points = b.batched_points;
+  if (rounds) *rounds = b.batched_rounds;
+  return a.pts == b.pts && a.lnk == b.lnk && a.type == b.type && a.shuffle == b.shuffle;
+}
 }

@@ -38,8 +38,22 @@ def lib():
         H.hostsim_n_leaves.argtypes = [c_void_p]
         H.hostsim_grid_g.restype = c_size_t
         H.hostsim_grid_g.argtypes = [c_void_p]
+        H.hostsim_build_batched_equal.restype = c_int
+        H.hostsim_build_batched_equal.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p]
         _H = H
     return _H
+
+
+def build_batched_equal(xa, ya, flags=0, order=None):
+    """(identical?, points located through the batched protocol, rounds)"""
+    xa = np.ascontiguousarray(xa, dtype=np.float64)
+    ya = np.ascontiguousarray(ya, dtype=np.float64)
+    order = None if order is None else np.ascontiguousarray(order, dtype=np.uint64)
+    bp, rd = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    r = lib().hostsim_build_batched_equal(_p(xa), _p(ya), xa.size, flags, _p(order), ctypes.byref(bp), ctypes.byref(rd))
+    if r < 0:
+        raise RuntimeError("build failed (%d)" % r)
+    return bool(r), bp.value, rd.value
 
 
 class HostSim:

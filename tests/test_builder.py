@@ -94,3 +94,35 @@ def test_builder_matches_reference(n, flags, seed, kind):
     for k in ref:
         assert np.array_equal(mine[k], ref[k]), k
     rt.close()
+
+
+# ---- the batched-locate protocol of the builder: gsi_build_locator with the
+# descents run on the host over a copy of every snapshot must give the plain build's tree node for
+# node (the CUDA locator, k_build_locate, is compared the same way in tests/test_gpu_parity.py)
+@pytest.mark.parametrize("kind,n,flags,seed", [("uniform", 20000, 0, 5), ("cluster", 30000, 0, 9),
+                                               ("grid", 10000, 0, 3), ("grid", 8100, 1, None),
+                                               ("collinear", 6000, 2, 4), ("uniform", 4097, 0, 1)])
+def test_batched_locate_protocol_gives_the_same_tree(kind, n, flags, seed):
+    import hostsim_py
+    if kind == "uniform":
+        xa, ya = synth.uniform_nodes(n, seed=77 + n)
+    elif kind == "cluster":
+        xa, ya = synth.clustered_nodes(n, seed=77 + n)
+    elif kind == "grid":                               # cocircular quadruples everywhere: ties and fallbacks
+        s = int(round(n ** 0.5))
+        rng = np.random.default_rng(n)
+        xa, ya = (np.arange(s * s) % s).astype(float), (np.arange(s * s) // s).astype(float)
+        xa, ya = xa + 1e-6 * rng.standard_normal(s * s), ya + 1e-6 * rng.standard_normal(s * s)
+    else:                                              # long collinear runs
+        rng = np.random.default_rng(n)
+        xa = np.repeat(np.arange(n // 6, dtype=float), 6)
+        ya = rng.integers(0, 40, size=xa.size).astype(float)
+        xa, ya = np.unique(np.stack([xa, ya], axis=1), axis=0).T.copy()
+        xa = xa + 1e-7 * rng.standard_normal(xa.size)   # exactly collinear triples are rejected by the builder
+    order = None if seed is None else g.shuffle_mt19937(seed, xa.size)
+    try:
+        same, batched, rounds = hostsim_py.build_batched_equal(xa, ya, flags, order)
+    except RuntimeError:
+        pytest.skip("the plain build rejects this point set (as the reference's builder does)")
+    assert same
+    assert batched == xa.size - 4096 and rounds >= 1

@@ -183,12 +183,15 @@ def test_sixteen_fields_raster_vs_port():
     w.free()
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
-def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel):
-    """k_walk (0) and k_locate (1) on config 1 (1 field) and the config-3 mix (3 fields)"""
+@pytest.mark.parametrize("kernel,extra", [(0, {}), (1, {}), (0, {"walk_variant": 0}), (0, {"walk_dynamic": 0}),
+                                          (0, {"walk_pf": 0}), (0, {"walk_pf": 2}), (0, {"walk_pf": 3}),
+                                          (0, {"walk_pf": 4}), (0, {"walk_chunk": 32}), (0, {"walk_ctas_per_sm": 1})])
+def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel, extra):
+    """the walk kernels (0: k_walkp by default, k_walk with walk_variant = 0, every way of dealing chunks
+    and of requesting leaf lines ahead) and k_locate (1) on config 1 (1 field) and the config-3 mix (3 fields)"""
     xa, ya = synth.uniform_nodes(1000)
     w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
-             kernel=kernel)
+             kernel=kernel, **extra)
     xq, yq = synth.uniform_queries(10000)
     st, zq, leaf = w.eval_e(xq, yq)
     assert np.array_equal(leaf, golden["cfg1_leaf"]) and refimpl.same_bits(zq, golden["cfg1_val"])
@@ -200,7 +203,7 @@ def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel):
     w.free()
     n = 3000
     xa, ya = synth.clustered_nodes(n)
-    w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), kernel=kernel)
+    w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), kernel=kernel, **extra)
     xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
     xq[:3] = [np.nan, np.inf, 1e300]                    # non-finite / outside the cage
     st, zq, leaf = w.eval_e(xq, yq)
@@ -596,3 +599,37 @@ def test_division_by_hoisted_reciprocal():
     vouched, mismatches = int(out[0]), int(out[1])
     assert mismatches == 0
     assert vouched > 0.3 * n                    # the data-like family is never deferred, the wild ones mostly are
+
+
+@pytest.mark.parametrize("kind,n", [("uniform", 300_000), ("cluster", 200_000)])
+def test_builder_with_device_located_points_gives_the_host_tree(kind, n):
+    """the builder's point locations in batches on the GPU (k_build_locate on
+    snapshots of the growing tree, the host finishing each descent) give the tree of the host-only
+    build node for node; the evaluation of both is identical too"""
+    xa, ya = synth.uniform_nodes(n, seed=5) if kind == "uniform" else synth.clustered_nodes(n, seed=5)
+    order = g.shuffle_mt19937(11, n)
+    trees, stats = [], []
+    for dev in (1, 0):
+        w = g.ScatteredCuda(n, 1)
+        w.set_param("build_device", dev)
+        w.build(xa, ya, g.DEFAULT, order)
+        trees.append(w.get_tree(w.n_simplexes(), n))
+        stats.append(w.build_stats())
+        w.free()
+    assert stats[0]["batched_points"] == n - 4096 and stats[0]["rounds"] >= 6
+    assert stats[1]["batched_points"] == 0
+    for k in ("pts3", "lnk3", "type", "shuffle", "shift", "scale", "seed_points"):
+        assert np.array_equal(trees[0][k], trees[1][k]), k
+
+
+def test_walk_trace_diagnostic(golden):
+    """per-CTA trace of the last fast-path launch: every query handed out exactly once"""
+    n, nq = 20000, 1_000_000
+    xa, ya = synth.uniform_nodes(n)
+    w = make(xa, ya, synth.values(n, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n), walk_trace=1)
+    xq, yq = synth.uniform_queries(nq)
+    w.eval_e(xq, yq)
+    tr = w.walk_trace(0)
+    assert tr.shape[0] > 0 and int(tr[:, 3].sum()) == nq
+    assert (tr[:, 2] >= tr[:, 1]).all() and (tr[:, 0] < 200).all()
+    w.free()
