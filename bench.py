@@ -70,6 +70,8 @@ def parse():
     ap.add_argument("--param", action="append", default=[], help="library knob name=value (repeatable)")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[1..3] legs (N = 1 only)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1 only)")
+    ap.add_argument("--trace-out", default=None,
+                    help="diagnostic: write every rank's per-CTA trace of the last timed launch to PREFIX_rank<r>.npy")
     ap.add_argument("--pageable-queries", type=int, default=20_000_000,
                     help="queries per GPU per step for the pageable host-buffer leg")
     return ap.parse_args()
@@ -395,6 +397,8 @@ def main_ours(args):
     if args.cells_per_leaf:
         w.set_param("cells_per_leaf", args.cells_per_leaf)
     w.set_param("profile", 1)
+    if args.trace_out:
+        w.set_param("walk_trace", 1)
     for kv in args.param:
         k, v = kv.split("=")
         w.set_param(k, float(v))
@@ -470,6 +474,9 @@ def main_ours(args):
         return dist_util.max_over_ranks(ms_mine, dev), dist_util.gather_over_ranks(ms_mine / steps, dev), clocks
 
     ms_total, ms_by_rank, clocks = timed_region(Q, args.steps, args.warmup, True)
+    if args.trace_out:
+        tr = w.walk_trace(local)
+        np.save(f"{args.trace_out}_rank{rank}.npy", tr[tr[:, 2] > 0])
     sm_by_rank = dist_util.gather_over_ranks(clocks["sm_mhz"] or 0.0, dev)
     mem_by_rank = dist_util.gather_over_ranks(clocks.get("mem_mhz") or 0.0, dev)
     pw_by_rank = dist_util.gather_over_ranks(clocks.get("power_w_max") or 0.0, dev)
@@ -586,7 +593,17 @@ def main_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        kernel_name = "k_bin + k_tile_walk + k_unpermute (reorder pipeline)" if reordered else "k_walk"
+        variant = {0: "k_walk", 1: "k_walkp", 2: "k_walkc"}
+        for kv in args.param:
+            if kv.startswith("walk_variant="):
+                walk_variant = int(float(kv.split("=")[1]))
+                break
+        else:
+            walk_variant = 2
+        for kv in args.param:
+            if kv.startswith("leaf_stride=") and int(float(kv.split("=")[1])) != 128 and walk_variant == 2:
+                walk_variant = 0
+        kernel_name = "k_bin + k_tile_walk + k_unpermute (reorder pipeline)" if reordered else variant[walk_variant]
         # DRAM traffic of the dominant kernel(s) from the committed ncu --set full capture (per query,
         # scaled to this launch).  Only emitted when the capture was taken on exactly these sources and
         # on this configuration (scripts/ncu_capture.sh writes the source hash into the file).

@@ -273,7 +273,7 @@ struct gsl_scattered_cuda
   size_t reorder_max_fields = 2;
   int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
   int exact_coop = 1;  /* deferred queries are replayed by four lanes each (0: one thread each) */
-  int walk_variant = 0; /* 1: k_walkp (two walks per lane in rotation behind L2 prefetches), 0: k_walk */
+  int walk_variant = 2; /* 1: k_walkp (two walks per lane in rotation behind L2 prefetches), 0: k_walk */
   int walk_dynamic = 1; /* k_walkp draws its chunks from a device counter (0: round-robin) */
   int walk_pf = 1;      /* k_walkp: 0 no prefetch, 1..4 = flavours of gsi_prefetch_leaf_l2 */
   int walk_trace = 0;   /* diagnostic: per-CTA {smid, start, end, queries} of the last k_walkp launch */
@@ -648,7 +648,8 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r, const eval_ctx *c)
   g.walk_variant = w->walk_variant;
   g.walk_dynamic = w->walk_dynamic;
   g.walk_pf = w->walk_pf;
-  g.walk_trace = (w->walk_trace && c->trace_ctas >= (size_t) r->sm_count * (size_t) w->walk_ctas_per_sm) ? c->trace : nullptr;
+  g.walk_trace = w->walk_trace ? c->trace : nullptr;
+  g.walk_trace_ctas = w->walk_trace ? c->trace_ctas : 0;
   g.list = c->list;
   g.list_capacity = c->list_cap;
   g.ovf_mask = c->ovf_mask;
@@ -771,7 +772,7 @@ eval_on_device(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, const
                                            (size_t) (w->list_fraction * (double) per_launch));
       const int s = ensure_list(c, want, per_launch);
       if (s) return s;
-      const size_t ctas = (size_t) r->sm_count * (size_t) w->walk_ctas_per_sm;
+      const size_t ctas = (size_t) r->sm_count * 16;
       if (w->walk_trace && c->trace_ctas < ctas)
         {
           if (c->trace) cudaFree(c->trace);
@@ -1092,6 +1093,7 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
   cudaStream_t st = nullptr;
   CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   cudaError_t e = cudaMemcpyAsync(r0->slab, image.data(), image.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = gsi_launch_leaf_rcp(r0->view, r0->slab + w->hdr.off_leaf, r0->sm_count, st);
   if (e == cudaSuccess) e = gsi_launch_entry_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_entry), r0->sm_count, st);
   if (e == cudaSuccess) e = gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->sm_count, st);
   if (e == cudaSuccess)
@@ -1177,6 +1179,7 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       unsigned long long *bad = nullptr;
       CU(cudaMalloc(&bad, sizeof *bad));
       cudaError_t e = gsi_launch_validate_slab(r->view, bad, r->sm_count, nullptr);
+      if (e == cudaSuccess) e = gsi_launch_leaf_rcp(r->view, r->slab + w->hdr.off_leaf, r->sm_count, nullptr);
       unsigned long long n_bad = 0;
       if (e == cudaSuccess) e = cudaMemcpy(&n_bad, bad, sizeof n_bad, cudaMemcpyDeviceToHost);
       cudaFree(bad);
@@ -1303,7 +1306,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
   else if (k == "build_device" && (value == 0 || value == 1)) w->build_device = (int) value;
   else if (k == "exact_coop" && (value == 0 || value == 1)) w->exact_coop = (int) value;
-  else if (k == "walk_variant" && (value == 0 || value == 1)) w->walk_variant = (int) value;
+  else if (k == "walk_variant" && (value == 0 || value == 1 || value == 2)) w->walk_variant = (int) value;
   else if (k == "walk_dynamic" && (value == 0 || value == 1)) w->walk_dynamic = (int) value;
   else if (k == "walk_pf" && value >= 0 && value <= 4) w->walk_pf = (int) value;
   else if (k == "walk_trace" && (value == 0 || value == 1)) w->walk_trace = (int) value;

@@ -14,7 +14,8 @@ struct gsi_flatten_params
   uint32_t grid_g = 0;          /* explicit G (0 = derive from cells_per_leaf) */
   double delta = 3.725290298461914e-09; /* 2^-28: absolute edge margin, standardised units */
   double tau_floor = 9.094947017729282e-13; /* 2^-40 */
-  uint32_t leaf_stride = 96;    /* 96 = packed records, 128 = one 128-byte line per leaf */
+  uint32_t leaf_stride = 128;   /* 128 = one 128-byte line per leaf (default: k_walkc fetches a leaf as one line and keeps
+                                   the reciprocals of its divisors in the spare bytes), 96 = packed records */
   uint32_t tile_leaves = 1000;  /* target leaves per Morton-prefix tile (reorder pipeline) */
 };
 

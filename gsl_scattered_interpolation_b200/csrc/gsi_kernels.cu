@@ -846,6 +846,282 @@ k_walkp(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val,
     }
 }
 
+/* ---- fast path, warp-cooperative staging of the visited leaves (walk_variant = 2) ----------------
+ * The walk kernels above gather a leaf record with three fully divergent 256-bit loads per lane:
+ * 96 L1 tag look-ups per warp and iteration for 32 records, and that tag rate (about 0.6 sectors per
+ * clock and SM, whatever the hit rate) is what bounds them.  Here the leaves are 128-byte records on
+ * 128-byte lines (slab with leaf_stride = 128) and the WARP fetches them: eight lanes copy one record
+ * as eight 16-byte pieces of one line (cp.async, global -> shared memory without registers), four
+ * records per instruction, so a visit costs ONE tag look-up instead of three.  Every lane then reads
+ * its own record from shared memory (144-byte pitch: conflict-free 128-bit reads).  The spare 32 bytes
+ * of the line carry the reciprocals of the record's two divisors (k_leaf_rcp), so the two binary64
+ * divisions of the solve cost three operations each (gsi_walk_step_rcp; a quotient the hoisted form
+ * cannot vouch for defers the query).  With the record in shared memory the kernel fits 64
+ * registers: 8 CTAs = 32 warps per SM.  Queue as in k_walkp (continuous, chunks from a counter). */
+#define GSI_WALKC_PITCH 144
+
+struct gsi_warp_queue
+{
+  unsigned base = 0, next = 0, total = 0, ahead = 0; /* ahead: lane 0 only */
+  bool dry = false;
+  unsigned chunk, n_chunks, n_warps;
+  size_t nq;
+  unsigned *work;
+  int dynamic;
+
+  __device__ __forceinline__ void init(size_t nq_, unsigned chunk_, unsigned *work_, int dynamic_, unsigned lane)
+  {
+    nq = nq_; chunk = chunk_; work = work_; dynamic = dynamic_;
+    n_chunks = (unsigned) ((nq + chunk - 1) / chunk);
+    n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (lane == 0) ahead = dynamic ? atomicAdd(work, 1u) : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  }
+  /* warp-wide: every lane with `need` gets the next query of the stream in *q; false = none left for it */
+  __device__ __forceinline__ bool take(bool need, unsigned lane, unsigned lt_mask, unsigned *q)
+  {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned mask = __ballot_sync(FULL, need);
+    bool got = false;
+    if (!mask || dry) return false;
+    const unsigned cnt = (unsigned) __popc(mask), rank = (unsigned) __popc(mask & lt_mask);
+    const unsigned rem = total - next;
+    if (cnt > rem)
+      {
+        const unsigned ch = __shfl_sync(FULL, ahead, 0);
+        if (need && rank < rem)
+          {
+            got = true;
+            *q = base + next + rank;
+          }
+        if (ch < n_chunks)
+          {
+            if (lane == 0) ahead = dynamic ? atomicAdd(work, 1u) : ch + n_warps;
+            base = ch * chunk;
+            total = (unsigned) (nq - (size_t) base < (size_t) chunk ? nq - (size_t) base : (size_t) chunk);
+            const unsigned want = cnt - rem;
+            if (need && rank >= rem && rank - rem < total)
+              {
+                got = true;
+                *q = base + (rank - rem);
+              }
+            next = want < total ? want : total;
+          }
+        else
+          {
+            dry = true;
+            next = total;
+          }
+      }
+    else
+      {
+        if (need)
+          {
+            got = true;
+            *q = base + next + rank;
+          }
+        next += cnt;
+      }
+    return got;
+  }
+};
+
+/* gsi_seed_of with the cell computed by one fused multiply-add per axis and an integer clamp (the cell
+ * is a hint: any leaf slot is a correct start of the walk; NaN converts to 0, +-inf saturate) */
+struct gsi_cell_map
+{
+  double ax, bx, ay, by;
+};
+
+__device__ __forceinline__ int
+gsi_seed_of_fast(const gsi_view &V, const gsi_cell_map &C, double qx, double qy)
+{
+  const int ix = min(max(__double2int_rd(__fma_rn(qx, C.ax, C.bx)), 0), V.grid_g - 1);
+  const int iy = min(max(__double2int_rd(__fma_rn(qy, C.ay, C.by)), 0), V.grid_g - 1);
+  const unsigned cell = (unsigned) iy * (unsigned) V.grid_g + (unsigned) ix;
+  const unsigned off = __ldg(V.seed16 + cell);
+  const int base = __ldg(V.seedbase + (unsigned) (iy >> 3) * (unsigned) V.grid_gb + (unsigned) (ix >> 3));
+  if (off != GSI_SEED16_ESC) return base + (int) off;
+  return gsi_ld_seed(V.seeds + cell);
+}
+
+__device__ __forceinline__ void
+gsi_lds128(unsigned addr, unsigned long long &a, unsigned long long &b)
+{
+  asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
+template <class SRC, bool STATS, bool ONE_FIELD>
+__global__ void __launch_bounds__(GSI_WALK_THREADS, 8)
+k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
+        size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
+        int max_steps, int dynamic, unsigned long long *trace)
+{
+  __shared__ __align__(16) unsigned char stage_all[(GSI_WALK_THREADS / 32) * 32 * GSI_WALKC_PITCH];
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned stage = (unsigned) __cvta_generic_to_shared(stage_all) + (threadIdx.x >> 5) * (32u * GSI_WALKC_PITCH);
+  unsigned long long steps_acc = 0, t_start = 0;
+  unsigned handed = 0;
+  if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  gsi_warp_queue Q;
+  Q.init(nq, chunk, counters + GSI_CNT_WORK, dynamic, lane);
+
+  bool cur_v = false, nxt_v = false, nn_v = false;
+  unsigned cur_q = 0, nxt_q = 0, nn_q = 0;
+  double cur_x = 0, cur_y = 0, nxt_x = 0, nxt_y = 0, nn_x = 0, nn_y = 0;
+  int cur_slot = 0, nxt_seed = 0, cur_steps = 0;
+  for (;;)
+    {
+      /* refill: promote nxt -> cur, nn -> nxt (issue its seed load), take a new nn */
+      const bool need = !cur_v;
+      if (need)
+        {
+          cur_v = nxt_v; cur_q = nxt_q; cur_x = nxt_x; cur_y = nxt_y;
+          cur_slot = nxt_seed; cur_steps = 0;
+          nxt_v = nn_v; nxt_q = nn_q; nxt_x = nn_x; nxt_y = nn_y;
+          /* a non-finite query gets slot -1: nothing is staged for it and it is deferred below */
+          if (nxt_v) nxt_seed = (isfinite(nxt_x) && isfinite(nxt_y)) ? gsi_seed_of_fast(V, C, nxt_x, nxt_y) : -1;
+          nn_v = false;
+        }
+      {
+        unsigned q = 0;
+        const bool got = Q.take(need, lane, lt_mask, &q);
+        if (got)
+          {
+            nn_v = true;
+            nn_q = q;
+            src.get_linear((size_t) q, nn_x, nn_y);
+          }
+        if (trace) handed += (unsigned) __popc(__ballot_sync(FULL, got));
+      }
+      if (!__any_sync(FULL, cur_v || nxt_v || nn_v)) break;
+
+      /* the warp copies the records its lanes are about to visit: lanes 8j .. 8j+7 move record j of
+         each group of four as 16-byte pieces of one line (the last piece is padding) */
+      const bool live = cur_v && cur_slot >= 0;
+      const int my = live ? cur_slot : -1;
+      __syncwarp(); /* last iteration's reads of the staging area are done */
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        {
+          const unsigned qq = 4u * (unsigned) r + (lane >> 3);
+          const int sl = __shfl_sync(FULL, my, (int) qq);
+          if (sl >= 0 && (lane & 7u) != 7u)
+            {
+              const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
+              const unsigned d = stage + qq * GSI_WALKC_PITCH + (lane & 7u) * 16u;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+            }
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+
+      bool defer = false;
+      if (cur_v)
+        {
+          if (!live)
+            defer = true;
+          else
+            {
+              const unsigned mine = stage + lane * GSI_WALKC_PITCH;
+              unsigned long long a, b;
+              gsi_rec r;
+              gsi_lds128(mine, a, b);
+              r.x0x = __longlong_as_double((long long) a); r.x0y = __longlong_as_double((long long) b);
+              gsi_lds128(mine + 16, a, b);
+              r.u00 = __longlong_as_double((long long) a); r.u01 = __longlong_as_double((long long) b);
+              gsi_lds128(mine + 32, a, b);
+              r.u11 = __longlong_as_double((long long) a); r.l10 = __longlong_as_double((long long) b);
+              gsi_lds128(mine + 48, a, b);
+              r.lnk[0] = (int32_t) (unsigned) a; r.lnk[1] = (int32_t) (unsigned) (a >> 32);
+              r.lnk[2] = (int32_t) (unsigned) b; r.meta = (uint32_t) (b >> 32);
+              gsi_lds128(mine + 96, a, b);
+              const double r11 = __longlong_as_double((long long) a), r00 = __longlong_as_double((long long) b);
+              double c0, c1;
+              const int st = gsi_walk_step_rcp(&V.xf, &r, r11, r00, cur_x, cur_y, &cur_slot, &c0, &c1);
+              ++cur_steps;
+              if (st == GSI_STEP_ACCEPT)
+                {
+                  gsi_leaf_tail t;
+                  gsi_lds128(mine + 64, a, b);
+                  t.s.node = (int32_t) (unsigned) a; t.s.vflags = (uint32_t) (a >> 32);
+                  t.s.z[0] = __longlong_as_double((long long) b);
+                  gsi_lds128(mine + 80, a, b);
+                  t.s.z[1] = __longlong_as_double((long long) a); t.s.z[2] = __longlong_as_double((long long) b);
+                  const size_t q = cur_q;
+                  if (leaf_out) GSI_ST_RESULT(leaf_out + q, t.g.node);
+                  if (val)
+                    {
+                      if (ONE_FIELD)
+                        GSI_ST_RESULT(val + q, gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0],
+                                           (int) (t.s.vflags & 2u), t.s.z[1],
+                                           (int) (t.s.vflags & 4u), t.s.z[2]));
+                      else
+                        gsi_blend_store(&V, &t, c0, c1, val, ld, q);
+                    }
+                  if (STATS) steps_acc += (unsigned) cur_steps;
+                  cur_v = false;
+                }
+              else if (st == GSI_STEP_DEFER || cur_steps >= max_steps)
+                defer = true;
+            }
+          if (defer) cur_v = false;
+        }
+      /* warp-aggregated append to the deferred list */
+      const unsigned dm = __ballot_sync(FULL, defer);
+      if (dm)
+        {
+          const int leader = __ffs(dm) - 1;
+          unsigned pos = 0;
+          if (lane == (unsigned) leader)
+            pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+          pos = __shfl_sync(FULL, pos, leader);
+          if (defer)
+            {
+              const unsigned at = pos + __popc(dm & lt_mask);
+              if (at < list_cap)
+                list[at] = cur_q;
+              else
+                mark_overflow(ovf_mask, (size_t) cur_q, counters);
+            }
+        }
+    }
+  if (STATS && steps_acc)
+    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
+  if (trace)
+    {
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          unsigned long long t_end;
+          unsigned smid;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          trace[4 * (size_t) blockIdx.x + 0] = smid;
+          trace[4 * (size_t) blockIdx.x + 1] = t_start;
+          trace[4 * (size_t) blockIdx.x + 2] = t_end;
+        }
+      if (lane == 0) atomicAdd(trace + 4 * (size_t) blockIdx.x + 3, (unsigned long long) handed);
+    }
+}
+
+/* reciprocals of the two divisors of every 128-byte leaf record, into the record's padding */
+__global__ void __launch_bounds__(256)
+k_leaf_rcp(const gsi_view V, char *leaf_base)
+{
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t s = (size_t) blockIdx.x * blockDim.x + threadIdx.x; s < (size_t) V.n_leaves; s += stride)
+    {
+      const gsi_rec *r = reinterpret_cast<const gsi_rec *>(leaf_base + s * 128u);
+      double *pad = reinterpret_cast<double *>(leaf_base + s * 128u + 96u);
+      const double u11 = r->u11, u00 = r->u00;
+      pad[0] = gsi_div_rcp_usable(u11) ? gsi_div_rcp(u11) : CUDART_NAN;
+      pad[1] = gsi_div_rcp_usable(u00) ? gsi_div_rcp(u00) : CUDART_NAN;
+    }
+}
+
 /* ---- reorder pipeline: k_bin -> k_tile_walk -> k_unpermute -----------------------------------
  * Uniformly random queries make every leaf fetch an isolated L2/DRAM line fill: at 10^6 nodes the
  * direct walk moves ~220 bytes per query through HBM for 28 algorithmic bytes.  The pipeline
@@ -1904,13 +2180,38 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
       const int g = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas
                                ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
                                : (size_t) ctas);
-      if (cfg.walk_variant)
+      if (cfg.walk_variant == 2 && V.leaf_stride == 128)
         {
-          if (cfg.walk_trace) cudaMemsetAsync(cfg.walk_trace, 0, (size_t) ctas * 4 * sizeof(unsigned long long), st);
+          const int ctas_c = cfg.sm_count * (cfg.walk_ctas_per_sm > 5 ? cfg.walk_ctas_per_sm : 8);
+          const int gc = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas_c
+                                    ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
+                                    : (size_t) ctas_c);
+          unsigned long long *trace = (size_t) gc <= cfg.walk_trace_ctas ? cfg.walk_trace : nullptr;
+          if (trace) cudaMemsetAsync(trace, 0, cfg.walk_trace_ctas * 4 * sizeof(unsigned long long), st);
+          gsi_cell_map CM;
+          CM.ax = V.xf.sx * V.inv_du;
+          CM.bx = (-V.xf.cx * V.xf.sx - V.u0) * V.inv_du;
+          CM.ay = V.xf.sy * V.inv_dv;
+          CM.by = (-V.xf.cy * V.xf.sy - V.v0) * V.inv_dv;
+#define GSI_LAUNCH_WALKC(STATS, ONE)                                                            \
+  k_walkc<SRC, STATS, ONE><<<gc, GSI_WALK_THREADS, 0, st>>>(V, CM, src, nq, (unsigned) chunk, val, leaf_out, \
+                                                            ld, cfg.list, list_cap, cfg.ovf_mask,      \
+                                                            cfg.counters, cfg.max_steps, cfg.walk_dynamic, \
+                                                            trace)
+          if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKC(true, true);
+          else if (cfg.stats) GSI_LAUNCH_WALKC(true, false);
+          else if (V.n_fields == 1) GSI_LAUNCH_WALKC(false, true);
+          else GSI_LAUNCH_WALKC(false, false);
+#undef GSI_LAUNCH_WALKC
+        }
+      else if (cfg.walk_variant == 1)
+        {
+          unsigned long long *trace = (size_t) g <= cfg.walk_trace_ctas ? cfg.walk_trace : nullptr;
+          if (trace) cudaMemsetAsync(trace, 0, cfg.walk_trace_ctas * 4 * sizeof(unsigned long long), st);
 #define GSI_LAUNCH_WALKP(STATS, ONE)                                                            \
   k_walkp<SRC, STATS, ONE><<<g, GSI_WALK_THREADS, 0, st>>>(V, src, nq, (unsigned) chunk, val, leaf_out, \
                                                            ld, cfg.list, list_cap, cfg.ovf_mask,      \
-                                                           cfg.counters, cfg.max_steps, cfg.walk_dynamic, cfg.walk_pf, cfg.walk_trace)
+                                                           cfg.counters, cfg.max_steps, cfg.walk_dynamic, cfg.walk_pf, trace)
           if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKP(true, true);
           else if (cfg.stats) GSI_LAUNCH_WALKP(true, false);
           else if (V.n_fields == 1) GSI_LAUNCH_WALKP(false, true);
@@ -2052,6 +2353,14 @@ gsi_launch_deriv(const gsi_view &V, const int *leaf, size_t nq, double *dzdx, do
 {
   if (nq == 0) return cudaSuccess;
   k_deriv<<<grid_for(nq, 256, sm_count, 8), 256, 0, st>>>(V, leaf, nq, dzdx, dzdy, ld);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_leaf_rcp(const gsi_view &V, char *leaf_base, int sm_count, cudaStream_t st)
+{
+  if (V.leaf_stride != 128 || V.n_leaves <= 0) return cudaSuccess;
+  k_leaf_rcp<<<grid_for((size_t) V.n_leaves, 256, sm_count, 8), 256, 0, st>>>(V, leaf_base);
   return cudaGetLastError();
 }
 

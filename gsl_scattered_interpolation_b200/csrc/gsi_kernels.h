@@ -65,10 +65,12 @@ struct gsi_launch_cfg
   int walk_ctas_per_sm = 5;
   int exact_coop = 1; /* deferred list: four lanes per query (k_exact_list4) instead of one thread (k_exact_list) */
   size_t walk_chunk = 0; /* 0 = derive from the launch size */
-  int walk_variant = 0;  /* 1 = k_walkp (two walks per lane in rotation behind L2 prefetches), 0 = k_walk */
+  int walk_variant = 2;  /* 0 = k_walk, 1 = k_walkp (two walks per lane in rotation behind L2 prefetches),
+                            2 = k_walkc (warp-cooperative cp.async staging; needs 128-byte leaf records) */
   int walk_dynamic = 1;  /* k_walkp: chunks dealt by a device counter (0: round-robin) */
   int walk_pf = 1;       /* k_walkp: how the next leaf line is requested ahead (gsi_prefetch_leaf_l2) */
-  unsigned long long *walk_trace = nullptr; /* k_walkp: 4 words per CTA {smid, start ns, end ns, queries}, zeroed here */
+  unsigned long long *walk_trace = nullptr; /* k_walkp / k_walkc: 4 words per CTA {smid, start ns, end ns, queries}, zeroed here */
+  size_t walk_trace_ctas = 0;               /* CTAs the trace buffer has room for */
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
   size_t list_capacity = 0;     /* deferred-list entries; overflow goes to the bitmask */
   unsigned *ovf_mask = nullptr; /* one bit per query of a launch (zero between launches) */
@@ -113,6 +115,10 @@ cudaError_t gsi_launch_validate_slab(const gsi_view &V, unsigned long long *bad,
 /* hoisted-reciprocal division against __ddiv_rn on n operand pairs: out2[0] = pairs vouched for,
  * out2[1] = mismatches among them (device memory) */
 cudaError_t gsi_launch_selftest_division(uint64_t seed, size_t n, unsigned long long *out2, int sm_count, cudaStream_t st);
+
+/* slabs with 128-byte leaf records: fill the reciprocals of each record's two divisors into its padding
+ * (bytes 96..111), which k_walkc divides with; no-op for 96-byte records */
+cudaError_t gsi_launch_leaf_rcp(const gsi_view &V, char *leaf_base, int sm_count, cudaStream_t st);
 
 /* batched locate of the builder's points [first, first + count) on a snapshot of the growing tree
  * (device arrays as in gsi_host_tree + the LU records); outputs are device arrays of `count` */

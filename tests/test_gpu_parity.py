@@ -185,7 +185,10 @@ def test_sixteen_fields_raster_vs_port():
 
 @pytest.mark.parametrize("kernel,extra", [(0, {}), (1, {}), (0, {"walk_variant": 0}), (0, {"walk_dynamic": 0}),
                                           (0, {"walk_pf": 0}), (0, {"walk_pf": 2}), (0, {"walk_pf": 3}),
-                                          (0, {"walk_pf": 4}), (0, {"walk_chunk": 32}), (0, {"walk_ctas_per_sm": 1})])
+                                          (0, {"walk_pf": 4}), (0, {"walk_chunk": 32}), (0, {"walk_ctas_per_sm": 1}),
+                                          (0, {"walk_variant": 0, "leaf_stride": 96}), (0, {"walk_variant": 2, "leaf_stride": 96}),
+                                          (0, {"walk_variant": 2, "walk_dynamic": 0, "walk_chunk": 64}),
+                                          (0, {"walk_variant": 1, "walk_chunk": 64})])
 def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel, extra):
     """the walk kernels (0: k_walkp by default, k_walk with walk_variant = 0, every way of dealing chunks
     and of requesting leaf lines ahead) and k_locate (1) on config 1 (1 field) and the config-3 mix (3 fields)"""
@@ -630,6 +633,7 @@ def test_walk_trace_diagnostic(golden):
     xq, yq = synth.uniform_queries(nq)
     w.eval_e(xq, yq)
     tr = w.walk_trace(0)
+    tr = tr[tr[:, 2] > 0]                               # CTAs of the launch
     assert tr.shape[0] > 0 and int(tr[:, 3].sum()) == nq
     assert (tr[:, 2] >= tr[:, 1]).all() and (tr[:, 0] < 200).all()
     w.free()

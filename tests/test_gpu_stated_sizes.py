@@ -222,6 +222,7 @@ def test_million_nodes_uniform_queries_direct_and_reordered(million):
     del zf
     # one field, same tree, through the reorder pipeline (auto: 5*10^7 queries, 2*10^6 leaves)
     w1 = g.ScatteredCuda(n, 1)
+    w1.set_param("reorder", 2)
     w1.init_from_tree(tree["pts3"], tree["lnk3"], tree["type"], tree["shuffle"], tree["shift"], tree["scale"],
                       tree["seed_points"], np.stack([xa, ya], axis=1), za[:1])
     z1, l1 = _device_fast_vs_exact(w1, dx, dy, nq, 1)
