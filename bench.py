@@ -86,55 +86,97 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM / memory clocks, power and throttle reasons of one GPU sampled DURING the timed region.
+
+    The sampler is started once, before the warm-up steps, and keeps sampling; window() returns the
+    summary of the samples taken between two time stamps.  (Starting an nvidia-smi process right
+    before the timed region, as an earlier version did, stalls the first kernel launch of the region
+    by tens of milliseconds on multi-GPU boxes while NVML enumerates the devices: the GPU idles and
+    the step looks 35-60 % slower on whichever ranks lose that race -- profiles/r2n2b_*.)
+    In-process NVML (pynvml) when available, else one long-lived `nvidia-smi -lms` child."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks.mem,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
-
-    def start(self):
+    def __init__(self, index, period=0.025):
+        self.index, self.period = index, period
+        self.samples = []                       # (t, sm, sm_max, power_w, mem, [reasons])
+        self.stop_flag = threading.Event()
+        self.proc = None
+        self.kind = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.kind = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                     str(int(1e3 * period)), "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                    text=True)
+                self.kind = "nvidia-smi"
+                self.t = threading.Thread(target=self._read_smi, daemon=True)
+                self.t.start()
+            except Exception:
+                self.kind = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mem = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                r = int(reasons_fn(self.h))
+                self.samples.append((time.perf_counter(), sm, self.sm_max, pw, mem, [n for n, b in bits if r & b]))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power, mem = [], [], set(), [], []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            c = [x.strip() for x in ln.split(",")]
+            c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3])); mem.append(float(c[4]))
+                self.samples.append((time.perf_counter(), float(c[1]), float(c[2]), float(c[3]), float(c[4]),
+                                     [n for n, v in zip(self.NAMES, c[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "power_w_max": float(max(power)) if power else None,
-                "mem_mhz": float(np.median(mem)) if mem else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+    def window(self, t0, t1):
+        if self.kind is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        rows = [x for x in list(self.samples) if t0 <= x[0] <= t1]
+        if not rows:                            # a region shorter than the period: the nearest sample
+            rows = sorted(list(self.samples), key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:1]
+        reasons = sorted({n for x in rows for n in x[5]})
+        return {"sm_mhz": float(np.median([x[1] for x in rows])) if rows else None,
+                "sm_max_mhz": float(max(x[2] for x in rows)) if rows else None,
+                "power_w_max": float(max(x[3] for x in rows)) if rows else None,
+                "mem_mhz": float(np.median([x[4] for x in rows])) if rows else None,
+                "samples": len(rows), "reasons": reasons, "source": self.kind}
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
 
 
 def bind_near_gpu(local):
@@ -450,6 +492,8 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)                  # started long before anything is timed
+
     def timed_region(nq, steps, warmup, sample_clocks):
         """`steps` passes over the first nq queries of this rank's arrays: (max-over-ranks ms of the
         region, per-rank ms per step, clocks); every pass is one eval_device_e call"""
@@ -459,18 +503,18 @@ def main_ours(args):
             step()
         barrier()
         w.reset_counters()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start()                  # every rank samples its own GPU
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(steps):
             step()
         e1.record(stream)
+        stream.synchronize()
+        t1 = time.perf_counter()
         barrier()
         ms_mine = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.window(t0, t1) if sample_clocks else None   # every rank samples its own GPU
         return dist_util.max_over_ranks(ms_mine, dev), dist_util.gather_over_ranks(ms_mine / steps, dev), clocks
 
     ms_total, ms_by_rank, clocks = timed_region(Q, args.steps, args.warmup, True)
@@ -529,6 +573,8 @@ def main_ours(args):
         ms_s, ms_s_by_rank, _ = timed_region(s1 - s0, args.steps, max(1, args.warmup), False)
         strong = {"scaling": "strong", "queries_total_per_step": Q, "value": Q * args.steps / (ms_s * 1e-3),
                   "unit": "queries/s", "ms_per_step": ms_s / args.steps, "ms_per_step_by_rank": ms_s_by_rank}
+
+    sampler.stop()
 
     # --- e2e: the same metric through the host-buffer C-ABI call (H2D of the inputs and D2H of leaf
     #     ids + values inside the timed region), from pinned host memory and from pageable (malloc'd)

@@ -188,6 +188,7 @@ def test_sixteen_fields_raster_vs_port():
                                           (0, {"walk_pf": 4}), (0, {"walk_chunk": 32}), (0, {"walk_ctas_per_sm": 1}),
                                           (0, {"walk_variant": 0, "leaf_stride": 96}), (0, {"walk_variant": 2, "leaf_stride": 96}),
                                           (0, {"walk_variant": 2, "walk_dynamic": 0, "walk_chunk": 64}),
+                                          (0, {"walk_variant": 3}), (0, {"walk_variant": 3, "walk_dynamic": 0, "walk_chunk": 32}),
                                           (0, {"walk_variant": 1, "walk_chunk": 64})])
 def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel, extra):
     """the walk kernels (0: k_walkp by default, k_walk with walk_variant = 0, every way of dealing chunks
