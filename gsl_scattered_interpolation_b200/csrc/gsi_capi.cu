@@ -1306,7 +1306,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
   else if (k == "build_device" && (value == 0 || value == 1)) w->build_device = (int) value;
   else if (k == "exact_coop" && (value == 0 || value == 1)) w->exact_coop = (int) value;
-  else if (k == "walk_variant" && value >= 0 && value <= 3) w->walk_variant = (int) value;
+  else if (k == "walk_variant" && value >= 0 && value <= 2) w->walk_variant = (int) value;
   else if (k == "walk_dynamic" && (value == 0 || value == 1)) w->walk_dynamic = (int) value;
   else if (k == "walk_pf" && value >= 0 && value <= 4) w->walk_pf = (int) value;
   else if (k == "walk_trace" && (value == 0 || value == 1)) w->walk_trace = (int) value;

@@ -859,6 +859,9 @@ k_walkp(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val,
  * cannot vouch for defers the query).  With the record in shared memory the kernel fits 64
  * registers: 8 CTAs = 32 warps per SM.  Queue as in k_walkp (continuous, chunks from a counter). */
 #define GSI_WALKC_PITCH 144
+#ifndef GSI_WALKC_CP
+#define GSI_WALKC_CP "cg" /* L2 only: the staged lines are not read through L1 again */
+#endif
 
 struct gsi_warp_queue
 {
@@ -1025,7 +1028,7 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
             {
               const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
               const unsigned d = stage + qq * GSI_WALKC_PITCH + (lane & 7u) * 16u;
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+              asm volatile("cp.async." GSI_WALKC_CP ".shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
             }
         }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1102,188 +1105,6 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
             }
         }
     }
-  if (STATS && steps_acc)
-    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
-  if (trace)
-    {
-      __syncthreads();
-      if (threadIdx.x == 0)
-        {
-          unsigned long long t_end;
-          unsigned smid;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-          trace[4 * (size_t) blockIdx.x + 0] = smid;
-          trace[4 * (size_t) blockIdx.x + 1] = t_start;
-          trace[4 * (size_t) blockIdx.x + 2] = t_end;
-        }
-      if (lane == 0) atomicAdd(trace + 4 * (size_t) blockIdx.x + 3, (unsigned long long) handed);
-    }
-}
-
-/* ---- k_walkc with two sets of walks per lane (walk_variant = 3) ---------------------------------
- * k_walkc waits for its cp.async copies right after issuing them: a third of its warp time.  Here
- * every lane carries two walks, A and B, each with a staging buffer of its own: a half-iteration
- * steps the walks of one set out of its buffer, refills the finished ones, issues the copies of the
- * records that set needs NEXT and turns to the other set, whose copies were issued a
- * half-iteration ago (cp.async.wait_group 1: everything but the newest group has landed).  The
- * HBM latency of one set overlaps the arithmetic of the other.  112-byte pitch (still conflict
- * free), 7 CTAs per SM. */
-#define GSI_WALKC2_PITCH 112
-
-struct gsi_walk_set
-{
-  bool v = false;
-  unsigned q = 0;
-  double x = 0, y = 0;
-  int slot = 0, steps = 0;
-};
-
-template <class SRC, bool STATS, bool ONE_FIELD>
-__global__ void __launch_bounds__(GSI_WALK_THREADS, 7)
-k_walkc2(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
-         size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
-         int max_steps, int dynamic, unsigned long long *trace)
-{
-  __shared__ __align__(16) unsigned char stage_all[(GSI_WALK_THREADS / 32) * 2 * 32 * GSI_WALKC2_PITCH];
-  const unsigned FULL = 0xffffffffu;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned stage = (unsigned) __cvta_generic_to_shared(stage_all) + (threadIdx.x >> 5) * (2u * 32u * GSI_WALKC2_PITCH);
-  unsigned long long steps_acc = 0, t_start = 0;
-  unsigned handed = 0;
-  if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-  gsi_warp_queue Q;
-  Q.init(nq, chunk, counters + GSI_CNT_WORK, dynamic, lane);
-
-  gsi_walk_set A, B;
-  bool nxt_v = false, nn_v = false;
-  unsigned nxt_q = 0, nn_q = 0;
-  double nxt_x = 0, nxt_y = 0, nn_x = 0, nn_y = 0;
-  int nxt_base = 0;
-  unsigned nxt_off = 0;
-
-  auto half = [&](gsi_walk_set &S, const unsigned buf) {
-    /* this set's records were requested a half-iteration ago */
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    bool defer = false;
-    if (S.v)
-      {
-        if (S.slot < 0)
-          defer = true;
-        else
-          {
-            const unsigned mine = buf + lane * GSI_WALKC2_PITCH;
-            unsigned long long a, b;
-            gsi_rec r;
-            gsi_lds128(mine, a, b);
-            r.x0x = __longlong_as_double((long long) a); r.x0y = __longlong_as_double((long long) b);
-            gsi_lds128(mine + 16, a, b);
-            r.u00 = __longlong_as_double((long long) a); r.u01 = __longlong_as_double((long long) b);
-            gsi_lds128(mine + 32, a, b);
-            r.u11 = __longlong_as_double((long long) a); r.l10 = __longlong_as_double((long long) b);
-            gsi_lds128(mine + 48, a, b);
-            r.lnk[0] = (int32_t) (unsigned) a; r.lnk[1] = (int32_t) (unsigned) (a >> 32);
-            r.lnk[2] = (int32_t) (unsigned) b; r.meta = (uint32_t) (b >> 32);
-            gsi_lds128(mine + 96, a, b);
-            const double r11 = __longlong_as_double((long long) a), r00 = __longlong_as_double((long long) b);
-            double c0, c1;
-            const int st = gsi_walk_step_rcp(&V.xf, &r, r11, r00, S.x, S.y, &S.slot, &c0, &c1);
-            ++S.steps;
-            if (st == GSI_STEP_ACCEPT)
-              {
-                gsi_leaf_tail t;
-                gsi_lds128(mine + 64, a, b);
-                t.s.node = (int32_t) (unsigned) a; t.s.vflags = (uint32_t) (a >> 32);
-                t.s.z[0] = __longlong_as_double((long long) b);
-                gsi_lds128(mine + 80, a, b);
-                t.s.z[1] = __longlong_as_double((long long) a); t.s.z[2] = __longlong_as_double((long long) b);
-                const size_t q = S.q;
-                if (leaf_out) GSI_ST_RESULT(leaf_out + q, t.g.node);
-                if (val)
-                  {
-                    if (ONE_FIELD)
-                      GSI_ST_RESULT(val + q, gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0],
-                                         (int) (t.s.vflags & 2u), t.s.z[1],
-                                         (int) (t.s.vflags & 4u), t.s.z[2]));
-                    else
-                      gsi_blend_store(&V, &t, c0, c1, val, ld, q);
-                  }
-                if (STATS) steps_acc += (unsigned) S.steps;
-                S.v = false;
-              }
-            else if (st == GSI_STEP_DEFER || S.steps >= max_steps)
-              defer = true;
-          }
-        if (defer) S.v = false;
-      }
-    const unsigned dm = __ballot_sync(FULL, defer);
-    if (dm)
-      {
-        const int leader = __ffs(dm) - 1;
-        unsigned pos = 0;
-        if (lane == (unsigned) leader)
-          pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
-        pos = __shfl_sync(FULL, pos, leader);
-        if (defer)
-          {
-            const unsigned at = pos + __popc(dm & lt_mask);
-            if (at < list_cap)
-              list[at] = S.q;
-            else
-              mark_overflow(ovf_mask, (size_t) S.q, counters);
-          }
-      }
-    /* refill the finished walks of this set from the feeder stages */
-    const bool need = !S.v;
-    if (need)
-      {
-        S.v = nxt_v; S.q = nxt_q; S.x = nxt_x; S.y = nxt_y;
-        S.steps = 0;
-        if (S.v) S.slot = gsi_seed_resolve(V, C, S.x, S.y, nxt_off, nxt_base);
-        nxt_v = nn_v; nxt_q = nn_q; nxt_x = nn_x; nxt_y = nn_y;
-        nxt_off = 0;
-        nxt_base = -1;
-        if (nxt_v && isfinite(nxt_x) && isfinite(nxt_y)) gsi_seed_issue(V, C, nxt_x, nxt_y, &nxt_off, &nxt_base);
-        nn_v = false;
-      }
-    {
-      unsigned q = 0;
-      const bool got = Q.take(need, lane, lt_mask, &q);
-      if (got)
-        {
-          nn_v = true;
-          nn_q = q;
-          src.get_linear((size_t) q, nn_x, nn_y);
-        }
-      if (trace) handed += (unsigned) __popc(__ballot_sync(FULL, got));
-    }
-    /* request the records this set reads in its next half-iteration */
-    const int my = (S.v && S.slot >= 0) ? S.slot : -1;
-    __syncwarp(); /* every lane has read its record of this buffer */
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-      {
-        const unsigned qq = 4u * (unsigned) r + (lane >> 3);
-        const int sl = __shfl_sync(FULL, my, (int) qq);
-        if (sl >= 0 && (lane & 7u) != 7u)
-          {
-            const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
-            const unsigned d = buf + qq * GSI_WALKC2_PITCH + (lane & 7u) * 16u;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-          }
-      }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  for (;;)
-    {
-      half(A, stage);
-      half(B, stage + 32u * GSI_WALKC2_PITCH);
-      if (!__any_sync(FULL, A.v || B.v || nxt_v || nn_v)) break;
-    }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (STATS && steps_acc)
     atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
   if (trace)
@@ -2376,9 +2197,9 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
       const int g = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas
                                ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
                                : (size_t) ctas);
-      if ((cfg.walk_variant == 2 || cfg.walk_variant == 3) && V.leaf_stride == 128)
+      if (cfg.walk_variant == 2 && V.leaf_stride == 128)
         {
-          const int ctas_c = cfg.sm_count * (cfg.walk_ctas_per_sm > 5 ? cfg.walk_ctas_per_sm : (cfg.walk_variant == 3 ? 7 : 8));
+          const int ctas_c = cfg.sm_count * (cfg.walk_ctas_per_sm > 5 ? cfg.walk_ctas_per_sm : 8);
           const int gc = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas_c
                                     ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
                                     : (size_t) ctas_c);
@@ -2394,24 +2215,11 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
                                                             ld, cfg.list, list_cap, cfg.ovf_mask,      \
                                                             cfg.counters, cfg.max_steps, cfg.walk_dynamic, \
                                                             trace)
-#define GSI_LAUNCH_WALKC2(STATS, ONE)                                                           \
-  k_walkc2<SRC, STATS, ONE><<<gc, GSI_WALK_THREADS, 0, st>>>(V, CM, src, nq, (unsigned) chunk, val, leaf_out, \
-                                                             ld, cfg.list, list_cap, cfg.ovf_mask,      \
-                                                             cfg.counters, cfg.max_steps, cfg.walk_dynamic, \
-                                                             trace)
-          if (cfg.walk_variant == 3)
-            {
-              if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKC2(true, true);
-              else if (cfg.stats) GSI_LAUNCH_WALKC2(true, false);
-              else if (V.n_fields == 1) GSI_LAUNCH_WALKC2(false, true);
-              else GSI_LAUNCH_WALKC2(false, false);
-            }
-          else if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKC(true, true);
+          if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKC(true, true);
           else if (cfg.stats) GSI_LAUNCH_WALKC(true, false);
           else if (V.n_fields == 1) GSI_LAUNCH_WALKC(false, true);
           else GSI_LAUNCH_WALKC(false, false);
 #undef GSI_LAUNCH_WALKC
-#undef GSI_LAUNCH_WALKC2
         }
       else if (cfg.walk_variant == 1)
         {

@@ -188,7 +188,6 @@ def test_sixteen_fields_raster_vs_port():
                                           (0, {"walk_pf": 4}), (0, {"walk_chunk": 32}), (0, {"walk_ctas_per_sm": 1}),
                                           (0, {"walk_variant": 0, "leaf_stride": 96}), (0, {"walk_variant": 2, "leaf_stride": 96}),
                                           (0, {"walk_variant": 2, "walk_dynamic": 0, "walk_chunk": 64}),
-                                          (0, {"walk_variant": 3}), (0, {"walk_variant": 3, "walk_dynamic": 0, "walk_chunk": 32}),
                                           (0, {"walk_variant": 1, "walk_chunk": 64})])
 def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel, extra):
     """the walk kernels (0: k_walkp by default, k_walk with walk_variant = 0, every way of dealing chunks
@@ -310,15 +309,16 @@ def test_two_devices_if_present(golden):
 
 # ---- reorder pipeline (k_bin -> k_tile_locate -> k_unpermute) -------------------------------
 
+@pytest.mark.parametrize("stride", [96, 128])       # 96: the tile arrives by one TMA bulk copy; 128: by 128-bit loads
 @pytest.mark.parametrize("chunk,tile_leaves,threads", [(8192, 1000, 768), (8192, 3, 768), (4096, 40, 768), (96, 10, 768),
                                                        (1024, 100000, 768), (8192, 1000, 64), (96, 3, 32)])
-def test_reorder_pipeline_on_the_golden_sets(golden, chunk, tile_leaves, threads):
+def test_reorder_pipeline_on_the_golden_sets(golden, chunk, tile_leaves, threads, stride):
     """Forced reorder (param reorder=1) on config 1 and on the config-3 mix (3 fields, on-edge /
     on-vertex / outside-hull queries that are deferred to the exact replay): every chunk size, tile
     size (one tile for everything, tiles of a handful of leaves) and CTA shape of the tile kernel must give the reference's leaf ids and value bits."""
     xa, ya = synth.uniform_nodes(1000)
     w = make(xa, ya, synth.values(1000, 1), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, 1000),
-             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_threads=threads)
+             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_threads=threads, leaf_stride=stride)
     xq, yq = synth.uniform_queries(10000)
     st, zq, leaf = w.eval_e(xq, yq)
     assert st == g.SUCCESS
@@ -334,7 +334,7 @@ def test_reorder_pipeline_on_the_golden_sets(golden, chunk, tile_leaves, threads
     n = 3000
     xa, ya = synth.clustered_nodes(n)
     w = make(xa, ya, synth.values(n, 3), g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n),
-             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_threads=threads)
+             reorder=1, reorder_chunk=chunk, tile_leaves=tile_leaves, tile_threads=threads, leaf_stride=stride)
     xq, yq = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
     st, zq, leaf = w.eval_e(xq, yq)
     assert st == g.SUCCESS
