@@ -639,7 +639,7 @@ def main_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        variant = {0: "k_walk", 1: "k_walkp", 2: "k_walkc", 3: "k_walkc"}
+        variant = {0: "k_walk", 1: "k_walkp", 2: "k_walkc", 3: "k_walkf"}
         for kv in args.param:
             if kv.startswith("walk_variant="):
                 walk_variant = int(float(kv.split("=")[1]))

@@ -1153,7 +1153,9 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       || !extent_ok(h.off_seeds, cells, sizeof(int32_t), bytes) || !extent_ok(h.off_entry, cells, sizeof(int32_t), bytes)
       || !extent_ok(h.off_tiles, ((uint64_t) 1 << h.tile_bits) + 1, sizeof(int32_t), bytes)
       || !extent_ok(h.off_seed16, cells, sizeof(uint16_t), bytes)
-      || !extent_ok(h.off_seedbase, (((uint64_t) h.grid_g + 7) >> 3) * (((uint64_t) h.grid_g + 7) >> 3), sizeof(int32_t), bytes)
+      || h.seed_shift < 3 || h.seed_shift > 15 || gsi_seed_blocks(h.grid_g, h.seed_shift) > GSI_SEED_GB_MAX
+      || !extent_ok(h.off_seedbase, (uint64_t) gsi_seed_blocks(h.grid_g, h.seed_shift) * gsi_seed_blocks(h.grid_g, h.seed_shift),
+                    sizeof(int32_t), bytes)
       || (h.off_dag | h.off_leaf | h.off_z | h.off_seeds | h.off_entry | h.off_tiles | h.off_seed16 | h.off_seedbase) % 32 != 0
       || !(h.inv_du > 0) || !(h.inv_dv > 0) || !(h.delta > 0))
     GSI_ERROR("slab sections out of range", GSL_SCATTERED_EINVAL);
@@ -1306,7 +1308,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
   else if (k == "build_device" && (value == 0 || value == 1)) w->build_device = (int) value;
   else if (k == "exact_coop" && (value == 0 || value == 1)) w->exact_coop = (int) value;
-  else if (k == "walk_variant" && value >= 0 && value <= 2) w->walk_variant = (int) value;
+  else if (k == "walk_variant" && value >= 0 && value <= 3) w->walk_variant = (int) value;
   else if (k == "walk_dynamic" && (value == 0 || value == 1)) w->walk_dynamic = (int) value;
   else if (k == "walk_pf" && value >= 0 && value <= 4) w->walk_pf = (int) value;
   else if (k == "walk_trace" && (value == 0 || value == 1)) w->walk_trace = (int) value;

@@ -230,12 +230,12 @@ gsi_seed_of(const gsi_view *V, double qx, double qy)
   const size_t cell = (size_t) iy * (size_t) V->grid_g + (size_t) ix;
 #if defined(__CUDA_ARCH__)
   const unsigned off = __ldg(V->seed16 + cell);
-  const int base = __ldg(V->seedbase + (size_t) (iy >> 3) * (size_t) V->grid_gb + (size_t) (ix >> 3));
+  const int base = __ldg(V->seedbase + (size_t) (iy >> V->seed_shift) * (size_t) V->grid_gb + (size_t) (ix >> V->seed_shift));
   if (off != GSI_SEED16_ESC) return base + (int) off;
   return gsi_ld_seed(V->seeds + cell);
 #else
   const unsigned off = V->seed16[cell];
-  if (off != GSI_SEED16_ESC) return V->seedbase[(size_t) (iy >> 3) * (size_t) V->grid_gb + (size_t) (ix >> 3)] + (int) off;
+  if (off != GSI_SEED16_ESC) return V->seedbase[(size_t) (iy >> V->seed_shift) * (size_t) V->grid_gb + (size_t) (ix >> V->seed_shift)] + (int) off;
   return V->seeds[cell];
 #endif
 }

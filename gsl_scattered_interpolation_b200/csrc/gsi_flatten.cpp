@@ -135,7 +135,18 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
     {
       const double want = std::sqrt(std::max(1.0, prm.cells_per_leaf * (double) L));
       G = (uint32_t) std::min(16384.0, std::max(1.0, std::ceil(want)));
+      /* large grids: a multiple of eight seed blocks per side, so that the coarse Morton boundaries
+         (where neighbouring cells' seeds are more than 64K slots apart) fall between blocks */
+      if (G >= 256)
+        {
+          const uint32_t B = 1u << gsi_seed_shift_for(G);
+          uint32_t gb = ((G + 4 * B) / (8 * B)) * 8;
+          if (gb < 8) gb = 8;
+          if (gb > GSI_SEED_GB_MAX) gb = GSI_SEED_GB_MAX;
+          G = gb * B;
+        }
     }
+  const uint32_t seed_shift = gsi_seed_shift_for(G);
 
   /* --- sizes --------------------------------------------------------------------------- */
   gsi_slab_header h;
@@ -147,6 +158,7 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   h.n_dag = N;
   h.n_leaves = L;
   h.grid_g = G;
+  h.seed_shift = seed_shift;
   h.xf = xf;
   h.u0 = umin; h.v0 = vmin;
   h.inv_du = (double) G / du;
@@ -162,7 +174,7 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   h.off_entry = off; off = align256(off + (uint64_t) G * G * sizeof(int32_t));
   h.off_seed16 = off; off = align256(off + (uint64_t) G * G * sizeof(uint16_t));
   {
-    const uint64_t gb = ((uint64_t) G + 7) >> 3;
+    const uint64_t gb = gsi_seed_blocks(G, seed_shift);
     h.off_seedbase = off; off = align256(off + gb * gb * sizeof(int32_t));
   }
   /* Morton-prefix tiles of about tile_leaves leaves: P bits, 2 <= P <= 12 */

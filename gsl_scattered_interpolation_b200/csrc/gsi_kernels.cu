@@ -353,55 +353,42 @@ k_seed_cells(const gsi_view V, int32_t *seeds)
     }
 }
 
-/* compact seed table (gsi_layout.h): one thread per block of 8 x 8 cells takes the smallest seed
- * of the block as its base and stores every cell's 16-bit offset, 0xffff where it does not fit */
+/* compact seed table (gsi_layout.h): one WARP per block of B x B cells (B = 2^seed_shift).  The base
+ * of a block is the seed of its centre cell minus 32768, so the 16-bit window covers the block's own
+ * leaves and their neighbours in Morton order on both sides.  A cell whose seed (the leaf holding its
+ * centre) lies outside the window -- a leaf whose centroid falls into a block far away along the Morton
+ * curve, typically just across a coarse Morton boundary -- gets the in-window seed of the nearest cell of
+ * its row or column instead: the seed is only the START of the walk, which then needs a step or two
+ * more for the queries of that cell, and no query ever waits for a second, dependent table look-up.
+ * 0xffff (escape to the int32 table) remains for cells with no in-window seed in their row and column. */
 __global__ void __launch_bounds__(128)
 k_pack_seeds(const gsi_view V, const int32_t *seeds, uint16_t *seed16, int32_t *seedbase)
 {
-  const unsigned g = (unsigned) V.grid_g, gb = (unsigned) V.grid_gb;
+  const unsigned g = (unsigned) V.grid_g, gb = (unsigned) V.grid_gb, sh = (unsigned) V.seed_shift, B = 1u << sh;
+  const unsigned lane = threadIdx.x & 31u;
   const size_t nblk = (size_t) gb * gb;
-  const size_t stride = (size_t) gridDim.x * blockDim.x;
-  for (size_t b = (size_t) blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += stride)
+  const size_t wstride = ((size_t) gridDim.x * blockDim.x) >> 5;
+  for (size_t b = ((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nblk; b += wstride)
     {
       const unsigned by = (unsigned) (b / gb), bx = (unsigned) (b - (size_t) by * gb);
-      const unsigned x0 = bx << 3, y0 = by << 3, x1 = min(x0 + 8u, g), y1 = min(y0 + 8u, g);
-      /* base = the smallest seed that still lets most of the block fit: the minimum, unless the
-         block straddles a coarse Morton boundary; then the most common 64K-slot window wins */
-      int lo = 0x7fffffff;
-      for (unsigned y = y0; y < y1; y++)
-        for (unsigned x = x0; x < x1; x++) lo = min(lo, seeds[(size_t) y * g + x]);
-      int best = lo, best_n = -1;
-      for (int pass = 0; pass < 2; pass++)
+      const unsigned x0 = bx << sh, y0 = by << sh, x1 = min(x0 + B, g), y1 = min(y0 + B, g);
+      const unsigned w = x1 - x0, ncell = w * (y1 - y0);
+      const int base = max(seeds[(size_t) ((y0 + y1) >> 1) * g + ((x0 + x1) >> 1)] - 32768, 0);
+      if (lane == 0) seedbase[b] = base;
+      for (unsigned k = lane; k < ncell; k += 32)
         {
-          /* candidate bases: the minimum, and the smallest seed that is more than 64K above it */
-          int cand = lo;
-          if (pass == 1)
+          const unsigned y = y0 + k / w, x = x0 + k % w;
+          int d = seeds[(size_t) y * g + x] - base;
+          for (unsigned r = 1; !(d >= 0 && d < (int) GSI_SEED16_ESC) && r < B; r++)
             {
-              cand = 0x7fffffff;
-              for (unsigned y = y0; y < y1; y++)
-                for (unsigned x = x0; x < x1; x++)
-                  {
-                    const int s = seeds[(size_t) y * g + x];
-                    if (s - lo >= (int) GSI_SEED16_ESC) cand = min(cand, s);
-                  }
-              if (cand == 0x7fffffff) break;
+              int c;
+              if (x >= x0 + r && (c = seeds[(size_t) y * g + (x - r)] - base) >= 0 && c < (int) GSI_SEED16_ESC) d = c;
+              else if (x + r < x1 && (c = seeds[(size_t) y * g + (x + r)] - base) >= 0 && c < (int) GSI_SEED16_ESC) d = c;
+              else if (y >= y0 + r && (c = seeds[(size_t) (y - r) * g + x] - base) >= 0 && c < (int) GSI_SEED16_ESC) d = c;
+              else if (y + r < y1 && (c = seeds[(size_t) (y + r) * g + x] - base) >= 0 && c < (int) GSI_SEED16_ESC) d = c;
             }
-          int n = 0;
-          for (unsigned y = y0; y < y1; y++)
-            for (unsigned x = x0; x < x1; x++)
-              {
-                const int d = seeds[(size_t) y * g + x] - cand;
-                n += d >= 0 && d < (int) GSI_SEED16_ESC;
-              }
-          if (n > best_n) { best_n = n; best = cand; }
+          seed16[(size_t) y * g + x] = (d >= 0 && d < (int) GSI_SEED16_ESC) ? (uint16_t) d : (uint16_t) GSI_SEED16_ESC;
         }
-      seedbase[b] = best;
-      for (unsigned y = y0; y < y1; y++)
-        for (unsigned x = x0; x < x1; x++)
-          {
-            const int d = seeds[(size_t) y * g + x] - best;
-            seed16[(size_t) y * g + x] = (d >= 0 && d < (int) GSI_SEED16_ESC) ? (uint16_t) d : (uint16_t) GSI_SEED16_ESC;
-          }
     }
 }
 
@@ -935,22 +922,24 @@ struct gsi_cell_map
   double ax, bx, ay, by;
 };
 
-/* issue the two loads of the compact seed table for a query; nothing waits for them here */
+/* issue the load of a query's 16-bit seed offset (nothing waits for it here) and note its seed block */
 __device__ __forceinline__ void
-gsi_seed_issue(const gsi_view &V, const gsi_cell_map &C, double qx, double qy, unsigned *off, int *base)
+gsi_seed_issue(const gsi_view &V, const gsi_cell_map &C, double qx, double qy, unsigned *off, int *blk)
 {
   const int ix = min(max(__double2int_rd(__fma_rn(qx, C.ax, C.bx)), 0), V.grid_g - 1);
   const int iy = min(max(__double2int_rd(__fma_rn(qy, C.ay, C.by)), 0), V.grid_g - 1);
   const unsigned cell = (unsigned) iy * (unsigned) V.grid_g + (unsigned) ix;
   *off = __ldg(V.seed16 + cell);
-  *base = __ldg(V.seedbase + (unsigned) (iy >> 3) * (unsigned) V.grid_gb + (unsigned) (ix >> 3));
+  *blk = (int) ((unsigned) (iy >> V.seed_shift) * (unsigned) V.grid_gb + (unsigned) (ix >> V.seed_shift));
 }
 
-/* ... and turn them into the seed slot an iteration later (escaped cells: the int32 table) */
+/* ... and turn it into the seed slot an iteration later: block base from the copy of the base table in
+   shared memory (escaped cells, if any: the int32 table) */
 __device__ __forceinline__ int
-gsi_seed_resolve(const gsi_view &V, const gsi_cell_map &C, double qx, double qy, unsigned off, int base)
+gsi_seed_resolve(const gsi_view &V, const gsi_cell_map &C, const int *sbase, double qx, double qy, unsigned off, int blk)
 {
-  if (off != GSI_SEED16_ESC) return base + (int) off;
+  if (blk < 0) return -1; /* non-finite query: no seed, the caller defers it */
+  if (off != GSI_SEED16_ESC) return sbase[blk] + (int) off;
   const int ix = min(max(__double2int_rd(__fma_rn(qx, C.ax, C.bx)), 0), V.grid_g - 1);
   const int iy = min(max(__double2int_rd(__fma_rn(qy, C.ay, C.by)), 0), V.grid_g - 1);
   return gsi_ld_seed(V.seeds + ((unsigned) iy * (unsigned) V.grid_g + (unsigned) ix));
@@ -969,10 +958,16 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
         int max_steps, int dynamic, unsigned long long *trace)
 {
   __shared__ __align__(16) unsigned char stage_all[(GSI_WALK_THREADS / 32) * 32 * GSI_WALKC_PITCH];
+  __shared__ int sbase[GSI_SEED_GB_MAX * GSI_SEED_GB_MAX]; /* the seed-block bases: at most 4 KB */
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned stage = (unsigned) __cvta_generic_to_shared(stage_all) + (threadIdx.x >> 5) * (32u * GSI_WALKC_PITCH);
+  {
+    const unsigned nb = (unsigned) V.grid_gb * (unsigned) V.grid_gb;
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sbase[i] = __ldg(V.seedbase + i);
+  }
+  __syncthreads();
   unsigned long long steps_acc = 0, t_start = 0;
   unsigned handed = 0;
   if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -993,9 +988,9 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
         {
           cur_v = nxt_v; cur_q = nxt_q; cur_x = nxt_x; cur_y = nxt_y;
           cur_steps = 0;
-          if (cur_v) cur_slot = gsi_seed_resolve(V, C, cur_x, cur_y, nxt_off, nxt_base);
+          if (cur_v) cur_slot = gsi_seed_resolve(V, C, sbase, cur_x, cur_y, nxt_off, nxt_base);
           nxt_v = nn_v; nxt_q = nn_q; nxt_x = nn_x; nxt_y = nn_y;
-          /* a non-finite query gets slot -1: nothing is staged for it and it is deferred below */
+          /* a non-finite query gets block -1, hence slot -1: nothing is staged for it and it is deferred below */
           nxt_off = 0;
           nxt_base = -1;
           if (nxt_v && isfinite(nxt_x) && isfinite(nxt_y)) gsi_seed_issue(V, C, nxt_x, nxt_y, &nxt_off, &nxt_base);
@@ -1122,6 +1117,276 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
         }
       if (lane == 0) atomicAdd(trace + 4 * (size_t) blockIdx.x + 3, (unsigned long long) handed);
     }
+}
+
+/* ---- fast path, fresh batches + a ring of walkers (walk_variant = 3) ------------------------------
+ * k_walkc decouples lanes from queries with a warp-wide queue and pays for it on EVERY visit: about
+ * 15 warp instructions per query, two divergent seed-table gathers and scattered result stores, and it
+ * runs at the L1 wavefront rate (one divergent line = about two cycles of the SM's L1 pipe: 7.5
+ * cycles per query and SM whether the structure is L2-resident or not).  Three out of four queries
+ * are accepted by the first leaf they visit, so this kernel gives that visit a straight path:
+ *   - a warp takes 32 CONSECUTIVE queries (a batch): coalesced coordinate loads two batches ahead,
+ *     the 16-bit seed offsets one batch ahead, the block bases from a <= 4 KB table in SHARED memory
+ *     (one divergent global access per seed instead of two), the 32 seed leaves staged by the warp
+ *     (cp.async, as in k_walkc), one walk step per lane, results of the accepted lanes written to
+ *     consecutive addresses;
+ *   - a lane whose query has to move on pushes {x, y, query, next slot, steps} onto the warp's ring
+ *     in shared memory; whenever the ring holds 32 walkers (or no batch is left) the warp pops 32 of
+ *     them and gives them one visit with the same code.  Lanes stay full, no per-lane queue state.
+ * Deferred queries go to the same list as in the other kernels.  Needs 128-byte leaf records. */
+#define GSI_WALKF_PITCH 112 /* 7 x 16 bytes of a record; 28 words: conflict-free 128-bit reads */
+#define GSI_WALKF_RING 64
+#ifndef GSI_WALKF_STAGE
+#define GSI_WALKF_STAGE 0
+#endif
+#define GSI_WALKF_WARP_BYTES (32 * GSI_WALKF_PITCH + GSI_WALKF_RING * 24 + GSI_WALKF_RING + 64)
+#define GSI_WALKF_SBASE_BYTES (GSI_SEED_GB_MAX * GSI_SEED_GB_MAX * 4)
+#define GSI_WALKF_SMEM (GSI_WALKF_SBASE_BYTES + (GSI_WALK_THREADS / 32) * GSI_WALKF_WARP_BYTES)
+
+template <class SRC, bool STATS, bool ONE_FIELD>
+__global__ void __launch_bounds__(GSI_WALK_THREADS, 8)
+k_walkf(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
+        size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
+        int max_steps, int dynamic)
+{
+  extern __shared__ __align__(16) unsigned char walkf_smem[];
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int *sbase = reinterpret_cast<int *>(walkf_smem);
+  unsigned char *wmem = walkf_smem + GSI_WALKF_SBASE_BYTES + (threadIdx.x >> 5) * GSI_WALKF_WARP_BYTES;
+  const unsigned stage = (unsigned) __cvta_generic_to_shared(wmem);
+  double *rx = reinterpret_cast<double *>(wmem + 32 * GSI_WALKF_PITCH);
+  double *ry = rx + GSI_WALKF_RING;
+  unsigned *rq = reinterpret_cast<unsigned *>(ry + GSI_WALKF_RING);
+  int *rs = reinterpret_cast<int *>(rq + GSI_WALKF_RING);
+  unsigned char *rn = reinterpret_cast<unsigned char *>(rs + GSI_WALKF_RING);
+  {
+    const unsigned nb = (unsigned) V.grid_gb * (unsigned) V.grid_gb;
+    for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sbase[i] = __ldg(V.seedbase + i);
+  }
+  __syncthreads();
+  const int step_cap = max_steps < 255 ? max_steps : 255;
+  unsigned long long steps_acc = 0;
+
+  /* chunks of consecutive queries, dealt by a device counter; batches of 32 within a chunk */
+  unsigned *work = counters + GSI_CNT_WORK;
+  const unsigned n_chunks = (unsigned) ((nq + chunk - 1) / chunk);
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned ahead = 0, cbase = 0, cleft = 0;
+  bool dry = false;
+  if (lane == 0) ahead = dynamic ? atomicAdd(work, 1u) : (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+  /* stage A: coordinates loaded; stage B: seed offset requested */
+  unsigned a_n = 0, a_q0 = 0, b_n = 0, b_q0 = 0, b_off = 0, b_blk = 0;
+  double a_x = 0, a_y = 0, b_x = 0, b_y = 0;
+  unsigned head = 0, tail = 0; /* ring positions (free-running) */
+
+  /* advance the batch pipeline: returns stage B as the current batch, B <- A, A <- a new batch */
+#define GSI_WALKF_ADVANCE()                                                                        \
+  do                                                                                               \
+    {                                                                                              \
+      b_n = a_n; b_q0 = a_q0; b_x = a_x; b_y = a_y;                                                \
+      b_off = GSI_SEED16_ESC; b_blk = 0xffffffffu;                                                 \
+      if (lane < b_n && isfinite(b_x) && isfinite(b_y))                                            \
+        {                                                                                          \
+          const int ix = min(max(__double2int_rd(__fma_rn(b_x, C.ax, C.bx)), 0), V.grid_g - 1);    \
+          const int iy = min(max(__double2int_rd(__fma_rn(b_y, C.ay, C.by)), 0), V.grid_g - 1);    \
+          b_off = __ldg(V.seed16 + ((unsigned) iy * (unsigned) V.grid_g + (unsigned) ix));         \
+          b_blk = (unsigned) (iy >> V.seed_shift) * (unsigned) V.grid_gb + (unsigned) (ix >> V.seed_shift); \
+        }                                                                                          \
+      a_n = 0;                                                                                     \
+      if (cleft == 0 && !dry)                                                                      \
+        {                                                                                          \
+          const unsigned ch = __shfl_sync(FULL, ahead, 0);                                         \
+          if (ch >= n_chunks)                                                                      \
+            dry = true;                                                                            \
+          else                                                                                     \
+            {                                                                                      \
+              if (lane == 0) ahead = dynamic ? atomicAdd(work, 1u) : ch + n_warps;                 \
+              cbase = ch * chunk;                                                                  \
+              cleft = (unsigned) (nq - (size_t) cbase < (size_t) chunk ? nq - (size_t) cbase : (size_t) chunk); \
+            }                                                                                      \
+        }                                                                                          \
+      if (cleft)                                                                                   \
+        {                                                                                          \
+          a_n = cleft < 32u ? cleft : 32u;                                                         \
+          a_q0 = cbase;                                                                            \
+          cbase += a_n; cleft -= a_n;                                                              \
+          if (lane < a_n) src.get_linear((size_t) a_q0 + lane, a_x, a_y);                          \
+        }                                                                                          \
+    }                                                                                              \
+  while (0)
+
+  GSI_WALKF_ADVANCE(); /* A filled */
+  GSI_WALKF_ADVANCE(); /* B filled, A refilled */
+
+  for (;;)
+    {
+      __syncwarp(); /* ring entries pushed in the last iteration are visible */
+      const unsigned cnt = tail - head;
+      const bool have_fresh = (a_n | b_n) != 0;
+      bool v = false;
+      unsigned q = 0;
+      double x = 0, y = 0;
+      int slot = -1, steps = 0;
+      if (cnt >= 32u || (!have_fresh && cnt))
+        {
+          const unsigned n = cnt < 32u ? cnt : 32u;
+          v = lane < n;
+          const unsigned idx = (head + lane) & (GSI_WALKF_RING - 1);
+          if (v)
+            {
+              x = rx[idx]; y = ry[idx]; q = rq[idx]; slot = rs[idx]; steps = rn[idx];
+            }
+          head += n;
+        }
+      else if (have_fresh)
+        {
+          v = lane < b_n;
+          q = b_q0 + lane;
+          x = b_x; y = b_y;
+          if (v && b_blk != 0xffffffffu)
+            {
+              if (b_off != GSI_SEED16_ESC)
+                slot = sbase[b_blk] + (int) b_off;
+              else
+                {
+                  const int ix = min(max(__double2int_rd(__fma_rn(x, C.ax, C.bx)), 0), V.grid_g - 1);
+                  const int iy = min(max(__double2int_rd(__fma_rn(y, C.ay, C.by)), 0), V.grid_g - 1);
+                  slot = gsi_ld_seed(V.seeds + ((unsigned) iy * (unsigned) V.grid_g + (unsigned) ix));
+                }
+            }
+          GSI_WALKF_ADVANCE();
+        }
+      else
+        break;
+
+      /* the warp copies the 32 records its lanes visit (k_walkc's scheme, 112-byte pitch) */
+      const bool live = v && slot >= 0;
+      const int my = live ? slot : -1;
+      __syncwarp(); /* last iteration's reads of the staging area are done */
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        {
+          const unsigned qq = 4u * (unsigned) r + (lane >> 3);
+          const int sl = __shfl_sync(FULL, my, (int) qq);
+#if GSI_WALKF_STAGE == 1
+          /* experiment: all eight pieces of the line are requested (the eighth lands in a scratch slot) */
+          if (sl >= 0)
+            {
+              const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
+              const unsigned d = (lane & 7u) != 7u ? stage + qq * GSI_WALKF_PITCH + (lane & 7u) * 16u
+                                                   : stage + GSI_WALKF_WARP_BYTES - 64u + (lane >> 3) * 16u;
+              asm volatile("cp.async." GSI_WALKC_CP ".shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+            }
+#elif GSI_WALKF_STAGE == 2
+          /* experiment: 128-bit loads through registers instead of cp.async */
+          if (sl >= 0 && (lane & 7u) != 7u)
+            {
+              const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
+              const unsigned d = stage + qq * GSI_WALKF_PITCH + (lane & 7u) * 16u;
+              unsigned long long a, b;
+              asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(g));
+              asm volatile("st.shared.v2.u64 [%0], {%1,%2};" ::"r"(d), "l"(a), "l"(b) : "memory");
+            }
+#else
+          if (sl >= 0 && (lane & 7u) != 7u)
+            {
+              const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
+              const unsigned d = stage + qq * GSI_WALKF_PITCH + (lane & 7u) * 16u;
+              asm volatile("cp.async." GSI_WALKC_CP ".shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+            }
+#endif
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+
+      bool defer = false, moved = false;
+      if (v)
+        {
+          if (!live)
+            defer = true; /* non-finite coordinates */
+          else
+            {
+              const unsigned mine = stage + lane * GSI_WALKF_PITCH;
+              unsigned long long a, b;
+              gsi_rec r;
+              gsi_lds128(mine, a, b);
+              r.x0x = __longlong_as_double((long long) a); r.x0y = __longlong_as_double((long long) b);
+              gsi_lds128(mine + 16, a, b);
+              r.u00 = __longlong_as_double((long long) a); r.u01 = __longlong_as_double((long long) b);
+              gsi_lds128(mine + 32, a, b);
+              r.u11 = __longlong_as_double((long long) a); r.l10 = __longlong_as_double((long long) b);
+              gsi_lds128(mine + 48, a, b);
+              r.lnk[0] = (int32_t) (unsigned) a; r.lnk[1] = (int32_t) (unsigned) (a >> 32);
+              r.lnk[2] = (int32_t) (unsigned) b; r.meta = (uint32_t) (b >> 32);
+              gsi_lds128(mine + 96, a, b);
+              const double r11 = __longlong_as_double((long long) a), r00 = __longlong_as_double((long long) b);
+              double c0, c1;
+              const int st = gsi_walk_step_rcp(&V.xf, &r, r11, r00, x, y, &slot, &c0, &c1);
+              ++steps;
+              if (st == GSI_STEP_ACCEPT)
+                {
+                  gsi_leaf_tail t;
+                  gsi_lds128(mine + 64, a, b);
+                  t.s.node = (int32_t) (unsigned) a; t.s.vflags = (uint32_t) (a >> 32);
+                  t.s.z[0] = __longlong_as_double((long long) b);
+                  gsi_lds128(mine + 80, a, b);
+                  t.s.z[1] = __longlong_as_double((long long) a); t.s.z[2] = __longlong_as_double((long long) b);
+                  const size_t qi = q;
+                  if (leaf_out) GSI_ST_RESULT(leaf_out + qi, t.g.node);
+                  if (val)
+                    {
+                      if (ONE_FIELD)
+                        GSI_ST_RESULT(val + qi, gsi_blend(c0, c1, (int) (t.s.vflags & 1u), t.s.z[0],
+                                                          (int) (t.s.vflags & 2u), t.s.z[1],
+                                                          (int) (t.s.vflags & 4u), t.s.z[2]));
+                      else
+                        gsi_blend_store(&V, &t, c0, c1, val, ld, qi);
+                    }
+                  if (STATS) steps_acc += (unsigned) steps;
+                }
+              else if (st == GSI_STEP_DEFER || steps >= step_cap)
+                defer = true;
+              else
+                moved = true;
+            }
+        }
+      /* walkers go (back) onto the ring: at most 31 were left, at most 32 arrive */
+      const unsigned mm = __ballot_sync(FULL, moved);
+      if (mm)
+        {
+          if (moved)
+            {
+              const unsigned idx = (tail + (unsigned) __popc(mm & lt_mask)) & (GSI_WALKF_RING - 1);
+              rx[idx] = x; ry[idx] = y; rq[idx] = q; rs[idx] = slot; rn[idx] = (unsigned char) steps;
+            }
+          tail += (unsigned) __popc(mm);
+        }
+      /* warp-aggregated append to the deferred list */
+      const unsigned dm = __ballot_sync(FULL, defer);
+      if (dm)
+        {
+          const int leader = __ffs(dm) - 1;
+          unsigned pos = 0;
+          if (lane == (unsigned) leader)
+            pos = atomicAdd(counters + GSI_CNT_DEFERRED, (unsigned) __popc(dm));
+          pos = __shfl_sync(FULL, pos, leader);
+          if (defer)
+            {
+              const unsigned at = pos + __popc(dm & lt_mask);
+              if (at < list_cap)
+                list[at] = q;
+              else
+                mark_overflow(ovf_mask, (size_t) q, counters);
+            }
+        }
+    }
+#undef GSI_WALKF_ADVANCE
+  if (STATS && steps_acc)
+    atomicAdd(reinterpret_cast<unsigned long long *>(counters + GSI_CNT_STEPS), steps_acc);
 }
 
 /* reciprocals of the two divisors of every 128-byte leaf record, into the record's padding */
@@ -1931,7 +2196,7 @@ k_validate_slab(const gsi_view V, unsigned long long n_points, unsigned long lon
             const size_t iy = i / (size_t) V.grid_g, ix = i - iy * (size_t) V.grid_g;
             const unsigned off = V.seed16[i];
             if (off != GSI_SEED16_ESC)
-              mine += (unsigned) (V.seedbase[(iy >> 3) * (size_t) V.grid_gb + (ix >> 3)] + (int) off) >= (unsigned) V.n_leaves;
+              mine += (unsigned) (V.seedbase[(iy >> V.seed_shift) * (size_t) V.grid_gb + (ix >> V.seed_shift)] + (int) off) >= (unsigned) V.n_leaves;
           }
           if (V.entry) mine += (unsigned) V.entry[i] >= (unsigned) V.n_dag;
         }
@@ -2221,6 +2486,33 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
           else GSI_LAUNCH_WALKC(false, false);
 #undef GSI_LAUNCH_WALKC
         }
+      else if (cfg.walk_variant == 3 && V.leaf_stride == 128)
+        {
+          const int ctas_f = cfg.sm_count * (cfg.walk_ctas_per_sm > 5 ? cfg.walk_ctas_per_sm : 8);
+          const int gf = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas_f
+                                    ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
+                                    : (size_t) ctas_f);
+          gsi_cell_map CM;
+          CM.ax = V.xf.sx * V.inv_du;
+          CM.bx = (-V.xf.cx * V.xf.sx - V.u0) * V.inv_du;
+          CM.ay = V.xf.sy * V.inv_dv;
+          CM.by = (-V.xf.cy * V.xf.sy - V.v0) * V.inv_dv;
+#define GSI_LAUNCH_WALKF(STATS, ONE)                                                            \
+  do                                                                                            \
+    {                                                                                           \
+      cudaFuncSetAttribute(k_walkf<SRC, STATS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_WALKF_SMEM); \
+      k_walkf<SRC, STATS, ONE><<<gf, GSI_WALK_THREADS, GSI_WALKF_SMEM, st>>>(V, CM, src, nq, (unsigned) chunk, val, \
+                                                                            leaf_out, ld, cfg.list, list_cap,     \
+                                                                            cfg.ovf_mask, cfg.counters,           \
+                                                                            cfg.max_steps, cfg.walk_dynamic);     \
+    }                                                                                           \
+  while (0)
+          if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKF(true, true);
+          else if (cfg.stats) GSI_LAUNCH_WALKF(true, false);
+          else if (V.n_fields == 1) GSI_LAUNCH_WALKF(false, true);
+          else GSI_LAUNCH_WALKF(false, false);
+#undef GSI_LAUNCH_WALKF
+        }
       else if (cfg.walk_variant == 1)
         {
           unsigned long long *trace = (size_t) g <= cfg.walk_trace_ctas ? cfg.walk_trace : nullptr;
@@ -2307,8 +2599,8 @@ cudaError_t
 gsi_launch_pack_seeds(const gsi_view &V, const int32_t *seeds, uint16_t *seed16, int32_t *seedbase, int sm_count,
                       cudaStream_t st)
 {
-  const size_t nblk = (size_t) V.grid_gb * V.grid_gb;
-  k_pack_seeds<<<grid_for(nblk, 128, sm_count, 16), 128, 0, st>>>(V, seeds, seed16, seedbase);
+  const size_t nblk = (size_t) V.grid_gb * V.grid_gb; /* one warp per block */
+  k_pack_seeds<<<grid_for(nblk * 32, 128, sm_count, 16), 128, 0, st>>>(V, seeds, seed16, seedbase);
   return cudaGetLastError();
 }
 

@@ -18,12 +18,17 @@
  *                               coordinates: leaf slot containing the cell centre
  *                               (filled on the device by the exact-replay kernel)
  *   seed16   uint16[G*G] +      the same table as the fast path reads it: seed = base[block] + seed16[cell]
- *   seedbase int32[GB*GB]       with one base (the smallest seed) per block of 8 x 8 cells, GB = ceil(G/8).
- *                               Leaves are in Morton order, so the seeds of a block are a narrow slot
+ *   seedbase int32[GB*GB]       with one base (the smallest seed) per block of B x B cells, B = 2^seed_shift,
+ *                               GB = ceil(G/B) <= 32.  Leaves are in Morton order and the grid covers the
+ *                               box the Morton keys quantise, so the seeds of a block are a narrow slot
  *                               range; 0xffff = escape to the int32 table (blocks that straddle a
- *                               coarse Morton boundary, dense clusters).  2 bytes per cell instead of 4
- *                               and, above all, a table that stays L2-resident beside ~200 MB of
- *                               randomly gathered leaf records (16 MB instead of 32 MB at 10^6 nodes)
+ *                               coarse Morton boundary, dense clusters).  2 bytes per cell instead of 4:
+ *                               a table that stays L2-resident beside ~250 MB of randomly gathered
+ *                               leaf records (16 MB instead of 32 MB at 10^6 nodes).  The base table is
+ *                               at most 4 KB, so the walk kernel keeps it in shared memory: a query's
+ *                               seed costs ONE divergent global access (seed16), not two.  The
+ *                               flattener rounds G to a multiple of 8 B so that the coarse Morton
+ *                               boundaries (multiples of 1/8 of the box) fall between blocks.
  *   tiles    int32[2^P + 1]     the leaves are sorted by the Morton key of their centroid, so the
  *                               leaves whose key starts with the P-bit prefix t are the slot
  *                               range [tiles[t], tiles[t+1]): a spatial tile whose records can be
@@ -44,7 +49,8 @@
 #include "gsi_core.h"
 
 #define GSI_SLAB_MAGIC 0x3142414c53495347ull /* "GSISLAB1" */
-#define GSI_SLAB_VERSION 5u
+#define GSI_SLAB_VERSION 6u
+#define GSI_SEED_GB_MAX 32 /* seed blocks per side: the base table is at most 32 x 32 x 4 = 4 KB */
 #define GSI_SEED16_ESC 0xffffu
 
 /* One compacted leaf: 96 bytes = three 32-byte sectors, each fetched with one 256-bit load
@@ -95,13 +101,29 @@ typedef struct
   uint64_t total_bytes;
   uint64_t reserved[2]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
   uint64_t off_seed16;  /* uint16[grid_g^2] */
-  uint64_t off_seedbase; /* int32[ceil(grid_g/8)^2] */
+  uint64_t off_seedbase; /* int32[ceil(grid_g / 2^seed_shift)^2] */
   uint32_t tile_bits;       /* tiles = the 2^tile_bits prefixes of the leaves' 32-bit Morton keys */
   uint32_t tile_max_leaves; /* largest tile */
   uint64_t off_tiles;       /* int32[2^tile_bits + 1]: first leaf slot of every tile */
-  uint64_t reserved2;
+  uint32_t seed_shift;      /* seed blocks are 2^seed_shift cells wide (>= 3) */
+  uint32_t reserved2;
   uint64_t off_entry;
 } gsi_slab_header;
+
+/* seed blocks: the smallest power-of-two width (>= 8 cells) that leaves at most GSI_SEED_GB_MAX per side */
+static inline uint32_t
+gsi_seed_shift_for(uint32_t grid_g)
+{
+  uint32_t sh = 3;
+  while (((grid_g + (1u << sh) - 1u) >> sh) > GSI_SEED_GB_MAX) sh++;
+  return sh;
+}
+
+static inline uint32_t
+gsi_seed_blocks(uint32_t grid_g, uint32_t seed_shift)
+{
+  return (grid_g + (1u << seed_shift) - 1u) >> seed_shift;
+}
 
 /* what the kernels receive by value */
 typedef struct
@@ -119,7 +141,8 @@ typedef struct
   double u0, v0, inv_du, inv_dv;
   double delta;
   int32_t grid_g;
-  int32_t grid_gb; /* blocks of 8 x 8 cells per side */
+  int32_t grid_gb; /* seed blocks per side */
+  int32_t seed_shift;
   int32_t n_fields;
   int32_t n_dag;
   int32_t n_leaves;
@@ -151,7 +174,8 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   v.seeds = (const int32_t *) (b + h->off_seeds);
   v.seed16 = (const uint16_t *) (b + h->off_seed16);
   v.seedbase = (const int32_t *) (b + h->off_seedbase);
-  v.grid_gb = (int32_t) ((h->grid_g + 7u) >> 3);
+  v.seed_shift = (int32_t) h->seed_shift;
+  v.grid_gb = (int32_t) gsi_seed_blocks(h->grid_g, h->seed_shift);
   v.entry = (const int32_t *) (b + h->off_entry);
   v.tiles = (const int32_t *) (b + h->off_tiles);
   v.tile_bits = (int32_t) h->tile_bits;

@@ -72,24 +72,32 @@ hostsim_create(const double *xa, const double *ya, const double *za, size_t n, s
       const int slot = gsi_exact_one(&h->view, qx, qy, nullptr, nullptr, 0, c);
       seeds[c] = slot < 0 ? 0 : slot;
     }
-  /* what k_pack_seeds does on the device, with the minimum as the block base (the kernel may pick a later
-     base for a block that straddles a coarse Morton boundary; either is a valid table) */
+  /* what k_pack_seeds does on the device: base = seed of the block's centre cell - 32768; a cell whose seed
+     is outside the 16-bit window takes the in-window seed of the nearest cell of its row / column */
   {
-    const size_t g = h->hdr.grid_g, gb = (g + 7) >> 3;
+    const size_t g = h->hdr.grid_g, B = (size_t) 1 << h->hdr.seed_shift, gb = (g + B - 1) / B;
     uint16_t *s16 = (uint16_t *) (h->image.data() + h->hdr.off_seed16);
     int32_t *sb = (int32_t *) (h->image.data() + h->hdr.off_seedbase);
+    const int ESC = (int) GSI_SEED16_ESC;
     for (size_t by = 0; by < gb; by++)
       for (size_t bx = 0; bx < gb; bx++)
         {
-          int lo = 0x7fffffff;
-          for (size_t y = by * 8; y < std::min(by * 8 + 8, g); y++)
-            for (size_t x = bx * 8; x < std::min(bx * 8 + 8, g); x++) lo = std::min(lo, seeds[y * g + x]);
-          sb[by * gb + bx] = lo;
-          for (size_t y = by * 8; y < std::min(by * 8 + 8, g); y++)
-            for (size_t x = bx * 8; x < std::min(bx * 8 + 8, g); x++)
+          const size_t x0 = bx * B, y0 = by * B, x1 = std::min(x0 + B, g), y1 = std::min(y0 + B, g);
+          const int base = std::max(seeds[((y0 + y1) >> 1) * g + ((x0 + x1) >> 1)] - 32768, 0);
+          sb[by * gb + bx] = base;
+          for (size_t y = y0; y < y1; y++)
+            for (size_t x = x0; x < x1; x++)
               {
-                const int d = seeds[y * g + x] - lo;
-                s16[y * g + x] = d < (int) GSI_SEED16_ESC ? (uint16_t) d : (uint16_t) GSI_SEED16_ESC;
+                int d = seeds[y * g + x] - base;
+                for (size_t r = 1; !(d >= 0 && d < ESC) && r < B; r++)
+                  {
+                    int c;
+                    if (x >= x0 + r && (c = seeds[y * g + (x - r)] - base) >= 0 && c < ESC) d = c;
+                    else if (x + r < x1 && (c = seeds[y * g + (x + r)] - base) >= 0 && c < ESC) d = c;
+                    else if (y >= y0 + r && (c = seeds[(y - r) * g + x] - base) >= 0 && c < ESC) d = c;
+                    else if (y + r < y1 && (c = seeds[(y + r) * g + x] - base) >= 0 && c < ESC) d = c;
+                  }
+                s16[y * g + x] = (d >= 0 && d < ESC) ? (uint16_t) d : (uint16_t) GSI_SEED16_ESC;
               }
         }
   }
@@ -102,6 +110,17 @@ hostsim_free(hostsim *h)
   delete h;
 }
 
+/* cells of the compact seed table that escape to the int32 table */
+size_t
+hostsim_seed_escapes(const hostsim *h)
+{
+  const uint16_t *s16 = (const uint16_t *) (h->image.data() + h->hdr.off_seed16);
+  const size_t cells = (size_t) h->hdr.grid_g * h->hdr.grid_g;
+  size_t n = 0;
+  for (size_t c = 0; c < cells; c++) n += s16[c] == GSI_SEED16_ESC;
+  return n;
+}
+int hostsim_seed_shift(const hostsim *h) { return (int) h->hdr.seed_shift; }
 size_t hostsim_n_leaves(const hostsim *h) { return (size_t) h->hdr.n_leaves; }
 size_t hostsim_grid_g(const hostsim *h) { return (size_t) h->hdr.grid_g; }
 const int32_t *hostsim_tiles(const hostsim *h) { return (const int32_t *) (h->image.data() + h->hdr.off_tiles); }

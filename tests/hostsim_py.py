@@ -37,6 +37,10 @@ def lib():
         H.hostsim_n_leaves.restype = c_size_t
         H.hostsim_n_leaves.argtypes = [c_void_p]
         H.hostsim_grid_g.restype = c_size_t
+        H.hostsim_seed_escapes.restype = c_size_t
+        H.hostsim_seed_escapes.argtypes = [c_void_p]
+        H.hostsim_seed_shift.restype = c_int
+        H.hostsim_seed_shift.argtypes = [c_void_p]
         H.hostsim_grid_g.argtypes = [c_void_p]
         H.hostsim_build_batched_equal.restype = c_int
         H.hostsim_build_batched_equal.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p]
@@ -81,6 +85,10 @@ class HostSim:
         bits = self.H.hostsim_tile_bits(self.h)
         buf = (ctypes.c_int32 * ((1 << bits) + 1)).from_address(self.H.hostsim_tiles(self.h))
         return bits, np.frombuffer(buf, dtype=np.int32).copy(), self.H.hostsim_tile_max_leaves(self.h)
+
+    def seed_table(self):
+        """(grid side, log2 of the seed-block width, cells that escape to the int32 table)"""
+        return (self.H.hostsim_grid_g(self.h), self.H.hostsim_seed_shift(self.h), self.H.hostsim_seed_escapes(self.h))
 
     def node_is_leaf(self, node):
         return bool(self.H.hostsim_node_is_leaf(self.h, int(node)))

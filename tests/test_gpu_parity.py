@@ -188,7 +188,12 @@ def test_sixteen_fields_raster_vs_port():
                                           (0, {"walk_pf": 4}), (0, {"walk_chunk": 32}), (0, {"walk_ctas_per_sm": 1}),
                                           (0, {"walk_variant": 0, "leaf_stride": 96}), (0, {"walk_variant": 2, "leaf_stride": 96}),
                                           (0, {"walk_variant": 2, "walk_dynamic": 0, "walk_chunk": 64}),
-                                          (0, {"walk_variant": 1, "walk_chunk": 64})])
+                                          (0, {"walk_variant": 1, "walk_chunk": 64}),
+                                          (0, {"walk_variant": 3}), (0, {"walk_variant": 3, "walk_chunk": 32}),
+                                          (0, {"walk_variant": 3, "walk_dynamic": 0, "walk_chunk": 96}),
+                                          (0, {"walk_variant": 3, "walk_ctas_per_sm": 1, "max_steps": 2}),
+                                          (0, {"walk_variant": 3, "cells_per_leaf": 0.05}),
+                                          (0, {"walk_variant": 2, "grid_g": 300}), (0, {"walk_variant": 3, "grid_g": 300})])
 def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel, extra):
     """the walk kernels (0: k_walkp by default, k_walk with walk_variant = 0, every way of dealing chunks
     and of requesting leaf lines ahead) and k_locate (1) on config 1 (1 field) and the config-3 mix (3 fields)"""
