@@ -133,6 +133,7 @@ struct eval_ctx
   cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
   unsigned *list = nullptr;
   size_t list_cap = 0;
+  size_t list_want = 0; /* entries the last launches would have needed (read_counters): the list grows to it */
   unsigned *ovf_mask = nullptr; /* overflow bitmask, one bit per query of a launch */
   size_t ovf_words = 0;
   unsigned *counters = nullptr;
@@ -275,6 +276,9 @@ struct gsl_scattered_cuda
   int exact_coop = 1;  /* deferred queries are replayed by four lanes each (0: one thread each) */
   int walk_variant = 2; /* 1: k_walkp (two walks per lane in rotation behind L2 prefetches), 0: k_walk */
   int walk_dynamic = 1; /* k_walkp draws its chunks from a device counter (0: round-robin) */
+  int walk_carveout = 72; /* k_walkc / k_walkf: preferred shared-memory carve-out in percent (-1: the driver's choice).
+                             164 KB of shared memory leave 92 KB of L1: with 196 KB or more (60 KB of L1 or less)
+                             the walk kernels lose a quarter of their rate, profiles/r2u_carveout_and_pitch.txt */
   int walk_pf = 1;      /* k_walkp: 0 no prefetch, 1..4 = flavours of gsi_prefetch_leaf_l2 */
   int walk_trace = 0;   /* diagnostic: per-CTA {smid, start, end, queries} of the last k_walkp launch */
   int build_device = 1; /* the builder locates its points in batches on the GPU when there is one (0: host only) */
@@ -647,6 +651,7 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r, const eval_ctx *c)
   g.walk_chunk = w->walk_chunk;
   g.walk_variant = w->walk_variant;
   g.walk_dynamic = w->walk_dynamic;
+  g.walk_carveout = w->walk_carveout;
   g.walk_pf = w->walk_pf;
   g.walk_trace = w->walk_trace ? c->trace : nullptr;
   g.walk_trace_ctas = w->walk_trace ? c->trace_ctas : 0;
@@ -768,8 +773,9 @@ eval_on_device(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, const
     {
       /* deferred list: a fraction of the launch size (overflow goes to a bitmask) */
       const size_t per_launch = std::min(chunk, nq);
-      const size_t want = std::max<size_t>(std::min<size_t>(per_launch, 65536),
-                                           (size_t) (w->list_fraction * (double) per_launch));
+      const size_t want = std::max<size_t>(std::max<size_t>(std::min<size_t>(per_launch, 65536),
+                                                            (size_t) (w->list_fraction * (double) per_launch)),
+                                           std::min(c->list_want, per_launch));
       const int s = ensure_list(c, want, per_launch);
       if (s) return s;
       const size_t ctas = (size_t) r->sm_count * 16;
@@ -814,6 +820,10 @@ int
 read_counters(eval_ctx *c, unsigned out[GSI_CNT_WORDS])
 {
   CU(cudaMemcpy(out, c->counters, GSI_CNT_WORDS * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  /* the last launch deferred more queries than the list holds (the rest went through the overflow
+     bitmask, which is slower): size the list for such launches from now on */
+  const size_t deferred = out[GSI_CNT_DEFERRED];
+  if (deferred > c->list_cap) c->list_want = std::max(c->list_want, deferred + deferred / 4);
   return 0;
 }
 
@@ -1310,6 +1320,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "exact_coop" && (value == 0 || value == 1)) w->exact_coop = (int) value;
   else if (k == "walk_variant" && value >= 0 && value <= 3) w->walk_variant = (int) value;
   else if (k == "walk_dynamic" && (value == 0 || value == 1)) w->walk_dynamic = (int) value;
+  else if (k == "walk_carveout" && value >= -1 && value <= 100) w->walk_carveout = (int) value;
   else if (k == "walk_pf" && value >= 0 && value <= 4) w->walk_pf = (int) value;
   else if (k == "walk_trace" && (value == 0 || value == 1)) w->walk_trace = (int) value;
   else if (k == "copy_threads" && value >= 1 && value <= 64) w->copy_threads = (int) value;

@@ -337,6 +337,47 @@ k_exact_list4(const gsi_view V, const SRC src, const unsigned *list, unsigned li
     exact_one4(V, src, (size_t) list[g], val, leaf_out, ld, counters, gmask, gbase, sub);
 }
 
+/* exact replay of the queries marked in the overflow bitmask, four lanes per query: a warp takes 32
+ * mask words at a time (one per lane) and, round after round, the first eight lanes that still hold a
+ * marked query hand one each to the warp's eight groups */
+template <class SRC>
+__global__ void __launch_bounds__(128, 8)
+k_exact_overflow4(const gsi_view V, const SRC src, size_t nq, unsigned *mask, double *val, int *leaf_out, size_t ld,
+                  unsigned *counters)
+{
+  if (counters[GSI_CNT_OVERFLOW] == 0) return;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u;
+  const int sub = (int) (lane & 3u), gbase = (int) (lane & ~3u);
+  const unsigned gmask = 0xfu << gbase, group = lane >> 2;
+  const size_t n_words = (nq + 31) >> 5;
+  const size_t wstride = (((size_t) gridDim.x * blockDim.x) >> 5) * 32;
+  for (size_t w0 = ((((size_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5); w0 < n_words; w0 += wstride)
+    {
+      const size_t w = w0 + lane;
+      unsigned m = w < n_words ? mask[w] : 0u;
+      if (m) mask[w] = 0;
+      for (;;)
+        {
+          const unsigned have = __ballot_sync(FULL, m != 0);
+          if (!have) break;
+          /* the lane that serves this group in this round: the (group+1)-th lane with a marked query */
+          const unsigned srcl = __fns(have, 0, (int) group + 1);
+          unsigned bit = 0;
+          const bool giver = m != 0 && (unsigned) __popc(have & ((1u << lane) - 1u)) < 8u;
+          if (giver)
+            {
+              bit = (unsigned) __ffs(m) - 1u;
+              m &= m - 1u;
+            }
+          const unsigned sl = srcl < 32u ? srcl : 0u;
+          const unsigned b = __shfl_sync(FULL, bit, (int) sl);
+          if (srcl < 32u)
+            exact_one4(V, src, ((w0 + sl) << 5) + (size_t) b, val, leaf_out, ld, counters, gmask, gbase, sub);
+        }
+    }
+}
+
 /* seeds[cell] = leaf slot containing the cell centre (exact replay of the centre) */
 __global__ void __launch_bounds__(128)
 k_seed_cells(const gsi_view V, int32_t *seeds)
@@ -840,12 +881,18 @@ k_walkp(const gsi_view V, const SRC src, size_t nq, unsigned chunk, double *val,
  * 128-byte lines (slab with leaf_stride = 128) and the WARP fetches them: eight lanes copy one record
  * as eight 16-byte pieces of one line (cp.async, global -> shared memory without registers), four
  * records per instruction, so a visit costs ONE tag look-up instead of three.  Every lane then reads
- * its own record from shared memory (144-byte pitch: conflict-free 128-bit reads).  The spare 32 bytes
+ * its own record from shared memory (112-byte pitch: conflict-free 128-bit reads).  The spare 32 bytes
  * of the line carry the reciprocals of the record's two divisors (k_leaf_rcp), so the two binary64
  * divisions of the solve cost three operations each (gsi_walk_step_rcp; a quotient the hoisted form
  * cannot vouch for defers the query).  With the record in shared memory the kernel fits 64
  * registers: 8 CTAs = 32 warps per SM.  Queue as in k_walkp (continuous, chunks from a counter). */
-#define GSI_WALKC_PITCH 144
+#ifndef GSI_WALKC_THREADS
+#define GSI_WALKC_THREADS 128 /* CTA size of k_walkc; 1024 / GSI_WALKC_THREADS CTAs per SM */
+#endif
+#ifndef GSI_WALKC_SBASE
+#define GSI_WALKC_SBASE (GSI_SEED_GB_MAX * GSI_SEED_GB_MAX)
+#endif
+#define GSI_WALKC_PITCH 112 /* 7 x 16 bytes; 28 words: conflict-free 128-bit reads, 8 CTAs in 164 KB of shared memory */
 #ifndef GSI_WALKC_CP
 #define GSI_WALKC_CP "cg" /* L2 only: the staged lines are not read through L1 again */
 #endif
@@ -929,7 +976,7 @@ gsi_seed_issue(const gsi_view &V, const gsi_cell_map &C, double qx, double qy, u
   const int ix = min(max(__double2int_rd(__fma_rn(qx, C.ax, C.bx)), 0), V.grid_g - 1);
   const int iy = min(max(__double2int_rd(__fma_rn(qy, C.ay, C.by)), 0), V.grid_g - 1);
   const unsigned cell = (unsigned) iy * (unsigned) V.grid_g + (unsigned) ix;
-  *off = __ldg(V.seed16 + cell);
+  *off = gsi_ld_seed16(V.seed16 + cell);
   *blk = (int) ((unsigned) (iy >> V.seed_shift) * (unsigned) V.grid_gb + (unsigned) (ix >> V.seed_shift));
 }
 
@@ -952,13 +999,13 @@ gsi_lds128(unsigned addr, unsigned long long &a, unsigned long long &b)
 }
 
 template <class SRC, bool STATS, bool ONE_FIELD>
-__global__ void __launch_bounds__(GSI_WALK_THREADS, 8)
+__global__ void __launch_bounds__(GSI_WALKC_THREADS, 1024 / GSI_WALKC_THREADS)
 k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
         size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
         int max_steps, int dynamic, unsigned long long *trace)
 {
-  __shared__ __align__(16) unsigned char stage_all[(GSI_WALK_THREADS / 32) * 32 * GSI_WALKC_PITCH];
-  __shared__ int sbase[GSI_SEED_GB_MAX * GSI_SEED_GB_MAX]; /* the seed-block bases: at most 4 KB */
+  __shared__ __align__(16) unsigned char stage_all[(GSI_WALKC_THREADS / 32) * 32 * GSI_WALKC_PITCH];
+  __shared__ int sbase[GSI_WALKC_SBASE]; /* the seed-block bases: at most 4 KB */
   const unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -1134,7 +1181,9 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
  *     in shared memory; whenever the ring holds 32 walkers (or no batch is left) the warp pops 32 of
  *     them and gives them one visit with the same code.  Lanes stay full, no per-lane queue state.
  * Deferred queries go to the same list as in the other kernels.  Needs 128-byte leaf records. */
+#ifndef GSI_WALKF_PITCH
 #define GSI_WALKF_PITCH 112 /* 7 x 16 bytes of a record; 28 words: conflict-free 128-bit reads */
+#endif
 #define GSI_WALKF_RING 64
 #ifndef GSI_WALKF_STAGE
 #define GSI_WALKF_STAGE 0
@@ -1192,7 +1241,7 @@ k_walkf(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
         {                                                                                          \
           const int ix = min(max(__double2int_rd(__fma_rn(b_x, C.ax, C.bx)), 0), V.grid_g - 1);    \
           const int iy = min(max(__double2int_rd(__fma_rn(b_y, C.ay, C.by)), 0), V.grid_g - 1);    \
-          b_off = __ldg(V.seed16 + ((unsigned) iy * (unsigned) V.grid_g + (unsigned) ix));         \
+          b_off = gsi_ld_seed16(V.seed16 + ((unsigned) iy * (unsigned) V.grid_g + (unsigned) ix)); \
           b_blk = (unsigned) (iy >> V.seed_shift) * (unsigned) V.grid_gb + (unsigned) (ix >> V.seed_shift); \
         }                                                                                          \
       a_n = 0;                                                                                     \
@@ -2464,10 +2513,10 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
                                : (size_t) ctas);
       if (cfg.walk_variant == 2 && V.leaf_stride == 128)
         {
-          const int ctas_c = cfg.sm_count * (cfg.walk_ctas_per_sm > 5 ? cfg.walk_ctas_per_sm : 8);
-          const int gc = (int) ((n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32) < (size_t) ctas_c
-                                    ? (n_chunks + GSI_WALK_THREADS / 32 - 1) / (GSI_WALK_THREADS / 32)
-                                    : (size_t) ctas_c);
+          const int wpc = GSI_WALKC_THREADS / 32; /* warps per CTA */
+          const int ctas_c = GSI_WALKC_THREADS == 128 ? cfg.sm_count * (cfg.walk_ctas_per_sm > 5 ? cfg.walk_ctas_per_sm : 8)
+                                                      : cfg.sm_count * (1024 / GSI_WALKC_THREADS);
+          const int gc = (int) ((n_chunks + wpc - 1) / wpc < (size_t) ctas_c ? (n_chunks + wpc - 1) / wpc : (size_t) ctas_c);
           unsigned long long *trace = (size_t) gc <= cfg.walk_trace_ctas ? cfg.walk_trace : nullptr;
           if (trace) cudaMemsetAsync(trace, 0, cfg.walk_trace_ctas * 4 * sizeof(unsigned long long), st);
           gsi_cell_map CM;
@@ -2476,10 +2525,16 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
           CM.ay = V.xf.sy * V.inv_dv;
           CM.by = (-V.xf.cy * V.xf.sy - V.v0) * V.inv_dv;
 #define GSI_LAUNCH_WALKC(STATS, ONE)                                                            \
-  k_walkc<SRC, STATS, ONE><<<gc, GSI_WALK_THREADS, 0, st>>>(V, CM, src, nq, (unsigned) chunk, val, leaf_out, \
-                                                            ld, cfg.list, list_cap, cfg.ovf_mask,      \
-                                                            cfg.counters, cfg.max_steps, cfg.walk_dynamic, \
-                                                            trace)
+  do                                                                                            \
+    {                                                                                           \
+      if (cfg.walk_carveout >= 0)                                                               \
+        cudaFuncSetAttribute(k_walkc<SRC, STATS, ONE>, cudaFuncAttributePreferredSharedMemoryCarveout, cfg.walk_carveout); \
+      k_walkc<SRC, STATS, ONE><<<gc, GSI_WALKC_THREADS, 0, st>>>(V, CM, src, nq, (unsigned) chunk, val, leaf_out, \
+                                                                ld, cfg.list, list_cap, cfg.ovf_mask,      \
+                                                                cfg.counters, cfg.max_steps, cfg.walk_dynamic, \
+                                                                trace);                                    \
+    }                                                                                           \
+  while (0)
           if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKC(true, true);
           else if (cfg.stats) GSI_LAUNCH_WALKC(true, false);
           else if (V.n_fields == 1) GSI_LAUNCH_WALKC(false, true);
@@ -2501,6 +2556,8 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   do                                                                                            \
     {                                                                                           \
       cudaFuncSetAttribute(k_walkf<SRC, STATS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GSI_WALKF_SMEM); \
+      if (cfg.walk_carveout >= 0)                                                               \
+        cudaFuncSetAttribute(k_walkf<SRC, STATS, ONE>, cudaFuncAttributePreferredSharedMemoryCarveout, cfg.walk_carveout); \
       k_walkf<SRC, STATS, ONE><<<gf, GSI_WALK_THREADS, GSI_WALKF_SMEM, st>>>(V, CM, src, nq, (unsigned) chunk, val, \
                                                                             leaf_out, ld, cfg.list, list_cap,     \
                                                                             cfg.ovf_mask, cfg.counters,           \
@@ -2558,8 +2615,11 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   else
     k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld,
                                                         cfg.counters);
-  k_exact_overflow<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, nq, cfg.ovf_mask, val, leaf_out, ld,
-                                                          cfg.counters);
+  if (cfg.exact_coop)
+    k_exact_overflow4<SRC><<<cfg.sm_count * 8, 128, 0, st>>>(V, src, nq, cfg.ovf_mask, val, leaf_out, ld, cfg.counters);
+  else
+    k_exact_overflow<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, nq, cfg.ovf_mask, val, leaf_out, ld,
+                                                            cfg.counters);
   if (cfg.ev_exact1) cudaEventRecord(cfg.ev_exact1, st);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -68,6 +68,7 @@ struct gsi_launch_cfg
   int walk_variant = 2;  /* 0 = k_walk, 1 = k_walkp (two walks per lane in rotation behind L2 prefetches),
                             2 = k_walkc (warp-cooperative cp.async staging; needs 128-byte leaf records) */
   int walk_dynamic = 1;  /* k_walkp: chunks dealt by a device counter (0: round-robin) */
+  int walk_carveout = -1; /* k_walkc / k_walkf: cudaFuncAttributePreferredSharedMemoryCarveout in percent, -1 = default */
   int walk_pf = 1;       /* k_walkp: how the next leaf line is requested ahead (gsi_prefetch_leaf_l2) */
   unsigned long long *walk_trace = nullptr; /* k_walkp / k_walkc: 4 words per CTA {smid, start ns, end ns, queries}, zeroed here */
   size_t walk_trace_ctas = 0;               /* CTAs the trace buffer has room for */
