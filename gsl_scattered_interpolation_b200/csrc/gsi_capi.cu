@@ -276,6 +276,7 @@ struct gsl_scattered_cuda
   int exact_coop = 1;  /* deferred queries are replayed by four lanes each (0: one thread each) */
   int walk_variant = 2; /* 1: k_walkp (two walks per lane in rotation behind L2 prefetches), 0: k_walk */
   int walk_dynamic = 1; /* k_walkp draws its chunks from a device counter (0: round-robin) */
+  int walk_l1 = -1;       /* k_walkc: cp.async.ca (1) / .cg (0) for the leaf lines, -1 = by structure size */
   int walk_carveout = 72; /* k_walkc / k_walkf: preferred shared-memory carve-out in percent (-1: the driver's choice).
                              164 KB of shared memory leave 92 KB of L1: with 196 KB or more (60 KB of L1 or less)
                              the walk kernels lose a quarter of their rate, profiles/r2u_carveout_and_pitch.txt */
@@ -620,7 +621,8 @@ ensure_list(eval_ctx *c, size_t cap, size_t per_launch)
       if (c->list) cudaFree(c->list);
       c->list = nullptr;
       c->list_cap = 0;
-      CU(cudaMalloc(&c->list, cap * sizeof(unsigned)));
+      /* twice: the second half receives what the vertex-memo pass leaves of the list (k_memo_list) */
+      CU(cudaMalloc(&c->list, 2 * cap * sizeof(unsigned)));
       c->list_cap = cap;
     }
   const size_t words = (per_launch + 31) / 32;
@@ -652,10 +654,12 @@ cfg_of(const gsl_scattered_cuda *w, const replica *r, const eval_ctx *c)
   g.walk_variant = w->walk_variant;
   g.walk_dynamic = w->walk_dynamic;
   g.walk_carveout = w->walk_carveout;
+  g.walk_l1 = w->walk_l1;
   g.walk_pf = w->walk_pf;
   g.walk_trace = w->walk_trace ? c->trace : nullptr;
   g.walk_trace_ctas = w->walk_trace ? c->trace_ctas : 0;
   g.list = c->list;
+  g.list2 = c->list ? c->list + c->list_cap : nullptr;
   g.list_capacity = c->list_cap;
   g.ovf_mask = c->ovf_mask;
   g.counters = c->counters;
@@ -1105,6 +1109,8 @@ install_image(gsl_scattered_cuda *w, const std::vector<char> &image)
   cudaError_t e = cudaMemcpyAsync(r0->slab, image.data(), image.size(), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = gsi_launch_leaf_rcp(r0->view, r0->slab + w->hdr.off_leaf, r0->sm_count, st);
   if (e == cudaSuccess) e = gsi_launch_entry_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_entry), r0->sm_count, st);
+  if (e == cudaSuccess && w->hdr.memo_bits)
+    e = gsi_launch_memo_fill(r0->view, (gsi_memo *) (r0->slab + w->hdr.off_memo), r0->sm_count, st);
   if (e == cudaSuccess) e = gsi_launch_seed_cells(r0->view, (int32_t *) (r0->slab + w->hdr.off_seeds), r0->sm_count, st);
   if (e == cudaSuccess)
     e = gsi_launch_pack_seeds(r0->view, (const int32_t *) (r0->slab + w->hdr.off_seeds), (uint16_t *) (r0->slab + w->hdr.off_seed16),
@@ -1163,6 +1169,8 @@ adopt_slab(gsl_scattered_cuda *w, const gsi_slab_header &h, const void *src, siz
       || !extent_ok(h.off_seeds, cells, sizeof(int32_t), bytes) || !extent_ok(h.off_entry, cells, sizeof(int32_t), bytes)
       || !extent_ok(h.off_tiles, ((uint64_t) 1 << h.tile_bits) + 1, sizeof(int32_t), bytes)
       || !extent_ok(h.off_seed16, cells, sizeof(uint16_t), bytes)
+      || h.memo_bits > 31
+      || (h.memo_bits && (h.off_memo % 32 != 0 || !extent_ok(h.off_memo, (uint64_t) 1 << h.memo_bits, sizeof(gsi_memo), bytes)))
       || h.seed_shift < 3 || h.seed_shift > 15 || gsi_seed_blocks(h.grid_g, h.seed_shift) > GSI_SEED_GB_MAX
       || !extent_ok(h.off_seedbase, (uint64_t) gsi_seed_blocks(h.grid_g, h.seed_shift) * gsi_seed_blocks(h.grid_g, h.seed_shift),
                     sizeof(int32_t), bytes)
@@ -1295,6 +1303,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "max_steps" && value >= 1) w->max_steps = (int) value;
   else if (k == "delta" && value > 0) w->fprm.delta = value;
   else if (k == "leaf_stride" && (value == 96 || value == 128)) w->fprm.leaf_stride = (uint32_t) value;
+  else if (k == "vertex_memo" && (value == 0 || value == 1)) w->fprm.vertex_memo = (int) value;
   else if (k == "mode" && (value == 0 || value == 1)) w->mode = (int) value;
   else if (k == "stats") w->stats = value != 0;
   else if (k == "chunk" && value >= 1) w->chunk = (size_t) value;
@@ -1321,6 +1330,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "walk_variant" && value >= 0 && value <= 3) w->walk_variant = (int) value;
   else if (k == "walk_dynamic" && (value == 0 || value == 1)) w->walk_dynamic = (int) value;
   else if (k == "walk_carveout" && value >= -1 && value <= 100) w->walk_carveout = (int) value;
+  else if (k == "walk_l1" && (value == -1 || value == 0 || value == 1)) w->walk_l1 = (int) value;
   else if (k == "walk_pf" && value >= 0 && value <= 4) w->walk_pf = (int) value;
   else if (k == "walk_trace" && (value == 0 || value == 1)) w->walk_trace = (int) value;
   else if (k == "copy_threads" && value >= 1 && value <= 64) w->copy_threads = (int) value;

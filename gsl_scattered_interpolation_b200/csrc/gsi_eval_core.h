@@ -409,6 +409,64 @@ gsi_leaf_box(const gsi_view *V, const gsi_rec *r, int swap, double grow, double 
     }
 }
 
+/* ---- vertex memo (gsi_layout.h) ------------------------------------------------------------------ */
+GSI_HD uint64_t
+gsi_f64_bits(double v)
+{
+#if defined(__CUDA_ARCH__)
+  return (uint64_t) __double_as_longlong(v);
+#else
+  uint64_t u;
+  memcpy(&u, &v, 8);
+  return u;
+#endif
+}
+
+GSI_HD uint32_t
+gsi_memo_hash(uint64_t xb, uint64_t yb)
+{
+  uint64_t z = xb * 0x9E3779B97F4A7C15ull + (yb ^ (yb >> 29)) * 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 31; z *= 0x94D049BB133111EBull;
+  z ^= z >> 29;
+  return (uint32_t) z;
+}
+
+/* the memoised answer for a query that coincides bit for bit with a data node: 1 = found */
+GSI_HD int
+gsi_memo_find(const gsi_view *V, double qx, double qy, int *node, int *slot)
+{
+  if (!V->memo) return 0;
+  const uint64_t xb = gsi_f64_bits(qx), yb = gsi_f64_bits(qy);
+  uint32_t h = gsi_memo_hash(xb, yb) & V->memo_mask;
+  for (int probe = 0; probe < GSI_MEMO_MAX_PROBES; probe++, h = (h + 1u) & V->memo_mask)
+    {
+#if defined(__CUDA_ARCH__)
+      unsigned long long a, b, c, d;
+      gsi_ld256(V->memo + h, a, b, c, d);
+      const uint32_t state = (uint32_t) a;
+      if (state == GSI_MEMO_EMPTY) return 0;
+      if (b == xb && c == yb)
+        {
+          if (state != GSI_MEMO_FULL) return 0;
+          *node = (int32_t) (uint32_t) (a >> 32);
+          *slot = (int32_t) (uint32_t) d;
+          return 1;
+        }
+#else
+      const gsi_memo *e = V->memo + h;
+      if (e->state == GSI_MEMO_EMPTY) return 0;
+      if (gsi_f64_bits(e->x) == xb && gsi_f64_bits(e->y) == yb)
+        {
+          if (e->state != GSI_MEMO_FULL) return 0;
+          *node = e->node;
+          *slot = e->slot;
+          return 1;
+        }
+#endif
+    }
+  return 0;
+}
+
 #define GSI_EXACT_OUTSIDE (-1)
 
 /* Exact replay of one query.  Returns the leaf's compact slot (>= 0) or GSI_EXACT_OUTSIDE;

@@ -6,6 +6,7 @@
  * calculate_bary_coords for every DAG node and leaf (linear_simplex.c:616-639).
  */
 #include "gsi_flatten.h"
+#include "gsi_eval_core.h"
 
 #include <algorithm>
 #include <cmath>
@@ -182,6 +183,15 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
   while (P < 12 && (double) L / (double) (1u << P) > (double) std::max<uint32_t>(1, prm.tile_leaves) * 1.05) P++;
   h.tile_bits = P;
   h.off_tiles = off; off = align256(off + ((uint64_t) (1u << P) + 1) * sizeof(int32_t));
+  /* vertex memo: a power of two of at least 2 n entries */
+  uint32_t memo_bits = 0;
+  if (prm.vertex_memo && n > 0 && xa && ya)
+    {
+      memo_bits = 4;
+      while (memo_bits < 31 && ((uint64_t) 1 << memo_bits) < 2 * (uint64_t) n) memo_bits++;
+      h.off_memo = off; off = align256(off + ((uint64_t) 1 << memo_bits) * sizeof(gsi_memo));
+    }
+  h.memo_bits = memo_bits;
   h.total_bytes = off;
 
   image->assign((size_t) h.total_bytes, 0);
@@ -288,6 +298,31 @@ gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const do
     gsi_slab_header *hp = (gsi_slab_header *) base;
     hp->tile_max_leaves = biggest;
   }
+
+  /* --- vertex memo: the keys (answers are filled in on the device) ----------------------- */
+  if (memo_bits)
+    {
+      gsi_memo *memo = (gsi_memo *) (base + h.off_memo);
+      const uint32_t mask = ((uint32_t) 1 << memo_bits) - 1u;
+      for (size_t i = 0; i < n; i++)
+        {
+          if (!(std::isfinite(xa[i]) && std::isfinite(ya[i]))) continue;
+          const uint64_t xb = gsi_f64_bits(xa[i]), yb = gsi_f64_bits(ya[i]);
+          uint32_t k = gsi_memo_hash(xb, yb) & mask;
+          for (int probe = 0; probe < GSI_MEMO_MAX_PROBES; probe++, k = (k + 1u) & mask)
+            {
+              gsi_memo &e = memo[k];
+              if (e.state == GSI_MEMO_EMPTY)
+                {
+                  e.state = GSI_MEMO_PENDING;
+                  e.x = xa[i];
+                  e.y = ya[i];
+                  break;
+                }
+              if (gsi_f64_bits(e.x) == xb && gsi_f64_bits(e.y) == yb) break; /* duplicate node */
+            }
+        }
+    }
 
   /* --- values -------------------------------------------------------------------------- */
   if (za)

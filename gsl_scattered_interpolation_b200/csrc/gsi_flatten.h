@@ -17,11 +17,13 @@ struct gsi_flatten_params
   uint32_t leaf_stride = 128;   /* 128 = one 128-byte line per leaf (default: k_walkc fetches a leaf as one line and keeps
                                    the reciprocals of its divisors in the spare bytes), 96 = packed records */
   uint32_t tile_leaves = 1000;  /* target leaves per Morton-prefix tile (reorder pipeline) */
+  int vertex_memo = 1;          /* hash table of the data nodes' coordinates for the exact answers at the nodes */
 };
 
 /* za: n_fields x n_points, field-major (may be NULL: values left zero).
  * The seeds, seed16, seedbase and entry sections are left zero (entry 0 = root); they are filled on
- * the device (seed16 all zero + seedbase all zero is a valid, if useless, compact table: slot 0). */
+ * the device (seed16 all zero + seedbase all zero is a valid, if useless, compact table: slot 0).  The
+ * memo section receives the keys (state PENDING); k_memo_fill computes the answers on the device. */
 int gsi_flatten(const gsi_host_tree &t, const double *xa, const double *ya, const double *za,
                 size_t n_fields, const gsi_flatten_params &prm, std::vector<char> *image,
                 std::string *err);

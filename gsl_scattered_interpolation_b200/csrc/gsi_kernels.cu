@@ -96,6 +96,25 @@ struct src_raster
   }
 };
 
+/* a deferred query that coincides with a data node: interp_point on the memoised leaf (the leaf is
+   not singular, so interp_point solves it afresh, linear_simplex.c:687) */
+__device__ __forceinline__ void
+memo_answer(const gsi_view &V, int node, int slot, double qx, double qy, double *val, int *leaf_out, size_t ld, size_t q)
+{
+  if (leaf_out) leaf_out[q] = node;
+  if (val)
+    {
+      const gsi_leaf *lf = gsi_leaf_at(&V, slot);
+      gsi_rec r;
+      gsi_fetch_rec(&r, lf);
+      double c0, c1;
+      gsi_solve(&V.xf, &r, (int) (r.meta >> 31), qx, qy, &c0, &c1);
+      gsi_leaf_tail t;
+      gsi_fetch_tail(&t, lf);
+      gsi_blend_store(&V, &t, c0, c1, val, ld, q);
+    }
+}
+
 /* exact replay on every query of a source */
 template <class SRC>
 __global__ void __launch_bounds__(128, 4)
@@ -112,13 +131,13 @@ k_exact_all(const gsi_view V, const SRC src, size_t nq, double *val, int *leaf_o
     }
 }
 
-/* exact replay on the deferred list written by k_locate */
+/* exact replay on a deferred list (the one the walk kernels wrote, or what k_memo_list left of it) */
 template <class SRC>
 __global__ void __launch_bounds__(128, 4)
-k_exact_list(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, double *val,
+k_exact_list(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, int cnt_word, double *val,
              int *leaf_out, size_t ld, unsigned *counters)
 {
-  const unsigned count = min(counters[GSI_CNT_DEFERRED], list_cap);
+  const unsigned count = min(counters[cnt_word], list_cap);
   const unsigned stride = gridDim.x * blockDim.x;
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride)
     {
@@ -127,6 +146,47 @@ k_exact_list(const gsi_view V, const SRC src, const unsigned *list, unsigned lis
       src.get_linear(q, qx, qy);
       if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
         atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+    }
+}
+
+/* vertex-memo pass over the deferred list: a query that coincides with a data node gets its answer
+ * from the hash table; the others are compacted into list2 for the replay kernels.  (Probing inside
+ * the four-lane replay instead leaves the groups of a warp out of step with one another: measured
+ * 48 % slower on queries that miss, and no faster on a half-and-half mix, scripts/profile_cfg3_classes.py.) */
+template <class SRC>
+__global__ void __launch_bounds__(128)
+k_memo_list(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, unsigned *list2, double *val,
+            int *leaf_out, size_t ld, unsigned *counters)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned count = min(counters[GSI_CNT_DEFERRED], list_cap);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned t0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); t0 < count; t0 += stride)
+    {
+      const unsigned t = t0 + lane;
+      bool miss = false;
+      unsigned qi = 0;
+      if (t < count)
+        {
+          qi = list[t];
+          double qx, qy;
+          src.get_linear((size_t) qi, qx, qy);
+          int mnode, mslot;
+          if (gsi_memo_find(&V, qx, qy, &mnode, &mslot))
+            memo_answer(V, mnode, mslot, qx, qy, val, leaf_out, ld, (size_t) qi);
+          else
+            miss = true;
+        }
+      const unsigned mm = __ballot_sync(FULL, miss);
+      if (mm)
+        {
+          const int leader = __ffs(mm) - 1;
+          unsigned pos = 0;
+          if (lane == (unsigned) leader) pos = atomicAdd(counters + GSI_CNT_DEFERRED2, (unsigned) __popc(mm));
+          pos = __shfl_sync(FULL, pos, leader);
+          if (miss) list2[pos + __popc(mm & ((1u << lane) - 1u))] = qi;
+        }
     }
 }
 
@@ -151,7 +211,10 @@ k_exact_overflow(const gsi_view V, const SRC src, size_t nq, unsigned *mask, dou
           const size_t q = (w << 5) + (size_t) b;
           double qx, qy;
           src.get_linear(q, qx, qy);
-          if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
+          int mnode, mslot;
+          if (gsi_memo_find(&V, qx, qy, &mnode, &mslot))
+            memo_answer(V, mnode, mslot, qx, qy, val, leaf_out, ld, q);
+          else if (gsi_exact_one(&V, qx, qy, val, leaf_out, ld, q) < 0)
             atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
         }
     }
@@ -295,7 +358,7 @@ descend4(const gsi_view &V, unsigned gmask, int gbase, int sub, int start, doubl
 }
 
 /* one deferred query per group of four lanes; lane 0 of the group writes the result */
-template <class SRC>
+template <bool MEMO, class SRC>
 __device__ __forceinline__ void
 exact_one4(const gsi_view &V, const SRC &src, size_t q, double *val, int *leaf_out, size_t ld, unsigned *counters,
            unsigned gmask, int gbase, int sub)
@@ -303,6 +366,17 @@ exact_one4(const gsi_view &V, const SRC &src, size_t q, double *val, int *leaf_o
   double qx, qy, c0 = 0, c1 = 0;
   src.get_linear(q, qx, qy);
   int slot = 0;
+  if (MEMO)
+    {
+    /* a query that coincides with a data node: the four lanes probe the memo alike (overflow path only:
+       the list kernels run behind k_memo_list) */
+    int mnode, mslot;
+    if (gsi_memo_find(&V, qx, qy, &mnode, &mslot))
+      {
+        if (sub == 0) memo_answer(V, mnode, mslot, qx, qy, val, leaf_out, ld, q);
+        return;
+      }
+  }
   const int start = V.entry ? GSI_LDG(V.entry + gsi_cell_of(&V, qx, qy)) : 0;
   const int node = descend4(V, gmask, gbase, sub, start, qx, qy, &c0, &c1, &slot);
   if (sub != 0) return;
@@ -325,16 +399,16 @@ exact_one4(const gsi_view &V, const SRC &src, size_t q, double *val, int *leaf_o
 
 template <class SRC>
 __global__ void __launch_bounds__(128, 8)
-k_exact_list4(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, double *val, int *leaf_out,
-              size_t ld, unsigned *counters)
+k_exact_list4(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, int cnt_word, double *val,
+              int *leaf_out, size_t ld, unsigned *counters)
 {
-  const unsigned count = min(counters[GSI_CNT_DEFERRED], list_cap);
+  const unsigned count = min(counters[cnt_word], list_cap);
   const unsigned lane = threadIdx.x & 31u;
   const int sub = (int) (lane & 3u), gbase = (int) (lane & ~3u);
   const unsigned gmask = 0xfu << gbase;
   const unsigned n_groups = (gridDim.x * blockDim.x) >> 2;
   for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; g < count; g += n_groups)
-    exact_one4(V, src, (size_t) list[g], val, leaf_out, ld, counters, gmask, gbase, sub);
+    exact_one4<false>(V, src, (size_t) list[g], val, leaf_out, ld, counters, gmask, gbase, sub);
 }
 
 /* exact replay of the queries marked in the overflow bitmask, four lanes per query: a warp takes 32
@@ -373,7 +447,7 @@ k_exact_overflow4(const gsi_view V, const SRC src, size_t nq, unsigned *mask, do
           const unsigned sl = srcl < 32u ? srcl : 0u;
           const unsigned b = __shfl_sync(FULL, bit, (int) sl);
           if (srcl < 32u)
-            exact_one4(V, src, ((w0 + sl) << 5) + (size_t) b, val, leaf_out, ld, counters, gmask, gbase, sub);
+            exact_one4<true>(V, src, ((w0 + sl) << 5) + (size_t) b, val, leaf_out, ld, counters, gmask, gbase, sub);
         }
     }
 }
@@ -442,6 +516,34 @@ k_entry_cells(const gsi_view V, int32_t *entry)
   const size_t stride = (size_t) gridDim.x * blockDim.x;
   for (size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += stride)
     entry[q] = gsi_entry_of_cell(&V, q);
+}
+
+/* vertex memo: the exact replay's answer for every key the flattener wrote (gsi_layout.h) */
+__global__ void __launch_bounds__(128)
+k_memo_fill(const gsi_view V, gsi_memo *memo)
+{
+  const size_t n = (size_t) V.memo_mask + 1;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+      gsi_memo *e = memo + i;
+      if (e->state != GSI_MEMO_PENDING) continue;
+      const double qx = e->x, qy = e->y;
+      double c0 = 0, c1 = 0;
+      int last = -1;
+      gsi_rec lr;
+      const int start = V.entry ? GSI_LDG(V.entry + gsi_cell_of(&V, qx, qy)) : 0;
+      const int node = gsi_descend(V.dag, &V.xf, start, qx, qy, &c0, &c1, &last, &lr, 0);
+      /* a singular leaf keeps the descent's stale coordinates (linear_simplex.c:641-642): not memoised */
+      if (node < 0 || (lr.meta & GSI_META_SINGULAR))
+        e->state = GSI_MEMO_SKIP;
+      else
+        {
+          e->node = node;
+          e->slot = lr.lnk[0];
+          e->state = GSI_MEMO_FULL;
+        }
+    }
 }
 
 /* rare: the deferred list is full -- mark the query in the overflow bitmask; k_exact_overflow
@@ -1002,7 +1104,7 @@ template <class SRC, bool STATS, bool ONE_FIELD>
 __global__ void __launch_bounds__(GSI_WALKC_THREADS, 1024 / GSI_WALKC_THREADS)
 k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsigned chunk, double *val, int *leaf_out,
         size_t ld, unsigned *list, unsigned list_cap, unsigned *ovf_mask, unsigned *counters,
-        int max_steps, int dynamic, unsigned long long *trace)
+        int max_steps, int dynamic, int l1_alloc, unsigned long long *trace)
 {
   __shared__ __align__(16) unsigned char stage_all[(GSI_WALKC_THREADS / 32) * 32 * GSI_WALKC_PITCH];
   __shared__ int sbase[GSI_WALKC_SBASE]; /* the seed-block bases: at most 4 KB */
@@ -1070,7 +1172,13 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
             {
               const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
               const unsigned d = stage + qq * GSI_WALKC_PITCH + (lane & 7u) * 16u;
-              asm volatile("cp.async." GSI_WALKC_CP ".shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+              /* .cg: the line goes to shared memory only (best when every visit is a miss anyway);
+                 .ca: it also allocates in L1, which takes the pressure off the L2 slice that owns a
+                 HOT leaf (cage leaves, the big leaves of sparse regions): launch_eval picks */
+              if (l1_alloc)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+              else
+                asm volatile("cp.async." GSI_WALKC_CP ".shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
             }
         }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -2215,6 +2323,7 @@ k_validate_slab(const gsi_view V, unsigned long long n_points, unsigned long lon
   if ((size_t) V.n_leaves > n) n = (size_t) V.n_leaves;
   if (cells > n) n = cells;
   if (nt1 > n) n = nt1;
+  if (V.memo && (size_t) V.memo_mask + 1 > n) n = (size_t) V.memo_mask + 1;
   unsigned long long mine = 0;
   const size_t stride = (size_t) gridDim.x * blockDim.x;
   for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -2248,6 +2357,12 @@ k_validate_slab(const gsi_view V, unsigned long long n_points, unsigned long lon
               mine += (unsigned) (V.seedbase[(iy >> V.seed_shift) * (size_t) V.grid_gb + (ix >> V.seed_shift)] + (int) off) >= (unsigned) V.n_leaves;
           }
           if (V.entry) mine += (unsigned) V.entry[i] >= (unsigned) V.n_dag;
+        }
+      if (V.memo && i <= (size_t) V.memo_mask)
+        {
+          const gsi_memo *e = V.memo + i;
+          mine += e->state > GSI_MEMO_SKIP
+                  || (e->state == GSI_MEMO_FULL && ((unsigned) e->node >= (unsigned) V.n_dag || (unsigned) e->slot >= (unsigned) V.n_leaves));
         }
       if (i < nt1)
         {
@@ -2363,6 +2478,7 @@ k_accumulate_deferred(unsigned *counters)
   *tot += c;
   counters[GSI_CNT_OVERFLOW] = 0;
   counters[GSI_CNT_WORK] = 0;
+  counters[GSI_CNT_DEFERRED2] = 0;
 }
 
 inline int
@@ -2513,6 +2629,9 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
                                : (size_t) ctas);
       if (cfg.walk_variant == 2 && V.leaf_stride == 128)
         {
+          /* leaf lines through L1?  Yes when the whole leaf section is small enough for hot leaves to matter
+             more than the L1 space of the in-flight misses (profiles/r2z_*): up to 64 MB of records */
+          const int l1_alloc = cfg.walk_l1 >= 0 ? cfg.walk_l1 : ((size_t) V.n_leaves * 128u <= ((size_t) 64 << 20));
           const int wpc = GSI_WALKC_THREADS / 32; /* warps per CTA */
           const int ctas_c = GSI_WALKC_THREADS == 128 ? cfg.sm_count * (cfg.walk_ctas_per_sm > 5 ? cfg.walk_ctas_per_sm : 8)
                                                       : cfg.sm_count * (1024 / GSI_WALKC_THREADS);
@@ -2532,7 +2651,7 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
       k_walkc<SRC, STATS, ONE><<<gc, GSI_WALKC_THREADS, 0, st>>>(V, CM, src, nq, (unsigned) chunk, val, leaf_out, \
                                                                 ld, cfg.list, list_cap, cfg.ovf_mask,      \
                                                                 cfg.counters, cfg.max_steps, cfg.walk_dynamic, \
-                                                                trace);                                    \
+                                                                l1_alloc, trace);                          \
     }                                                                                           \
   while (0)
           if (cfg.stats && V.n_fields == 1) GSI_LAUNCH_WALKC(true, true);
@@ -2610,10 +2729,18 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (cfg.ev_exact0) cudaEventRecord(cfg.ev_exact0, st);
+  const unsigned *rlist = cfg.list;
+  int cnt_word = GSI_CNT_DEFERRED;
+  if (V.memo && cfg.list2)
+    {
+      k_memo_list<SRC><<<cfg.sm_count * 8, 128, 0, st>>>(V, src, cfg.list, list_cap, cfg.list2, val, leaf_out, ld, cfg.counters);
+      rlist = cfg.list2;
+      cnt_word = GSI_CNT_DEFERRED2;
+    }
   if (cfg.exact_coop)
-    k_exact_list4<SRC><<<cfg.sm_count * 8, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld, cfg.counters);
+    k_exact_list4<SRC><<<cfg.sm_count * 8, 128, 0, st>>>(V, src, rlist, list_cap, cnt_word, val, leaf_out, ld, cfg.counters);
   else
-    k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, cfg.list, list_cap, val, leaf_out, ld,
+    k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, rlist, list_cap, cnt_word, val, leaf_out, ld,
                                                         cfg.counters);
   if (cfg.exact_coop)
     k_exact_overflow4<SRC><<<cfg.sm_count * 8, 128, 0, st>>>(V, src, nq, cfg.ovf_mask, val, leaf_out, ld, cfg.counters);
@@ -2669,6 +2796,14 @@ gsi_launch_entry_cells(const gsi_view &V, int32_t *entry, int sm_count, cudaStre
 {
   const size_t ncell = (size_t) V.grid_g * V.grid_g;
   k_entry_cells<<<grid_for(ncell, 128, sm_count, 16), 128, 0, st>>>(V, entry);
+  return cudaGetLastError();
+}
+
+cudaError_t
+gsi_launch_memo_fill(const gsi_view &V, gsi_memo *memo, int sm_count, cudaStream_t st)
+{
+  if (!V.memo) return cudaSuccess;
+  k_memo_fill<<<grid_for((size_t) V.memo_mask + 1, 128, sm_count, 16), 128, 0, st>>>(V, memo);
   return cudaGetLastError();
 }
 

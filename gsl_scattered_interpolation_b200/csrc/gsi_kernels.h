@@ -23,6 +23,7 @@
 #define GSI_CNT_STEPS 4          /* u64: walk steps of accepted queries (stats launches only) */
 #define GSI_CNT_OVERFLOW 8       /* u32: deferred queries of the current launch that did not fit the list */
 #define GSI_CNT_WORK 9           /* u32: chunk counter of k_walkp (zero between launches) */
+#define GSI_CNT_DEFERRED2 10     /* u32: deferred queries left after the vertex-memo pass (zero between launches) */
 #define GSI_CNT_WORDS 16
 
 #define GSI_MODE_FAST 0  /* grid-seeded walk + exact replay of the deferred queries */
@@ -68,11 +69,13 @@ struct gsi_launch_cfg
   int walk_variant = 2;  /* 0 = k_walk, 1 = k_walkp (two walks per lane in rotation behind L2 prefetches),
                             2 = k_walkc (warp-cooperative cp.async staging; needs 128-byte leaf records) */
   int walk_dynamic = 1;  /* k_walkp: chunks dealt by a device counter (0: round-robin) */
+  int walk_l1 = -1;       /* k_walkc: leaf lines allocate in L1 (cp.async.ca) 1, not (cp.async.cg) 0, -1 = by structure size */
   int walk_carveout = -1; /* k_walkc / k_walkf: cudaFuncAttributePreferredSharedMemoryCarveout in percent, -1 = default */
   int walk_pf = 1;       /* k_walkp: how the next leaf line is requested ahead (gsi_prefetch_leaf_l2) */
   unsigned long long *walk_trace = nullptr; /* k_walkp / k_walkc: 4 words per CTA {smid, start ns, end ns, queries}, zeroed here */
   size_t walk_trace_ctas = 0;               /* CTAs the trace buffer has room for */
   unsigned *list = nullptr;     /* deferred list, list_capacity entries */
+  unsigned *list2 = nullptr;    /* list_capacity entries more: what is left of the list after the vertex-memo pass */
   size_t list_capacity = 0;     /* deferred-list entries; overflow goes to the bitmask */
   unsigned *ovf_mask = nullptr; /* one bit per query of a launch (zero between launches) */
   unsigned *counters = nullptr; /* GSI_CNT_WORDS words */
@@ -97,6 +100,8 @@ cudaError_t gsi_launch_eval_raster(const gsi_view &V, double x0, double dx, doub
 cudaError_t gsi_launch_seed_cells(const gsi_view &V, int32_t *seeds, int sm_count,
                                   cudaStream_t st);
 
+/* vertex memo: answers of the exact replay for the keys the flattener wrote; run after the entry nodes */
+cudaError_t gsi_launch_memo_fill(const gsi_view &V, gsi_memo *memo, int sm_count, cudaStream_t st);
 /* fill the compact seed table (seed16 + seedbase) from the int32 seeds; run after the seeding */
 cudaError_t gsi_launch_pack_seeds(const gsi_view &V, const int32_t *seeds, uint16_t *seed16, int32_t *seedbase,
                                   int sm_count, cudaStream_t st);

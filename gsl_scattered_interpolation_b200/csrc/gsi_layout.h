@@ -33,6 +33,14 @@
  *                               leaves whose key starts with the P-bit prefix t are the slot
  *                               range [tiles[t], tiles[t+1]): a spatial tile whose records can be
  *                               staged in shared memory with one contiguous copy (reorder pipeline)
+ *   memo     gsi_memo[2^m]      open-addressing hash table keyed by the BIT PATTERN of a data node's raw
+ *                               coordinates: the exact replay's answer (leaf node id + slot) for a query
+ *                               that coincides with that node, computed once at init by the exact replay
+ *                               itself (k_memo_fill).  Such queries can never be accepted by the fast path
+ *                               (two weights are within rounding of 0) and their leaf is history-dependent;
+ *                               evaluating an interpolant AT its nodes is a common workload (residuals,
+ *                               BASELINE.json configs[2]).  The deferred-query kernels probe it before they
+ *                               descend the DAG; k_exact_all (the verification path) never does.
  *   entry    int32[G*G]         per grid cell, the deepest history-DAG node that the reference's
  *                               descent provably passes through for EVERY point of the cell
  *                               (0 = root): where the exact replay of a query of that cell
@@ -49,7 +57,7 @@
 #include "gsi_core.h"
 
 #define GSI_SLAB_MAGIC 0x3142414c53495347ull /* "GSISLAB1" */
-#define GSI_SLAB_VERSION 6u
+#define GSI_SLAB_VERSION 7u
 #define GSI_SEED_GB_MAX 32 /* seed blocks per side: the base table is at most 32 x 32 x 4 = 4 KB */
 #define GSI_SEED16_ESC 0xffffu
 
@@ -83,6 +91,21 @@ typedef struct
   gsi_leaf_tail t;
 } gsi_leaf;
 
+#define GSI_MEMO_EMPTY 0u   /* ends a probe sequence */
+#define GSI_MEMO_FULL 1u    /* key and answer */
+#define GSI_MEMO_PENDING 2u /* key written by the flattener, answer not yet filled in on the device */
+#define GSI_MEMO_SKIP 3u    /* key without an answer (outside the cage / singular leaf): keep probing */
+#define GSI_MEMO_MAX_PROBES 64
+
+typedef struct
+{
+  uint32_t state;
+  int32_t node; /* reference simplex_index of the leaf */
+  double x, y;  /* raw coordinates of the data node (compared bit for bit) */
+  int32_t slot; /* the leaf's compact slot */
+  uint32_t pad;
+} gsi_memo;
+
 typedef struct
 {
   uint64_t magic;
@@ -99,14 +122,15 @@ typedef struct
   double delta; /* absolute safety margin (standardised units) behind the per-leaf tau */
   uint64_t off_dag, off_leaf, off_z, off_seeds;
   uint64_t total_bytes;
-  uint64_t reserved[2]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
+  uint64_t reserved[1]; /* [0] = image checksum in files (gsl_scattered_cuda_fwrite) */
+  uint64_t off_memo;    /* gsi_memo[2^memo_bits] (memo_bits = 0: no memo) */
   uint64_t off_seed16;  /* uint16[grid_g^2] */
   uint64_t off_seedbase; /* int32[ceil(grid_g / 2^seed_shift)^2] */
   uint32_t tile_bits;       /* tiles = the 2^tile_bits prefixes of the leaves' 32-bit Morton keys */
   uint32_t tile_max_leaves; /* largest tile */
   uint64_t off_tiles;       /* int32[2^tile_bits + 1]: first leaf slot of every tile */
   uint32_t seed_shift;      /* seed blocks are 2^seed_shift cells wide (>= 3) */
-  uint32_t reserved2;
+  uint32_t memo_bits;
   uint64_t off_entry;
 } gsi_slab_header;
 
@@ -137,6 +161,8 @@ typedef struct
   const int32_t *seedbase;
   const int32_t *entry; /* NULL: exact replay always starts at the root */
   const int32_t *tiles; /* first leaf slot per Morton-prefix tile, 2^tile_bits + 1 entries */
+  const gsi_memo *memo; /* NULL: no vertex memo */
+  uint32_t memo_mask;   /* entries - 1 */
   int32_t tile_bits;
   double u0, v0, inv_du, inv_dv;
   double delta;
@@ -179,6 +205,8 @@ gsi_view_of(const void *slab_base, const gsi_slab_header *h)
   v.entry = (const int32_t *) (b + h->off_entry);
   v.tiles = (const int32_t *) (b + h->off_tiles);
   v.tile_bits = (int32_t) h->tile_bits;
+  v.memo = h->memo_bits ? (const gsi_memo *) (b + h->off_memo) : (const gsi_memo *) 0;
+  v.memo_mask = h->memo_bits ? (((uint32_t) 1) << h->memo_bits) - 1u : 0u;
   v.delta = h->delta;
   v.u0 = h->u0; v.v0 = h->v0; v.inv_du = h->inv_du; v.inv_dv = h->inv_dv;
   v.grid_g = (int32_t) h->grid_g;

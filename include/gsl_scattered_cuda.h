@@ -88,7 +88,12 @@ int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_
  * "walk_ctas_per_sm", "walk_chunk", "kernel" (0 = k_walk, 1 = k_locate, 2 = k_walk for query
  * arrays and k_locate for rasters, default), "leaf_stride" (96 or 128), "l2_fetch".
  * Exact replay: "exact_entry" (1 = start at the grid cell's certified entry node, default;
- * 0 = at the root; may be changed at any time).
+ * 0 = at the root; may be changed at any time); "vertex_memo" (1 = keep the exact answers for
+ * queries that coincide bit for bit with a data node in a hash table built at init, default;
+ * before init/upload); "exact_coop" (1 = four lanes per deferred query, default).
+ * Walk kernel: "walk_variant" (2 = k_walkc, default; 3 = k_walkf; 0 / 1 = the round-1 kernels),
+ * "walk_carveout" (preferred shared-memory carve-out of the walk kernel in percent, default 72;
+ * -1 = the driver's choice).
  * Reorder pipeline for incoherent query arrays (chunk-local counting sort by spatial tile ->
  * tile-major walk out of TMA-staged shared memory -> inverse permutation): "reorder" (0 = off,
  * default; 1 = always; 2 = auto: batches of at least "reorder_min" queries (2^24) with at most

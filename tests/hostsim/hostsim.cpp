@@ -22,6 +22,7 @@ struct hostsim
   std::vector<char> image;
   gsi_slab_header hdr;
   gsi_view view;
+  mutable long long memo_hits = 0; /* deferred queries answered from the vertex memo */
 };
 
 extern "C" {
@@ -63,6 +64,29 @@ hostsim_create(const double *xa, const double *ya, const double *za, size_t n, s
     for (size_t c = 0; c < ncell; c++) entry[c] = gsi_entry_of_cell(&h->view, c);
   else
     h->view.entry = nullptr;
+  /* what k_memo_fill does on the device */
+  if (h->hdr.memo_bits)
+    {
+      gsi_memo *memo = (gsi_memo *) (h->image.data() + h->hdr.off_memo);
+      for (size_t i = 0; i <= (size_t) h->view.memo_mask; i++)
+        {
+          gsi_memo *e = memo + i;
+          if (e->state != GSI_MEMO_PENDING) continue;
+          double c0 = 0, c1 = 0;
+          int last = -1;
+          gsi_rec lr;
+          const int start = h->view.entry ? h->view.entry[gsi_cell_of(&h->view, e->x, e->y)] : 0;
+          const int node = gsi_descend(h->view.dag, &h->view.xf, start, e->x, e->y, &c0, &c1, &last, &lr, 0);
+          if (node < 0 || (lr.meta & GSI_META_SINGULAR))
+            e->state = GSI_MEMO_SKIP;
+          else
+            {
+              e->node = node;
+              e->slot = lr.lnk[0];
+              e->state = GSI_MEMO_FULL;
+            }
+        }
+    }
   /* what k_seed_cells does on the device */
   int32_t *seeds = (int32_t *) (h->image.data() + h->hdr.off_seeds);
   for (size_t c = 0; c < ncell; c++)
@@ -121,6 +145,7 @@ hostsim_seed_escapes(const hostsim *h)
   return n;
 }
 int hostsim_seed_shift(const hostsim *h) { return (int) h->hdr.seed_shift; }
+long long hostsim_memo_hits(const hostsim *h) { return h->memo_hits; }
 size_t hostsim_n_leaves(const hostsim *h) { return (size_t) h->hdr.n_leaves; }
 size_t hostsim_grid_g(const hostsim *h) { return (size_t) h->hdr.grid_g; }
 const int32_t *hostsim_tiles(const hostsim *h) { return (const int32_t *) (h->image.data() + h->hdr.off_tiles); }
@@ -152,7 +177,25 @@ hostsim_eval(const hostsim *h, const double *xq, const double *yq, size_t nq, do
         deferred.push_back(q);
     }
   for (size_t q : deferred)
-    if (gsi_exact_one(&h->view, xq[q], yq[q], zq, leaf, nq, q) < 0) stats[2]++;
+    {
+      /* the deferred-query kernels probe the vertex memo first (memo_answer in gsi_kernels.cu) */
+      int mnode, mslot;
+      if (gsi_memo_find(&h->view, xq[q], yq[q], &mnode, &mslot))
+        {
+          const gsi_leaf *lf = gsi_leaf_at(&h->view, mslot);
+          gsi_rec r;
+          gsi_fetch_rec(&r, lf);
+          double c0, c1;
+          gsi_solve(&h->view.xf, &r, (int) (r.meta >> 31), xq[q], yq[q], &c0, &c1);
+          gsi_leaf_tail t;
+          gsi_fetch_tail(&t, lf);
+          if (leaf) leaf[q] = mnode;
+          if (zq) gsi_blend_store(&h->view, &t, c0, c1, zq, nq, q);
+          h->memo_hits++;
+        }
+      else if (gsi_exact_one(&h->view, xq[q], yq[q], zq, leaf, nq, q) < 0)
+        stats[2]++;
+    }
   stats[0] = (long long) deferred.size();
   return 0;
 }

@@ -40,6 +40,8 @@ def lib():
         H.hostsim_seed_escapes.restype = c_size_t
         H.hostsim_seed_escapes.argtypes = [c_void_p]
         H.hostsim_seed_shift.restype = c_int
+        H.hostsim_memo_hits.restype = ctypes.c_longlong
+        H.hostsim_memo_hits.argtypes = [c_void_p]
         H.hostsim_seed_shift.argtypes = [c_void_p]
         H.hostsim_grid_g.argtypes = [c_void_p]
         H.hostsim_build_batched_equal.restype = c_int
@@ -89,6 +91,10 @@ class HostSim:
     def seed_table(self):
         """(grid side, log2 of the seed-block width, cells that escape to the int32 table)"""
         return (self.H.hostsim_grid_g(self.h), self.H.hostsim_seed_shift(self.h), self.H.hostsim_seed_escapes(self.h))
+
+    def memo_hits(self):
+        """deferred queries answered from the vertex memo so far"""
+        return int(self.H.hostsim_memo_hits(self.h))
 
     def node_is_leaf(self, node):
         return bool(self.H.hostsim_node_is_leaf(self.h, int(node)))

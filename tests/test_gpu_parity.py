@@ -221,6 +221,29 @@ def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel, extra):
     w.free()
 
 
+@pytest.mark.parametrize("F,coop", [(1, 1), (3, 1), (3, 0)])
+def test_vertex_memo_answers_queries_at_data_nodes(golden, F, coop):
+    """queries that coincide with data nodes are answered from the hash table the exact replay filled at
+    init: same leaf ids and value bits as the replay itself (memo off, and mode 1 which never probes it),
+    through the list kernels and, with a tiny list, through the overflow bitmask"""
+    n = 3000
+    xa, ya = synth.clustered_nodes(n)
+    za = synth.values(n, F)
+    order = g.shuffle_mt19937(synth.SEED_SHUFFLE, n)
+    xm, ym = synth.mixed_queries(20000, xa, ya, golden["cfg3_leaf_rows"])
+    xq, yq = np.concatenate([xa, xm, xa[::-1]]), np.concatenate([ya, ym, ya[::-1]])
+    ref = make(xa, ya, za, g.DEFAULT, order, mode=1)
+    st, zr, lr = ref.eval_e(xq, yq)
+    for extra in ({}, {"vertex_memo": 0}, {"list_fraction": 1e-4}):
+        w = make(xa, ya, za, g.DEFAULT, order, exact_coop=coop, **extra)
+        st, zq, leaf = w.eval_e(xq, yq)
+        assert np.array_equal(leaf, lr), extra
+        assert refimpl.same_bits(zq, zr), extra
+        assert w.info()["n_deferred"] >= 2 * 0.95 * n
+        w.free()
+    ref.free()
+
+
 @pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_raster_odd_shapes_and_chunking(golden, kernel):
     """rasters whose sides are not multiples of the 8 x 32 launch tile, evaluated in several

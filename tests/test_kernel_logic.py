@@ -53,6 +53,16 @@ def test_logic_config3_mixed_golden(golden, mode):
     leaf, val, st = hs.eval(xq, yq, mode)
     assert np.array_equal(leaf, golden["cfg3_leaf"])
     assert refimpl.same_bits(val, golden["cfg3_val"])
+    if mode == 0:
+        # the 10 % of queries that coincide with data nodes are answered from the vertex memo
+        # (built by the exact replay at init), the on-edge ones by the replay itself
+        assert 0.08 * len(xq) < hs.memo_hits() <= st["deferred"]
+        # ... and every data node, queried directly, hits the memo with the replay's own answer
+        before = hs.memo_hits()
+        l0, v0, s0 = hs.eval(xa, ya, 0)
+        l1, v1, _ = hs.eval(xa, ya, 1)
+        assert hs.memo_hits() - before == s0["deferred"] >= 0.95 * n
+        assert np.array_equal(l0, l1) and refimpl.same_bits(v0, v1)
     hs.close()
 
 
