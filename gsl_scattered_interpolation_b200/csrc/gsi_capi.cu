@@ -273,7 +273,8 @@ struct gsl_scattered_cuda
   int reorder_chunk = GSI_BIN_CHUNK_MAX, tile_ranges = 0, tile_threads = GSI_TILE_THREADS;
   size_t reorder_max_fields = 2;
   int exact_entry = 1; /* exact replay starts at the cell's certified entry node (0: at the root) */
-  int exact_coop = 1;  /* deferred queries are replayed by four lanes each (0: one thread each) */
+  int exact_coop = 1;  /* deferred queries are replayed by four lanes each (1, default; 2 = groups refilled as they
+                          finish: measured slower; 0 = one thread each) */
   int walk_variant = 2; /* 1: k_walkp (two walks per lane in rotation behind L2 prefetches), 0: k_walk */
   int walk_dynamic = 1; /* k_walkp draws its chunks from a device counter (0: round-robin) */
   int walk_l1 = -1;       /* k_walkc: cp.async.ca (1) / .cg (0) for the leaf lines, -1 = by structure size */
@@ -1326,7 +1327,7 @@ gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double val
   else if (k == "tile_leaves" && value >= 1) w->fprm.tile_leaves = (uint32_t) value;
   else if (k == "vmm" && (value == 0 || value == 1)) w->vmm = (int) value;
   else if (k == "build_device" && (value == 0 || value == 1)) w->build_device = (int) value;
-  else if (k == "exact_coop" && (value == 0 || value == 1)) w->exact_coop = (int) value;
+  else if (k == "exact_coop" && (value == 0 || value == 1 || value == 2)) w->exact_coop = (int) value;
   else if (k == "walk_variant" && value >= 0 && value <= 3) w->walk_variant = (int) value;
   else if (k == "walk_dynamic" && (value == 0 || value == 1)) w->walk_dynamic = (int) value;
   else if (k == "walk_carveout" && value >= -1 && value <= 100) w->walk_carveout = (int) value;

@@ -411,6 +411,200 @@ k_exact_list4(const gsi_view V, const SRC src, const unsigned *list, unsigned li
     exact_one4<false>(V, src, (size_t) list[g], val, leaf_out, ld, counters, gmask, gbase, sub);
 }
 
+#ifndef GSI_EXACT4P_CTAS
+#define GSI_EXACT4P_CTAS 7 /* 72 registers: no spills */
+#endif
+/* ---- exact replay, four lanes per query, groups refilled as they finish (exact_coop = 2, opt-in) ----
+ * In k_exact_list4 the eight groups of a warp start a query together and the warp moves on when the
+ * LAST of the eight descents ends: descents differ in length (the deferred queries of a mixed workload
+ * take 10 to 40 levels from their entry nodes), so on average only 4.3 of the 8 groups are at work
+ * (12.8 active lanes per instruction, ncu).  Here every trip of the loop is ONE level for whatever query
+ * each group holds; a group whose query reached its leaf writes the result and takes the next entry of
+ * the list at once.  A fresh query enters as a level with a single virtual child, its entry node: the
+ * same fetch / solve / ballot instructions as a real level, so fresh and running groups stay in step.
+ * Semantics: those of descend4 / GSI_DEFINE_DESCEND, statement for statement (first passing child in
+ * link order, best-worst fallback with the stale-coordinate rule, singular or link-0 children fail
+ * without a test, link 0 re-enters the root); the tests compare it with the one-thread replay.
+ * Measured (scripts/gpu_r2_aa.sh, config 3): exact, but SLOWER than k_exact_list4 (1.97 vs 1.48 ms per 10^6
+ * descents, 6 / 7 / 8 CTAs per SM alike): the refill and the leaf paths (dependent loads) run while the other
+ * groups of the warp wait, once per trip instead of once per query.  Kept opt-in. */
+template <class SRC>
+__global__ void __launch_bounds__(128, GSI_EXACT4P_CTAS)
+k_exact_list4p(const gsi_view V, const SRC src, const unsigned *list, unsigned list_cap, int cnt_word, double *val,
+               int *leaf_out, size_t ld, unsigned *counters)
+{
+  const unsigned FULL = 0xffffffffu;
+  const unsigned count = min(counters[cnt_word], list_cap);
+  const unsigned lane = threadIdx.x & 31u;
+  const int sub = (int) (lane & 3u), gbase = (int) (lane & ~3u);
+  const unsigned gmask = 0xfu << gbase;
+  const unsigned n_groups = (gridDim.x * blockDim.x) >> 2;
+  const gsi_rec *dag = V.dag;
+  const gsi_xform *t = &V.xf;
+  unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+
+  bool have = false, fresh = false;
+  size_t q = 0;
+  double qx = 0, qy = 0, c0 = 0, c1 = 0;
+  int node = 0, last = -1, holder = 0, guard = 0, k0 = 0, k1 = 0, k2 = 0;
+  uint32_t meta = 0;
+  gsi_rec r; /* the record this lane fetched last: the current node's in lane `holder` */
+  r.meta = GSI_META_SINGULAR;
+  for (;;)
+    {
+      if (!have && g < count)
+        {
+          q = (size_t) list[g];
+          g += n_groups;
+          src.get_linear(q, qx, qy);
+          /* a virtual node whose only child is the entry node of the query's cell */
+          k0 = V.entry ? GSI_LDG(V.entry + gsi_cell_of(&V, qx, qy)) : 0;
+          k1 = k2 = 0;
+          c0 = c1 = 0;
+          last = -1;
+          node = -1;
+          guard = 0;
+          have = fresh = true;
+        }
+      if (!__any_sync(FULL, have)) break;
+      if (!have) continue;
+
+      const uint32_t type = meta & GSI_META_TYPE_MASK;
+      if (!fresh && type == GSI_LEAF)
+        {
+          /* interp_point solves the leaf again unless it is singular or was solved last */
+          if (!(meta & GSI_META_SINGULAR) && last != node)
+            {
+              double a, b;
+              gsi_solve(t, &r, (int) (r.meta & GSI_META_SWAP), qx, qy, &a, &b); /* meaningful in lane `holder` */
+              c0 = shfl_f64(gmask, a, gbase + (holder & 3));
+              c1 = shfl_f64(gmask, b, gbase + (holder & 3));
+            }
+          if (sub == 0)
+            {
+              if (leaf_out) leaf_out[q] = node;
+              if (val)
+                {
+                  gsi_leaf_tail tl;
+                  gsi_fetch_tail(&tl, gsi_leaf_at(&V, k0)); /* a leaf's lnk[0] is its compact slot */
+                  gsi_blend_store(&V, &tl, c0, c1, val, ld, q);
+                }
+            }
+          have = false;
+          continue;
+        }
+      bool outside = !fresh && ++guard > GSI_MAX_DESCENT; /* GSI_DESCEND_LOOP */
+      const int nch = fresh ? 1 : ((type == GSI_SUB_DPLUS1) ? 3 : 2);
+      if (nch < 3) k2 = 0;
+      const int k = sub == 0 ? k0 : (sub == 1 ? k1 : k2);
+      const bool active = !outside && sub < nch && (fresh || k != 0);
+      bool valid = false;
+      double a = 0, b = 0;
+      int pass = 0;
+      if (active)
+        {
+          GSI_FETCH_DAG(r, k);
+          valid = !(r.meta & GSI_META_SINGULAR);
+          if (valid)
+            {
+              gsi_solve(t, &r, (int) (r.meta & GSI_META_SWAP), qx, qy, &a, &b);
+              /* find_leaf tests the root (linear_simplex.c:343-347); a later entry node is a node the
+                 descent is known to pass: it is taken with its coordinates, no test */
+              pass = (fresh && k != 0) ? 1 : gsi_inside(a, b);
+            }
+        }
+      const unsigned pm = (__ballot_sync(gmask, pass) >> gbase) & 0xfu;
+      int chosen = 0;
+      if (fresh)
+        {
+          /* singular entry record, or a root that does not contain the query: outside the cage */
+          if (!pm) outside = true;
+          else
+            {
+              c0 = shfl_f64(gmask, a, gbase);
+              c1 = shfl_f64(gmask, b, gbase);
+              node = k0;
+              last = node;
+            }
+        }
+      else if (outside)
+        ;
+      else if (pm)
+        {
+          /* first passing child in link order; the children behind it are never evaluated, so
+             accel->coords and `last` are this child's */
+          chosen = __ffs(pm) - 1;
+          c0 = shfl_f64(gmask, a, gbase + chosen);
+          c1 = shfl_f64(gmask, b, gbase + chosen);
+          node = chosen == 0 ? k0 : (chosen == 1 ? k1 : k2);
+          last = node;
+        }
+      else
+        {
+          /* no child passes: every child was evaluated in order; a child with link 0 or a singular
+             matrix leaves accel->coords as they were (linear_simplex.c:375-395 after :641-642) */
+          const unsigned vm = (__ballot_sync(gmask, valid) >> gbase) & 0xfu;
+          int best_match = 0;
+          double best_worst = -1;
+          double e0 = c0, e1 = c1;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+            {
+              const double ai = shfl_f64(gmask, a, gbase + i), bi = shfl_f64(gmask, b, gbase + i);
+              if (i < nch)
+                {
+                  if (vm & (1u << i))
+                    {
+                      e0 = ai;
+                      e1 = bi;
+                      last = i == 0 ? k0 : (i == 1 ? k1 : k2);
+                    }
+                  const double worst = gsi_worst(e0, e1);
+                  if ((best_worst < 0) || (worst < best_worst))
+                    {
+                      best_worst = worst;
+                      best_match = i;
+                    }
+                }
+            }
+          c0 = e0;
+          c1 = e1;
+          chosen = best_match;
+          node = chosen == 0 ? k0 : (chosen == 1 ? k1 : k2);
+        }
+      if (outside)
+        {
+          if (sub == 0)
+            {
+              if (leaf_out) leaf_out[q] = -1;
+              if (val)
+                for (int f = 0; f < V.n_fields; f++) val[(size_t) f * ld + q] = GSI_NAN;
+              atomicAdd(counters + GSI_CNT_OUTSIDE, 1u);
+            }
+          have = false;
+          continue;
+        }
+      if (node == 0 && !fresh)
+        {
+          /* link 0: the reference would re-enter the root */
+          GSI_FETCH_DAG(r, 0);
+          holder = sub;
+          k0 = r.lnk[0]; k1 = r.lnk[1]; k2 = r.lnk[2];
+          meta = r.meta;
+        }
+      else
+        {
+          /* the chosen child's record sits in lane `chosen`: its links and meta word to everyone */
+          holder = chosen;
+          k0 = __shfl_sync(gmask, r.lnk[0], gbase + chosen);
+          k1 = __shfl_sync(gmask, r.lnk[1], gbase + chosen);
+          k2 = __shfl_sync(gmask, r.lnk[2], gbase + chosen);
+          meta = (uint32_t) __shfl_sync(gmask, (int) r.meta, gbase + chosen);
+        }
+      fresh = false;
+    }
+}
+
 /* exact replay of the queries marked in the overflow bitmask, four lanes per query: a warp takes 32
  * mask words at a time (one per lane) and, round after round, the first eight lanes that still hold a
  * marked query hand one each to the warp's eight groups */
@@ -2737,7 +2931,9 @@ launch_eval(const gsi_view &V, const SRC &src, size_t nq, double *val, int *leaf
       rlist = cfg.list2;
       cnt_word = GSI_CNT_DEFERRED2;
     }
-  if (cfg.exact_coop)
+  if (cfg.exact_coop == 2)
+    k_exact_list4p<SRC><<<cfg.sm_count * GSI_EXACT4P_CTAS, 128, 0, st>>>(V, src, rlist, list_cap, cnt_word, val, leaf_out, ld, cfg.counters);
+  else if (cfg.exact_coop)
     k_exact_list4<SRC><<<cfg.sm_count * 8, 128, 0, st>>>(V, src, rlist, list_cap, cnt_word, val, leaf_out, ld, cfg.counters);
   else
     k_exact_list<SRC><<<cfg.sm_count * 4, 128, 0, st>>>(V, src, rlist, list_cap, cnt_word, val, leaf_out, ld,

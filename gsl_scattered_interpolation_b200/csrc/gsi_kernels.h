@@ -64,7 +64,8 @@ struct gsi_launch_cfg
   int locate_ctas_per_sm = 8;
   int kernel = GSI_KERNEL_AUTO;
   int walk_ctas_per_sm = 5;
-  int exact_coop = 1; /* deferred list: four lanes per query (k_exact_list4) instead of one thread (k_exact_list) */
+  int exact_coop = 1; /* deferred list: 1 = four lanes per query, eight queries per warp (k_exact_list4, default),
+                         2 = groups refilled as they finish (k_exact_list4p: measured slower), 0 = one thread (k_exact_list) */
   size_t walk_chunk = 0; /* 0 = derive from the launch size */
   int walk_variant = 2;  /* 0 = k_walk, 1 = k_walkp (two walks per lane in rotation behind L2 prefetches),
                             2 = k_walkc (warp-cooperative cp.async staging; needs 128-byte leaf records) */

@@ -221,7 +221,7 @@ def test_every_fast_path_kernel_on_the_golden_sets(golden, kernel, extra):
     w.free()
 
 
-@pytest.mark.parametrize("F,coop", [(1, 1), (3, 1), (3, 0)])
+@pytest.mark.parametrize("F,coop", [(1, 2), (3, 2), (1, 1), (3, 1), (3, 0)])
 def test_vertex_memo_answers_queries_at_data_nodes(golden, F, coop):
     """queries that coincide with data nodes are answered from the hash table the exact replay filled at
     init: same leaf ids and value bits as the replay itself (memo off, and mode 1 which never probes it),
