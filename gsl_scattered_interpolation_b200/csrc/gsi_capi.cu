@@ -134,6 +134,8 @@ struct eval_ctx
   unsigned *list = nullptr;
   size_t list_cap = 0;
   size_t list_want = 0; /* entries the last launches would have needed (read_counters): the list grows to it */
+  unsigned *h_deferred = nullptr; /* pinned: deferred count of the last launch, copied back behind it on its stream,
+                                     so that asynchronous callers (who never read the counters) size the list too */
   unsigned *ovf_mask = nullptr; /* overflow bitmask, one bit per query of a launch */
   size_t ovf_words = 0;
   unsigned *counters = nullptr;
@@ -454,6 +456,7 @@ free_ctx(eval_ctx *c)
   if (c->ovf_mask) cudaFree(c->ovf_mask);
   if (c->counters) cudaFree(c->counters);
   if (c->scratch2) cudaFree(c->scratch2);
+  if (c->h_deferred) cudaFreeHost(c->h_deferred);
   if (c->trace) cudaFree(c->trace);
   free_reorder(c);
   free_host_stage(c);
@@ -509,6 +512,8 @@ make_ctx(eval_ctx **out)
   CU(cudaMalloc(&c->counters, GSI_CNT_WORDS * sizeof(unsigned)));
   CU(cudaMemset(c->counters, 0, GSI_CNT_WORDS * sizeof(unsigned)));
   CU(cudaMalloc(&c->scratch2, 2 * sizeof(unsigned long long)));
+  CU(cudaMallocHost(&c->h_deferred, sizeof(unsigned)));
+  *c->h_deferred = 0;
   CU(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
   for (int b = 0; b < 2; b++)
     {
@@ -776,8 +781,14 @@ eval_on_device(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, const
     }
   if (w->mode == GSI_MODE_FAST)
     {
-      /* deferred list: a fraction of the launch size (overflow goes to a bitmask) */
+      /* deferred list: a fraction of the launch size (overflow goes to a bitmask), or what the last
+         launch on this context turned out to need (possibly still running: then the value is the one
+         before it, which is just as good a hint) */
       const size_t per_launch = std::min(chunk, nq);
+      {
+        const size_t seen = *(volatile unsigned *) c->h_deferred;
+        if (seen > c->list_cap) c->list_want = std::max(c->list_want, seen + seen / 4);
+      }
       const size_t want = std::max<size_t>(std::max<size_t>(std::min<size_t>(per_launch, 65536),
                                                             (size_t) (w->list_fraction * (double) per_launch)),
                                            std::min(c->list_want, per_launch));
@@ -818,6 +829,8 @@ eval_on_device(const gsl_scattered_cuda *w, const replica *r, eval_ctx *c, const
                                    d_leaf ? d_leaf + off : nullptr, ld, cfg, st);
       CU(e);
     }
+  if (w->mode == GSI_MODE_FAST)
+    CU(cudaMemcpyAsync(c->h_deferred, c->counters + GSI_CNT_DEFERRED, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
   return 0;
 }
 

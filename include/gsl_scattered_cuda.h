@@ -161,7 +161,11 @@ int gsl_scattered_cuda_eval_raster_e(const gsl_scattered_cuda *w, double x0, dou
 
 /* Same two entry points on DEVICE pointers of device `dev` (must be one of the selected
  * devices), asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the library's
- * own stream followed by a synchronize).  ld = leading dimension of d_zq (>= nq). */
+ * own stream followed by a synchronize).  ld = leading dimension of d_zq (>= nq).
+ * With a caller's stream the call returns as soon as the work is enqueued, hence always
+ * GSL_SCATTERED_SUCCESS for well-formed arguments: queries outside the cage then show up only as
+ * leaf -1 / NaN in the outputs and in gsl_scattered_cuda_info.n_outside (read it after
+ * synchronising the stream); GSL_SCATTERED_EDOM is reported by the synchronous form (NULL). */
 int gsl_scattered_cuda_eval_device_e(const gsl_scattered_cuda *w, int dev, const double *d_xq,
                                      const double *d_yq, size_t nq, double *d_zq, size_t ld,
                                      int *d_leaf, void *stream);
