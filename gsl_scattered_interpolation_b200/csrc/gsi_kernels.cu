@@ -1,23 +1,35 @@
 /* gsi_kernels.cu -- sm_100a kernels of libgsl_scattered_cuda.
  *
- *   k_walk         fast path for query arrays (default): a warp consumes a chunk of queries through
- *                  a warp-wide work queue, one walk step per iteration for whatever query each lane
- *                  holds.  Seed from the uniform grid, cross the edge with the most negative
- *                  barycentric weight, accept the leaf only when all three weights clear the leaf's
- *                  safety margin, then blend.  The weights are the reference's own
- *                  (calculate_bary_coords, linear_simplex.c:607-651), so an accepted result is
- *                  bit-identical to find_leaf + interp_point; everything else is deferred.
+ *   k_walkc        fast path for query arrays (default): lanes decoupled from queries by a warp-wide
+ *                  queue, one walk step per iteration for whatever query each lane holds; the WARP
+ *                  copies the 32 leaf records its lanes visit into shared memory (cp.async, one
+ *                  128-byte line per record), the seed-block bases sit in shared memory.  Seed from
+ *                  the uniform grid, cross the edge with the most negative barycentric weight,
+ *                  accept the leaf only when all three weights clear the leaf's safety margin, then
+ *                  blend.  The weights are the reference's own (calculate_bary_coords,
+ *                  linear_simplex.c:607-651), so an accepted result is bit-identical to find_leaf +
+ *                  interp_point; everything else is deferred.
+ *   k_walkf / k_walk / k_walkp
+ *                  opt-in variants of the same step (walk_variant 3 / 0 / 1): fresh batches + a ring
+ *                  of walkers; the round-1 kernel with per-lane 256-bit gathers; its prefetching form.
  *   k_locate       the same per-query logic, one thread per query over compact pixel tiles: the
  *                  default for rasters (coherent queries).
  *   k_exact_*      exact replay of find_leaf/_find_leaf (linear_simplex.c:331-402) on the flattened
  *                  history DAG + interp_point (linear_simplex.c:678-711): the reference's
  *                  edge/vertex tie-breaks, cage leaves, stale-coords quirk.  Runs on the deferred
- *                  list, on grid-cell centres (seeding), or on every query; starts at the cell's
- *                  certified entry node (k_entry_cells).
+ *                  list (four lanes per query, k_exact_list4 / k_exact_overflow4), on grid-cell
+ *                  centres (seeding), on the data nodes (k_memo_fill) or on every query
+ *                  (k_exact_all); starts at the cell's certified entry node (k_entry_cells).
+ *   k_memo_list    queries of the deferred list that coincide with a data node are answered from the
+ *                  vertex memo, the others compacted for the replay.
+ *   k_seed_cells, k_pack_seeds, k_entry_cells, k_leaf_rcp, k_memo_fill
+ *                  the acceleration structure, filled on the device at init (gsi_layout.h).
  *   k_bin -> k_tile_walk -> k_unpermute
  *                  reorder pipeline for large incoherent query batches on triangulations beyond
  *                  the L2 (chunk-local counting sort by spatial tile, tile-major walk out of
- *                  TMA-staged shared memory, inverse permutation).
+ *                  TMA-staged shared memory, inverse permutation); opt-in.
+ *   k_deriv, k_build_locate, k_validate_slab, k_gen_uniform, k_checksum, k_compare
+ *                  gradients, the builder's batched point location, slab validation, bench helpers.
  *
  * This path is gather/latency bound: no tensor cores, no FMA contraction (gsi_core.h).
  * Measured bounds and the experiments that did not pay off are in DESIGN.md section 4.
