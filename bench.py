@@ -684,7 +684,12 @@ def main_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "traffic_source": traffic_src, "ncu": ncu_counters,
+                         "traffic_source": traffic_src,
+                         # the same launch on its REAL DRAM bytes (ncu) instead of the algorithmic ones: how close
+                         # the kernel is to the HBM wall on the traffic it actually causes
+                         "traffic_GBps": (traffic / locate_s / 1e9) if (traffic and locate_s > 0) else None,
+                         "traffic_frac_of_peak": (traffic / locate_s / 1e9 / peak) if (traffic and locate_s > 0) else None,
+                         "ncu": ncu_counters,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel_ms_per_launch": 1e3 * locate_s, "exact_replay_ms_per_step": 1e3 * exact_s},
             "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),

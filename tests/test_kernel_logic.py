@@ -87,6 +87,29 @@ def test_logic_walk_cap_and_nonfinite(golden):
     hs.close()
 
 
+@pytest.mark.parametrize("kind,n", [("uniform", 20000), ("clustered", 20000), ("uniform", 300)])
+def test_compact_seed_table_has_no_escapes_and_coarse_blocks(kind, n):
+    """slab v6+: at most 32 x 32 seed blocks (the base table fits 4 KB of shared memory), the grid of a
+    large triangulation is a multiple of 8 blocks per side, and every cell has a 16-bit seed (strays take a
+    neighbour's in-window seed): the walk never needs the int32 table.  The seed is only the start of the
+    walk, so the results stay those of the exact replay."""
+    xa, ya = synth.uniform_nodes(n) if kind == "uniform" else synth.clustered_nodes(n)
+    za = synth.values(n, 1)
+    hs = HostSim(xa, ya, za, g.DEFAULT, g.shuffle_mt19937(synth.SEED_SHUFFLE, n))
+    G, shift, escapes = hs.seed_table()
+    blocks = (G + (1 << shift) - 1) >> shift
+    assert shift >= 3 and blocks <= 32
+    if G >= 256:
+        assert G % (8 << shift) == 0
+    assert escapes == 0
+    xq, yq = synth.uniform_queries(20000)
+    l0, v0, st = hs.eval(xq, yq, 0)
+    l1, v1, _ = hs.eval(xq, yq, 1)
+    assert np.array_equal(l0, l1) and refimpl.same_bits(v0, v1)
+    assert st["steps"] / max(1, len(xq) - st["deferred"]) < (1.6 if kind == "uniform" else 4.0)
+    hs.close()
+
+
 @pytest.mark.parametrize("kind", ["collinear", "grid10"])
 def test_logic_degenerate_inputs_vs_port(kind):
     """collinear / cocircular nodes (gridded_test of the example) give near-singular and
