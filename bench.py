@@ -609,6 +609,9 @@ def main_ours(args):
         px, py = g.generate_uniform_host(synth.SEED_QUERIES, rank * Q, Qp, 0.0, 1.0, 0.0, 1.0)   # numpy = malloc'd
         pz = np.empty((F, Qp), dtype=np.float64)
         pl = np.empty(Qp, dtype=np.int32)
+        # several ranks share the host cores: keep the copy threads of all ranks within them
+        copy_threads = max(2, min(16, (3 * (os.cpu_count() or 16)) // (4 * world)))
+        w.set_param("copy_threads", copy_threads)
         w.eval_e(px, py, out_z=pz, out_leaf=pl)                 # warm-up (allocates the pinned staging)
         barrier()
         t0 = time.perf_counter()
@@ -617,7 +620,7 @@ def main_ours(args):
         dt = dist_util.max_over_ranks(time.perf_counter() - t0, dev)
         e2e_pageable = {"value": world * Qp * 2 / dt, "unit": "queries/s", "queries_per_gpu_per_step": Qp,
                         "host_memory": "pageable (numpy / malloc), staged through the library's pinned buffers by "
-                                       "4 host threads", "h2d_bytes_per_step": Qp * 16, "d2h_bytes_per_step": Qp * (4 + 8 * F)}
+                                       f"{copy_threads} host threads", "h2d_bytes_per_step": Qp * 16, "d2h_bytes_per_step": Qp * (4 + 8 * F)}
         del px, py, pz, pl
     tree_1e6 = None
     if rank == 0 and world == 1 and not args.no_configs and n == 1_000_000:

@@ -254,6 +254,14 @@ private:
 
 } // namespace
 
+static int
+default_copy_threads()
+{
+  const unsigned hw = std::thread::hardware_concurrency();
+  const unsigned t = hw ? (3 * hw) / 4 : 4;
+  return (int) (t < 4 ? 4 : (t > 16 ? 16 : t));
+}
+
 struct gsl_scattered_cuda
 {
   size_t n_cap = 0;
@@ -291,7 +299,10 @@ struct gsl_scattered_cuda
   size_t chunk = (size_t) 0xfffffff0u;
   double list_fraction = 1.0 / 8;
   size_t host_chunk = (size_t) 1 << 22;
-  int copy_threads = 4; /* host threads moving pageable caller arrays to / from the pinned staging */
+  /* host threads moving pageable caller arrays to / from the pinned staging: three quarters of the host's
+     hardware threads, between 4 and 16 (measured on a 16-core box: 0.69 / 1.03 / 1.29 / 1.32e9 queries/s
+     end to end with 4 / 8 / 12 / 16 threads) */
+  int copy_threads = default_copy_threads();
   size_t pageable_min = (size_t) 1 << 18; /* smaller pageable batches go straight through cudaMemcpyAsync */
   std::vector<int> devs;
   std::vector<replica *> reps;

@@ -103,7 +103,7 @@ int gsl_scattered_cuda_set_devices(gsl_scattered_cuda *w, const int dev[], size_
  * leaves per Morton-prefix tile, default 1000; fixed at init/upload), "tile_ranges" (work items
  * per tile, 0 = derived from the launch size), "tile_threads" (threads of the tile kernel's CTA).
  * Host pipeline: "copy_threads" (host threads that move pageable caller arrays through pinned
- * staging, default 4), "pageable_min" (smaller pageable batches go straight to cudaMemcpyAsync).
+ * staging, default: three quarters of the host's hardware threads, 4 to 16), "pageable_min" (smaller pageable batches go straight to cudaMemcpyAsync).
  * Parameters are read when a call starts: change them between calls, not during one. */
 int gsl_scattered_cuda_set_param(gsl_scattered_cuda *w, const char *name, double value);
 
