@@ -59,29 +59,14 @@ gsi_ld_seed(const int32_t *p)
   asm volatile("ld.global.nc" GSI_GATHER_HINT ".s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-/* the 16-bit seed offset of a cell (walk kernels) */
+/* the 16-bit seed offset of a cell (walk kernels; L1::no_allocate on this load and on the query loads was
+   measured 20-35 % slower, profiles/r2u_carveout_and_pitch.txt section 4) */
 __device__ __forceinline__ unsigned
 gsi_ld_seed16(const uint16_t *p)
 {
-#if defined(GSI_L1_NOALLOC)
-  unsigned short v;
-  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
-  return v;
-#else
   return __ldg(p);
-#endif
 }
-#if defined(GSI_L1_NOALLOC)
-__device__ __forceinline__ double
-gsi_ld_query_noalloc(const double *p)
-{
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-#define GSI_LD_QUERY(p) gsi_ld_query_noalloc(p)
-#define GSI_ST_RESULT(p, v) (*(p) = (v))
-#elif defined(GSI_STREAM_HINTS)
+#if defined(GSI_STREAM_HINTS)
 #define GSI_LD_QUERY(p) __ldcs(p)
 #define GSI_ST_RESULT(p, v) __stcs((p), (v))
 #else

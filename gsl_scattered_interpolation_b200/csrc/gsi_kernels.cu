@@ -1499,9 +1499,6 @@ k_walkc(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
 #define GSI_WALKF_PITCH 112 /* 7 x 16 bytes of a record; 28 words: conflict-free 128-bit reads */
 #endif
 #define GSI_WALKF_RING 64
-#ifndef GSI_WALKF_STAGE
-#define GSI_WALKF_STAGE 0
-#endif
 #define GSI_WALKF_WARP_BYTES (32 * GSI_WALKF_PITCH + GSI_WALKF_RING * 24 + GSI_WALKF_RING + 64)
 #define GSI_WALKF_SBASE_BYTES (GSI_SEED_GB_MAX * GSI_SEED_GB_MAX * 4)
 #define GSI_WALKF_SMEM (GSI_WALKF_SBASE_BYTES + (GSI_WALK_THREADS / 32) * GSI_WALKF_WARP_BYTES)
@@ -1634,33 +1631,12 @@ k_walkf(const gsi_view V, const gsi_cell_map C, const SRC src, size_t nq, unsign
         {
           const unsigned qq = 4u * (unsigned) r + (lane >> 3);
           const int sl = __shfl_sync(FULL, my, (int) qq);
-#if GSI_WALKF_STAGE == 1
-          /* experiment: all eight pieces of the line are requested (the eighth lands in a scratch slot) */
-          if (sl >= 0)
-            {
-              const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
-              const unsigned d = (lane & 7u) != 7u ? stage + qq * GSI_WALKF_PITCH + (lane & 7u) * 16u
-                                                   : stage + GSI_WALKF_WARP_BYTES - 64u + (lane >> 3) * 16u;
-              asm volatile("cp.async." GSI_WALKC_CP ".shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-            }
-#elif GSI_WALKF_STAGE == 2
-          /* experiment: 128-bit loads through registers instead of cp.async */
-          if (sl >= 0 && (lane & 7u) != 7u)
-            {
-              const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
-              const unsigned d = stage + qq * GSI_WALKF_PITCH + (lane & 7u) * 16u;
-              unsigned long long a, b;
-              asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(g));
-              asm volatile("st.shared.v2.u64 [%0], {%1,%2};" ::"r"(d), "l"(a), "l"(b) : "memory");
-            }
-#else
           if (sl >= 0 && (lane & 7u) != 7u)
             {
               const char *g = V.leaf + (size_t) sl * 128u + (lane & 7u) * 16u;
               const unsigned d = stage + qq * GSI_WALKF_PITCH + (lane & 7u) * 16u;
               asm volatile("cp.async." GSI_WALKC_CP ".shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
             }
-#endif
         }
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
